@@ -1,0 +1,35 @@
+"""Comparison rules of the reference's own tests, restated.
+
+* engine_close : abs tol 1e-2                      (/root/reference/src/test/Testing.cu:33-76)
+* smpc_close   : abs 0.1, or 0.1 % relative when |value| > 100
+                 (/root/reference/src/test/TestSmpcController.cu:28-47)
+"""
+import numpy as np
+
+
+def engine_close(got, want, tol=1e-2):
+    got = np.asarray(got, dtype=np.float64).reshape(-1)
+    want = np.asarray(want, dtype=np.float64).reshape(-1)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    err = np.abs(got - want)
+    bad = np.nonzero(~(err < tol))[0]
+    assert bad.size == 0, f"{bad.size} mismatches, first idx {bad[:5]} got {got[bad[:5]]} want {want[bad[:5]]}"
+    return float(err.max()) if err.size else 0.0
+
+
+def smpc_close(got, want):
+    got = np.asarray(got, dtype=np.float64).reshape(-1)
+    want = np.asarray(want, dtype=np.float64).reshape(-1)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    diff = got - want
+    big = np.abs(got) > 1e2
+    measure = np.where(big, diff / np.where(big, got, 1.0) * 100.0, diff)
+    bad = np.nonzero(~(np.abs(measure) < 1e-1))[0]
+    assert bad.size == 0, f"{bad.size} mismatches, first idx {bad[:5]} got {got[bad[:5]]} want {want[bad[:5]]}"
+    return float(np.abs(measure).max()) if measure.size else 0.0
+
+
+def rel_err(got, want):
+    got = np.asarray(got, dtype=np.float64).reshape(-1)
+    want = np.asarray(want, dtype=np.float64).reshape(-1)
+    return float(np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30))
