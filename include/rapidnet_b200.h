@@ -1,0 +1,251 @@
+/*
+ * rapidnet_b200.h -- C ABI of the B200-native APG stochastic-MPC path.
+ *
+ * The reference (GPUEngineering/RapidNet) has no FFI: its operator surface is the C++
+ * class API of one binary.  This header is the boundary underneath that surface -- what
+ * a maintainer of the reference would bind Engine / SmpcController to (see
+ * INTEGRATION.md).  Every entry point names the reference interface it replaces.
+ *
+ * Conventions: extern "C", plain pointers and sizes, int status (0 = ok; message via
+ * rn_last_error), opaque handle, caller-owned HOST buffers in, library-owned DEVICE
+ * buffers inside, one CUDA stream per handle, no hidden globals.  All matrices are flat
+ * column-major fp32, all per-node vectors node-major, exactly as the reference lays them
+ * out.  Tree node ids in rn_tree are the JSON's 1-based ids.
+ *
+ * There is no CPU fallback: every call that computes needs a CUDA device and fails with
+ * RN_ERR_CUDA otherwise.
+ */
+#ifndef RAPIDNET_B200_H_
+#define RAPIDNET_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rn_handle rn_handle;
+typedef int rn_status;
+
+enum {
+    RN_OK = 0,
+    RN_ERR_INVALID = 1,   /* bad argument / inconsistent dimensions */
+    RN_ERR_CUDA = 2,      /* CUDA runtime / cuSOLVER failure (no device, launch error, ...) */
+    RN_ERR_STATE = 3,     /* call order violated (e.g. solve before factor step) */
+    RN_ERR_SINGULAR = 4,  /* p*Rbar not invertible (reference: Engine.cu:1334-1353 exits) */
+    RN_ERR_NOMEM = 5
+};
+
+/* DwnNetwork / ScenarioTree / SmpcConfiguration dimensions (DwnNetwork.cuh:67-90,
+ * ScenarioTree.cuh:64-100, SmpcConfiguration.cuh:60-80). */
+typedef struct rn_dims {
+    int nx, nu, nd, ne, nv;   /* tanks, controls, demands, mixing nodes, nv = nu - ne */
+    int N, K, nodes;          /* horizon, scenarios, tree nodes */
+    int n_nonleaf;            /* nNonLeafNodes */
+    int n_children_tot;       /* nChildrenTot */
+} rn_dims;
+
+/* ScenarioTree getters (ScenarioTree.cuh:100-154); arrays as they appear in the JSON. */
+typedef struct rn_tree {
+    const int *stages;                 /* [nodes]   0-based stage of each node            */
+    const int *nodes_per_stage;        /* [N+1]     trailing 0                             */
+    const int *nodes_per_stage_cumul;  /* [N+2]                                            */
+    const int *leaves;                 /* [K]       1-based                                */
+    const int *children;               /* [n_children_tot] 1-based                         */
+    const int *ancestor;               /* [nodes]   1-based parent id, root = 0            */
+    const int *n_children;             /* [n_nonleaf]                                      */
+    const int *n_children_cumul;       /* [nodes]                                          */
+    const float *prob;                 /* [nodes]   path probability                       */
+    const float *err_demand;           /* [nodes*nd]                                       */
+    const float *err_price;            /* [nodes*nu]                                       */
+} rn_tree;
+
+/* DwnNetwork getters (DwnNetwork.cuh:91-143). matA is never used by the reference. */
+typedef struct rn_network {
+    const float *B;      /* nx*nu */
+    const float *Gd;     /* nx*nd */
+    const float *E;      /* ne*nu */
+    const float *Ed;     /* ne*nd */
+    const float *xmin, *xmax, *xsafe;   /* nx */
+    const float *umin, *umax;           /* nu */
+    const float *alpha1;                /* nu  (costAlpha1) */
+} rn_network;
+
+/* SmpcConfiguration getters (SmpcConfiguration.cuh:81-181). */
+typedef struct rn_config {
+    const float *costW;     /* nu*nu                                        */
+    const float *precond;   /* N*(nu+2nx), per stage [u | x | xsafe]        */
+    float penalty_x;        /* getPenaltyState()                            */
+    float penalty_xs;       /* getPenaltySafety()                           */
+    float step_size;        /* getStepSize()                                */
+    float weight_economical;/* getWeightEconomical() (hard-coded 1)         */
+    int max_iterations;     /* getMaxIterations()                           */
+} rn_config;
+
+/* How the solve step walks the tree (all give the same iterates up to fp32 rounding). */
+typedef enum rn_sweep_mode {
+    RN_SWEEP_PER_STAGE = 0,  /* one launch per stage, batched GEMV over the stage's nodes: the
+                                literal shape of SmpcController::solveStep (:593-741)           */
+    RN_SWEEP_CHAIN = 1       /* default: node-parallel factor stream, then one CTA per scenario
+                                chain below the last branching stage, per-stage launches above  */
+} rn_sweep_mode;
+
+/* Which per-node factor matrices the stream kernel reads (DESIGN.md "formulations"). */
+typedef enum rn_factor_mode {
+    RN_FACTORS_FULL = 0,     /* Phi, Psi, D, F  (what solveStep reads; Tier-A bytes)            */
+    RN_FACTORS_DF = 1        /* D, F only; v = -1/2 Omega r (exact identity, half the bytes)    */
+} rn_factor_mode;
+
+/* Single APG sub-steps, for the golden-vector tests (TestSmpcController.cu:114-398 calls
+ * the protected methods of SmpcController one by one). */
+typedef enum rn_step_kind {
+    RN_STEP_EXTRAPOLATE = 0,   /* SmpcController::dualExtrapolationStep(lambda)  :535-557 */
+    RN_STEP_SOLVE = 1,         /* SmpcController::solveStep()                    :563-755 */
+    RN_STEP_PROX = 2,          /* SmpcController::proximalFunG()                 :759-835 */
+    RN_STEP_RESIDUAL = 3,      /* SmpcController::computeFixedPointResidual()    :839-850 */
+    RN_STEP_DUAL_UPDATE = 4    /* SmpcController::dualUpdate()                   :854-864 */
+} rn_step_kind;
+
+/* Device buffers in the reference's packed layouts (Engine.cuh:104-318 getters and the
+ * protected members of SmpcController.cuh:262-462 that TestSmpcController pokes). */
+typedef enum rn_buffer_id {
+    /* Engine constants */
+    RN_BUF_SYS_MAT_B = 0,      /* getSysMatB      nx*nu                    */
+    RN_BUF_SYS_MAT_L,          /* getSysMatL      nu*nv                    */
+    RN_BUF_SYS_MAT_LHAT,       /* getSysMatLhat   nu*nd                    */
+    RN_BUF_SYS_MAT_F,          /* getSysMatF      nodes*(2nx*nx) dense, materialised on request */
+    RN_BUF_SYS_MAT_G,          /* getSysMatG      nodes*(nu*nu)  dense, materialised on request */
+    RN_BUF_SYS_XMIN,           /* getSysXmin      nodes*nx  (preconditioned)                     */
+    RN_BUF_SYS_XMAX,
+    RN_BUF_SYS_XS,
+    RN_BUF_SYS_XS_UPPER,       /* getSysXsUpper   nodes*nx  0x7F7F7F7F                           */
+    RN_BUF_SYS_UMIN,
+    RN_BUF_SYS_UMAX,
+    RN_BUF_MAT_PHI,            /* getMatPhi       nodes*(nv*2nx)           */
+    RN_BUF_MAT_PSI,            /* getMatPsi       nodes*(nv*nu)            */
+    RN_BUF_MAT_THETA,          /* getMatTheta     fb*(nv*nx)               */
+    RN_BUF_MAT_OMEGA,          /* getMatOmega     fb*(nv*nv)               */
+    RN_BUF_MAT_D,              /* getMatD         nodes*(nv*2nx)           */
+    RN_BUF_MAT_F,              /* getMatF         nodes*(nv*nu)            */
+    RN_BUF_MAT_G,              /* getMatG         nv*nx (the reference keeps K identical copies) */
+    RN_BUF_MAT_SIGMA,          /* getMatSigma     nodes*nv                 */
+    RN_BUF_MAT_WV,             /* devMatWv        nu*nv                    */
+    RN_BUF_DIAG,               /* private: nodes*(2nx+nu) = diag(sysF)|diag(sysG) per node      */
+    /* per-solve affine terms */
+    RN_BUF_VEC_E,              /* getVecE         nodes*nx                 */
+    RN_BUF_VEC_UHAT,           /* getVecUhat      nodes*nu                 */
+    RN_BUF_VEC_ALPHA,          /* getPriceAlpha   nodes*nu                 */
+    RN_BUF_VEC_BETA,           /* getVecBeta      nodes*nv                 */
+    RN_BUF_VEC_CURRENT_STATE,  /* getVecCurrentState      nx               */
+    RN_BUF_VEC_PREV_CONTROL,   /* getVecPreviousControl   nu               */
+    RN_BUF_VEC_PREV_UHAT,      /* getVecPreviousUhat      nu               */
+    RN_BUF_VEC_PREV_DEMAND,    /* getVecPreviousDemand    nd               */
+    /* SmpcController state */
+    RN_BUF_VEC_X,              /* devVecX         nodes*nx                 */
+    RN_BUF_VEC_U,              /* devVecU         nodes*nu                 */
+    RN_BUF_VEC_V,              /* devVecV         nodes*nv                 */
+    RN_BUF_VEC_XI,             /* devVecXi        nodes*2nx   y_{k-1}      */
+    RN_BUF_VEC_PSI,            /* devVecPsi       nodes*nu                 */
+    RN_BUF_VEC_ACCEL_XI,       /* devVecAcceleratedXi    w                 */
+    RN_BUF_VEC_ACCEL_PSI,
+    RN_BUF_VEC_PRIMAL_XI,      /* devVecPrimalXi         Hx                */
+    RN_BUF_VEC_PRIMAL_PSI,
+    RN_BUF_VEC_DUAL_XI,        /* devVecDualXi           z                 */
+    RN_BUF_VEC_DUAL_PSI,
+    RN_BUF_VEC_UPDATE_XI,      /* devVecUpdateXi         y_k               */
+    RN_BUF_VEC_UPDATE_PSI,
+    RN_BUF_VEC_RESIDUAL_XI,    /* devVecFixedPointResidualXi               */
+    RN_BUF_VEC_RESIDUAL_PSI,
+    RN_BUF_CONTROL_ACTION,     /* devControlAction       nu                */
+    RN_BUF_STATE_UPDATE,       /* devStateUpdate         nx                */
+    RN_BUF_COUNT_
+} rn_buffer_id;
+
+typedef struct rn_info {
+    int device, sm_count;
+    int final_branch_node;      /* ScenarioTree::getFinalBranchNode()  */
+    int final_branch_stage;     /* ScenarioTree::getFinalBranchStage() */
+    int chain_first_stage;      /* first stage of the non-branching tail; N if the tree has none */
+    int num_omega;              /* distinct Omega/Theta matrices */
+    int sweep_mode, factor_mode;
+    long long kernel_launches;  /* kernels launched by this handle so far */
+    long long launches_per_iteration;
+    size_t device_bytes;        /* library-owned device memory */
+    size_t factor_bytes;        /* bytes of Phi,Psi,D,F */
+    double stream_bytes_per_iteration;  /* algorithmic bytes the stream kernel moves per APG iteration */
+    double apg_bytes_per_iteration;     /* SURVEY 8(d) Tier-A figure for this problem and factor mode   */
+    float last_distance_x, last_distance_xs;   /* prox distances d1, d2 of the last iteration */
+    float last_stream_ms;       /* rn_profile_stream result */
+} rn_info;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+
+/* Engine::Engine + SmpcController::SmpcController allocation (Engine.cu:126-380,
+ * SmpcController.cu:117-232): copies the host arrays, allocates every device buffer once. */
+rn_status rn_create(const rn_dims *dims, const rn_tree *tree, const rn_network *net,
+                    const rn_config *cfg, int device, rn_handle **out);
+/* Engine::~Engine / SmpcController::~SmpcController */
+rn_status rn_destroy(rn_handle *h);
+/* message of the last failing call on `h` (or of the last failing rn_create if h == NULL) */
+const char *rn_last_error(const rn_handle *h);
+/* run all work of this handle on an existing cudaStream_t (default: a stream the handle owns) */
+rn_status rn_set_stream(rn_handle *h, void *cuda_stream);
+rn_status rn_get_stream(rn_handle *h, void **cuda_stream);
+rn_status rn_sync(rn_handle *h);
+rn_status rn_set_modes(rn_handle *h, rn_sweep_mode sweep, rn_factor_mode factors);
+rn_status rn_get_info(rn_handle *h, rn_info *info);
+
+/* ---- Engine --------------------------------------------------------------------------------- */
+
+/* Optional: use this null-space basis L (nu*nv) and particular solution Lhat (nu*nd) instead of
+ * computing them (Engine::calculateMatLandMatLhat, Engine.cu:466-669, cuSOLVER Dgesvd).  Lets a
+ * test feed the basis the golden vectors were produced with. */
+rn_status rn_set_null_space(rn_handle *h, const float *L, const float *Lhat);
+/* Engine::factorStep() (Engine.cu:671-774) incl. initialiseSystemDevice (:382-463) */
+rn_status rn_factor_step(rn_handle *h);
+/* Engine::updateStateControl(currentX, prevU, prevDemand) (Engine.cu:1300-1316) */
+rn_status rn_update_state(rn_handle *h, const float *x, const float *u_prev, const float *d_prev);
+/* Engine::eliminateInputDistubanceCoupling(nominalDemand[N*nd], nominalPrices[N*nu]) (Engine.cu:1147-1298) */
+rn_status rn_eliminate_coupling(rn_handle *h, const float *d_hat, const float *alpha_hat);
+/* Engine::setDemandUncertaintyFlag / setPriceUncertaintyFlag (Engine.cu:1135-1145) */
+rn_status rn_set_uncertainty(rn_handle *h, int demand, int price);
+
+/* ---- SmpcController -------------------------------------------------------------------------- */
+
+/* SmpcController::initialiseAlgorithm (SmpcController.cu:420-450): zero all duals (cold start) */
+rn_status rn_apg_init(rn_handle *h);
+/* one protected step method (see rn_step_kind); lambda is used by RN_STEP_EXTRAPOLATE only */
+rn_status rn_step(rn_handle *h, rn_step_kind kind, float lambda);
+/* SmpcController::algorithmApg() (SmpcController.cu:1500-1525): cold start + `iterations` fused
+ * iterations.  Asynchronous on the handle's stream unless a host output is requested:
+ *   u0_host          nullable, nu floats   = devVecU[0:nu]
+ *   primal_infs_host nullable, iterations floats = vecPrimalInfs (updatePrimalInfeasibity :1480-1496) */
+rn_status rn_apg_solve(rn_handle *h, int iterations, float *u0_host, float *primal_infs_host);
+/* SmpcController::controlAction(real_t* u) (:1607-1625) when clamp == 0;
+ * SmpcController::controlAction(fstream&) control vector (:1633-1667) when clamp != 0 (u0 clamped with
+ * the node-0 preconditioned bounds).  Host buffers in, u0 (nu floats) out; blocking. */
+rn_status rn_control_action(rn_handle *h, const float *x, const float *u_prev, const float *d_prev,
+                            const float *d_hat, const float *alpha_hat, int iterations, int clamp,
+                            float *u0_host);
+/* plant update of SmpcController::moveForewardInTime (:1679-1717): x_next = x + B*u0_clamped
+ * (reference drops the disturbance term).  Outputs nx and nu host floats. */
+rn_status rn_move_forward(rn_handle *h, float *x_next_host, float *u_applied_host);
+
+/* ---- buffers ---------------------------------------------------------------------------------- */
+
+/* borrowed device pointer + size in bytes of a buffer in the reference's packed layout */
+rn_status rn_buffer(rn_handle *h, rn_buffer_id id, void **dev_ptr, size_t *bytes);
+/* blocking convenience copies (count in floats, from the start of the buffer) */
+rn_status rn_read_buffer(rn_handle *h, rn_buffer_id id, float *host, size_t count);
+rn_status rn_write_buffer(rn_handle *h, rn_buffer_id id, const float *host, size_t count);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+
+/* launch the factor-stream kernel `reps` times back to back on the handle's stream (state is left
+ * untouched: lambda = 0 makes the extrapolation the identity) and return the mean duration in ms */
+rn_status rn_profile_stream(rn_handle *h, int reps, float *mean_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAPIDNET_B200_H_ */

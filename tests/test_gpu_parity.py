@@ -1,0 +1,181 @@
+"""GPU: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerance (BASELINE.md section 5 / north_star): fp32 relative 1e-4, norm-wise ||a-b||/||b|| on every iterate
+(U, X, y, z, Hx) and on u0, at equal iteration counts 1, 10, 100 and 500."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from rapidnet_b200 import cabi
+from rapidnet_b200.datagen import named_problem
+from refcompare import rel_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+PAIRS = [("VEC_U", "U"), ("VEC_X", "X"), ("VEC_V", "V"), ("VEC_UPDATE_XI", "update_xi"), ("VEC_UPDATE_PSI", "update_psi"),
+         ("VEC_XI", "xi"), ("VEC_PSI", "psi"), ("VEC_DUAL_XI", "dual_xi"), ("VEC_DUAL_PSI", "dual_psi"),
+         ("VEC_PRIMAL_XI", "primal_xi"), ("VEC_PRIMAL_PSI", "primal_psi"), ("VEC_ACCEL_XI", "accel_xi"),
+         ("VEC_RESIDUAL_XI", "res_xi"), ("VEC_RESIDUAL_PSI", "res_psi")]
+
+
+def _setup(prob, sweep, factors, slot=0):
+    s = cabi.Solver(prob)
+    s.set_modes(sweep, factors)
+    s.factor_step()
+    s.update_state()
+    s.eliminate_coupling(prob.forecast.demand[slot], prob.forecast.prices[slot])
+    # the oracle runs in the same null-space basis as the GPU engine
+    o = Oracle(prob, L=s.read("SYS_MAT_L"), Lhat=s.read("SYS_MAT_LHAT"))
+    o.factor_step()
+    o.update_state()
+    o.eliminate(prob.forecast.demand[slot], prob.forecast.prices[slot])
+    return s, o
+
+
+def _compare_state(s, o, tag):
+    worst = 0.0
+    for gname, oname in PAIRS:
+        err = rel_err(s.read(gname), o.get(oname))
+        worst = max(worst, err)
+        assert err < RTOL, f"{tag}: {gname} rel err {err:.3e}"
+    return worst
+
+
+@pytest.fixture(scope="module")
+def toy_problem(toy):
+    return toy[0]
+
+
+@pytest.mark.parametrize("sweep", [cabi.SWEEP_CHAIN, cabi.SWEEP_PER_STAGE], ids=["chain", "per_stage"])
+@pytest.mark.parametrize("factors", [cabi.FACTORS_FULL, cabi.FACTORS_DF], ids=["full", "df"])
+def test_toy_iterates_match_oracle(toy_problem, sweep, factors):
+    s, o = _setup(toy_problem, sweep, factors, slot=1)
+    for name in ("MAT_PHI", "MAT_PSI", "MAT_D", "MAT_F", "MAT_OMEGA", "MAT_THETA", "VEC_BETA", "VEC_E", "VEC_UHAT"):
+        oname = {"MAT_PHI": "Phi", "MAT_PSI": "Psi", "MAT_D": "D", "MAT_F": "F", "MAT_OMEGA": "Omega",
+                 "MAT_THETA": "Theta", "VEC_BETA": "beta", "VEC_E": "e", "VEC_UHAT": "uhat"}[name]
+        assert rel_err(s.read(name), o.get(oname)) < 1e-5, name
+    for iters in (1, 10, 100, 500):
+        u0, infs = s.apg_solve(iters, want_infs=True)
+        oinfs = o.apg(iters)
+        _compare_state(s, o, f"toy it={iters}")
+        assert rel_err(u0, o.get("U")[: u0.size]) < RTOL
+        # vecPrimalInfs: signed value at the arg-max-abs (SmpcController.cu:1487-1495)
+        assert np.allclose(infs, oinfs, rtol=1e-3, atol=1e-2), (iters, infs[-3:], oinfs[-3:])
+    s.close(); o.close()
+
+
+@pytest.mark.parametrize("name", ["C1", "C1r6", "C1r30"])
+def test_barcelona_iterates_match_oracle(name):
+    prob = named_problem(name)
+    s, o = _setup(prob, cabi.SWEEP_CHAIN, cabi.FACTORS_FULL)
+    for gname, oname in (("MAT_PHI", "Phi"), ("MAT_PSI", "Psi"), ("MAT_D", "D"), ("MAT_F", "F"), ("VEC_BETA", "beta")):
+        assert rel_err(s.read(gname), o.get(oname)) < 1e-5, gname
+    for iters in (1, 10, 100, 500):
+        u0, _ = s.apg_solve(iters)
+        o.apg(iters)
+        worst = _compare_state(s, o, f"{name} it={iters}")
+        assert rel_err(u0, o.get("U")[: u0.size]) < RTOL
+        print(f"{name} it={iters}: worst rel err {worst:.2e}")
+    info = s.info()
+    print(f"{name}: d1={info.last_distance_x:.3e} d2={info.last_distance_xs:.3e} thresholds "
+          f"{prob.config.penalty_x / prob.config.step_size:.1e} {prob.config.penalty_xs / prob.config.step_size:.1e}")
+    s.close(); o.close()
+
+
+def test_modes_agree_on_barcelona():
+    """per-stage / chain sweeps and FULL / DF factor streams give the same iterates (fp32 rounding apart)."""
+    prob = named_problem("C1r6")
+    ref = None
+    for sweep in (cabi.SWEEP_CHAIN, cabi.SWEEP_PER_STAGE):
+        for factors in (cabi.FACTORS_FULL, cabi.FACTORS_DF):
+            s = cabi.Solver(prob)
+            s.set_modes(sweep, factors)
+            s.factor_step(); s.update_state(); s.eliminate_coupling(prob.forecast.demand[0], prob.forecast.prices[0])
+            s.apg_solve(200)
+            cur = {k: s.read(k) for k in ("VEC_U", "VEC_X", "VEC_UPDATE_XI", "VEC_UPDATE_PSI")}
+            if ref is None:
+                ref = cur
+            else:
+                for k in cur:
+                    assert rel_err(cur[k], ref[k]) < RTOL, (sweep, factors, k)
+            s.close()
+
+
+def test_control_action_matches_oracle_and_clamps():
+    prob = named_problem("C1")
+    c, fc = prob.config, prob.forecast
+    s, o = _setup(prob, cabi.SWEEP_CHAIN, cabi.FACTORS_FULL)
+    iters = 50
+    u0 = s.control_action(c.current_x, c.prev_u, c.prev_demand, fc.demand[0], fc.prices[0], iters)
+    o.apg(iters)
+    ou0 = o.get("U")[: u0.size]
+    assert rel_err(u0, ou0) < RTOL
+    # controlAction(fstream&): clamp with the node-0 preconditioned bounds (SmpcController.cu:1649)
+    u0c = s.control_action(c.current_x, c.prev_u, c.prev_demand, fc.demand[0], fc.prices[0], iters, clamp=True)
+    lo, hi = o.get("umin")[: u0.size], o.get("umax")[: u0.size]
+    assert np.allclose(u0c, np.clip(ou0, lo, hi), rtol=1e-4, atol=1e-2)
+    # moveForewardInTime: x+ = x + B u0_clamped (SmpcController.cu:1692-1698)
+    xn, ua = s.move_forward()
+    B = prob.network.B.reshape(prob.network.nu, prob.network.nx).T
+    assert np.allclose(ua, u0c)
+    assert rel_err(xn, c.current_x + B @ u0c) < 1e-5
+    s.close(); o.close()
+
+
+def test_cold_start_is_repeatable():
+    """Every solve zeroes the duals (no warm start, SmpcController.cu:420-450): two solves are bit-identical."""
+    prob = named_problem("C1")
+    s, _ = _setup(prob, cabi.SWEEP_CHAIN, cabi.FACTORS_FULL)
+    s.apg_solve(37); a = {k: s.read(k) for k in ("VEC_U", "VEC_UPDATE_XI", "VEC_XI")}
+    s.apg_solve(37); b = {k: s.read(k) for k in ("VEC_U", "VEC_UPDATE_XI", "VEC_XI")}
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    s.close()
+
+
+def test_distance_branch_matches_oracle(toy_problem):
+    """Force both prox distance branches (tiny penalties) so the quirk path of SURVEY A.4-1 is exercised."""
+    import copy
+    prob = copy.deepcopy(toy_problem)
+    prob.config.penalty_x = 1e-3
+    prob.config.penalty_xs = 1e-3
+    s, o = _setup(prob, cabi.SWEEP_CHAIN, cabi.FACTORS_FULL, slot=1)
+    for iters in (1, 5, 40):
+        s.apg_solve(iters); o.apg(iters)
+        _compare_state(s, o, f"branch it={iters}")
+    assert o.distance(0) > prob.config.penalty_x / prob.config.step_size
+    assert o.distance(1) > prob.config.penalty_xs / prob.config.step_size
+    s.close(); o.close()
+
+
+def test_full_size_properties_c2():
+    """BASELINE config[1] (K=90, 1927 nodes) at full size: properties that need no oracle run.
+    * linear dynamics: X obeys x_i = x_par + e_i + B u_i and Hx = diag(s) [x;x;u] exactly as stored
+    * prox output lies inside the preconditioned boxes
+    * residual / dual update identities on the stored buffers"""
+    prob = named_problem("C2", max_iter=60)
+    s = cabi.Solver(prob)
+    s.factor_step(); s.update_state(); s.eliminate_coupling(prob.forecast.demand[0], prob.forecast.prices[0])
+    s.apg_solve(60)
+    n, t = prob.network, prob.tree
+    nx, nu = n.nx, n.nu
+    X = s.read("VEC_X").reshape(-1, nx); U = s.read("VEC_U").reshape(-1, nu); e = s.read("VEC_E").reshape(-1, nx)
+    B = n.B.reshape(nu, nx).T
+    par = t.ancestor.astype(np.int64) - 1
+    xp = np.where(par[:, None] >= 0, X[np.maximum(par, 0)], prob.config.current_x[None, :])
+    assert rel_err(X, xp + e + U @ B.T) < 1e-5
+    dg = s.read("DIAG").reshape(-1, 2 * nx + nu)
+    hx = s.read("VEC_PRIMAL_XI").reshape(-1, 2 * nx); hu = s.read("VEC_PRIMAL_PSI").reshape(-1, nu)
+    assert rel_err(hx, np.concatenate([X, X], axis=1) * dg[:, : 2 * nx]) < 1e-6
+    assert rel_err(hu, U * dg[:, 2 * nx:]) < 1e-6
+    z = s.read("VEC_DUAL_XI").reshape(-1, 2 * nx); zu = s.read("VEC_DUAL_PSI").reshape(-1, nu)
+    assert np.all(z[:, :nx] >= s.read("SYS_XMIN").reshape(-1, nx)) and np.all(z[:, :nx] <= s.read("SYS_XMAX").reshape(-1, nx))
+    assert np.all(z[:, nx:] >= s.read("SYS_XS").reshape(-1, nx))
+    assert np.all(zu >= s.read("SYS_UMIN").reshape(-1, nu)) and np.all(zu <= s.read("SYS_UMAX").reshape(-1, nu))
+    res = s.read("VEC_RESIDUAL_XI").reshape(-1, 2 * nx)
+    assert np.array_equal(res, hx - z)
+    w = s.read("VEC_ACCEL_XI").reshape(-1, 2 * nx); y = s.read("VEC_UPDATE_XI").reshape(-1, 2 * nx)
+    assert np.allclose(y, w + np.float32(prob.config.step_size) * res, rtol=1e-6, atol=1e-6)
+    assert s.info().chain_first_stage == 3 and s.info().launches_per_iteration >= 4
+    s.close()
