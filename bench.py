@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- APG iterations/sec and ms per SMPC solve on the Barcelona DWN (BASELINE.json metric).
+
+A "step" is one SMPC solve: `--iters` (default 500 = the reference's maxIterations) APG iterations on one
+scenario tree (default workload C2: Barcelona-shaped DWN 63/114/88, N=24, tree [6,5,3] -> K=90 scenarios,
+1927 nodes, 359 MB of Engine factor matrices -> larger than the 126 MB L2, so nothing is cache-resident between
+iterations).  Synthetic data of the reference's shape (rapidnet_b200/datagen.py; the true Barcelona blobs are
+missing from the reference).
+
+  value : APG iterations/s, whole job (all ranks), duals cold-started on the device, inputs resident in HBM;
+          CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+  e2e   : the same metric through rn_control_action (the reference's controlAction(real_t*)): HOST buffers in
+          (state, previous control/demand, demand and price forecasts), affine-term refresh, the APG solve, u0 back
+          to the host -- H2D and D2H inside the timed region.
+  N > 1 : one process per GPU, each rank solves its own independent SMPC instance (same network and tree, its
+          own initial tank levels): closed-loop Monte-Carlo instances shard with no data-path collective ("weak").
+  --impl reference : the reference's own CUDA/cuBLAS build (oracle/_ref/ref_driver, compiled from
+          /root/reference/src in place) on the same workload through its controlAction(real_t*); if that binary is
+          missing, the CPU oracle port on the host cores.  Rank 0 only.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "apg_iterations_per_sec"
+UNIT = "iter/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for key in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+                if key in d:
+                    return float(d[key]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower() == "active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w": float(np.median(power)) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def rank_problem(workload, iters, rank):
+    """The workload's problem; rank r > 0 is another Monte-Carlo instance (its own initial tank levels)."""
+    from rapidnet_b200.datagen import named_problem
+    prob = named_problem(workload, max_iter=iters)
+    if rank > 0:
+        rng = np.random.default_rng(977 + rank)
+        c, n = prob.config, prob.network
+        c.current_x = (rng.uniform(0.3, 0.9, size=n.nx) * n.xmax).astype(np.float32)
+    return prob
+
+
+def cpu_baseline(prob, iters_sample, threads):
+    """The oracle port (oracle/rapidnet_oracle.c, OpenMP over nodes) on a bounded sample of the same workload."""
+    from oracle.oracle import Oracle
+    o = Oracle(prob, L=prob.config.L, Lhat=prob.config.Lhat, threads=threads)
+    o.factor_step(); o.update_state(); o.eliminate(prob.forecast.demand[0], prob.forecast.prices[0])
+    o.apg(2)                                   # warm the caches / thread pool
+    t0 = time.perf_counter(); o.apg(iters_sample); dt = time.perf_counter() - t0
+    o.close()
+    return iters_sample / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    prob = rank_problem(args.workload, args.iters, 0)
+    cfg = {"workload": describe(args.workload, prob), "iterations_per_solve": args.iters, "cold_cache": "factors > L2"}
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    have_gpu = shutil.which("nvidia-smi") is not None and subprocess.call(
+        ["nvidia-smi", "-L"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 0
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg}
+    if os.path.exists(ref_bin) and have_gpu and not args.cpu_reference:
+        from rapidnet_b200.problem import write_problem
+        tmp = tempfile.mkdtemp(prefix="rn_ref_")
+        cfg_path = write_problem(prob, tmp)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+        out = subprocess.run([ref_bin, cfg_path, "0", str(args.warmup), str(args.steps)], capture_output=True,
+                             text=True, env=env, timeout=3000)
+        shutil.rmtree(tmp, ignore_errors=True)
+        rec = [ln for ln in out.stdout.splitlines() if ln.startswith("REF ")]
+        if out.returncode != 0 or not rec:
+            line.update({"unavailable": f"ref_driver failed rc={out.returncode}: {(out.stderr or out.stdout)[-300:]}"})
+            print(json.dumps(line)); return
+        kv = dict(x.split("=") for x in rec[-1].split()[1:])
+        ms = float(kv["ms_per_solve"])
+        val = args.iters / (ms * 1e-3)
+        line.update({"value": val, "ms_per_step": ms,
+                     "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference",
+                                      "sample": "the reference's own CUDA/cuBLAS build (it has no CPU path): full "
+                                                f"controlAction, {args.iters} iterations, median of {args.steps} on 1 GPU, "
+                                                "one host thread driving cuBLAS"},
+                     "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "reference_build": "oracle/_ref/ref_driver (unmodified /root/reference/src, nvcc sm_100, cuBLAS)"})
+        print(json.dumps(line)); return
+    # CPU oracle port on all host cores, bounded sample
+    threads = os.cpu_count() or 1
+    sample = max(4, min(args.iters, args.cpu_sample_iters))
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        v, dt = cpu_baseline(prob, sample, threads)
+        vals.append(v)
+    val = float(np.median(vals))
+    line.update({"value": val, "ms_per_step": args.iters / val * 1e3,
+                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                  "sample": f"{sample} APG iterations of the same workload (oracle port, OpenMP)"},
+                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+
+
+def describe(workload, prob):
+    d = prob.dims
+    return (f"{workload}: Barcelona-shaped DWN nx={d['nx']} nu={d['nu']} nd={d['nd']} nv={d['nv']} N={d['N']}, "
+            f"K={d['K']} scenarios, {d['nodes']} nodes")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--iters", type=int, default=500, help="APG iterations per SMPC solve (reference: 500)")
+    ap.add_argument("--cpu-sample-iters", type=int, default=500)
+    ap.add_argument("--cpu-reference", action="store_true", help="--impl reference: force the CPU oracle port")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", default="chain", choices=["chain", "per_stage"])
+    ap.add_argument("--factors", default="full", choices=["full", "df"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rapidnet_b200 import cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- rapidnet_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    prob = rank_problem(args.workload, args.iters, rank)
+    c, fc = prob.config, prob.forecast
+    s = cabi.Solver(prob, device=local)
+    stream = torch.cuda.Stream()
+    s.set_stream(stream.cuda_stream)          # torch.cuda.Event sees the stream the kernels are launched on
+    s.set_modes(cabi.SWEEP_CHAIN if args.sweep == "chain" else cabi.SWEEP_PER_STAGE,
+                cabi.FACTORS_FULL if args.factors == "full" else cabi.FACTORS_DF)
+    s.factor_step()
+    s.update_state()
+    s.eliminate_coupling(fc.demand[0], fc.prices[0])
+    iters = args.iters
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            s.apg_solve(iters, want_u0=False)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = s.info().kernel_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            s.apg_solve(iters, want_u0=False)
+        e1.record(stream)
+        barrier()
+        ms_dev = e0.elapsed_time(e1)
+        launches = s.info().kernel_launches - l0
+
+        # end to end through the reference-facing call: host buffers in, u0 back on the host
+        host_in = [np.ascontiguousarray(a, dtype=np.float32) for a in
+                   (c.current_x, c.prev_u, c.prev_demand, fc.demand[0], fc.prices[0])]
+        u0 = np.zeros(prob.network.nu, dtype=np.float32)
+        for _ in range(2):
+            s.control_action(*host_in, iters, out=u0)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            s.control_action(*host_in, iters, out=u0)
+        f1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max(f0.elapsed_time(f1), wall_ms)
+        clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    value = world * args.steps * iters / (ms_dev * 1e-3)
+    e2e_value = world * args.steps * iters / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        info = s.info()
+        prof = s.profile_kernels(min(iters, 100))
+        peak, peak_src = measured_peaks()
+        stream_bytes = info.stream_bytes_per_iteration
+        achieved = stream_bytes / (prof["stream"] * 1e-3) / 1e9 if prof["stream"] > 0 else 0.0
+        total_prof = sum(prof.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": describe(args.workload, prob), "iterations_per_solve": iters,
+                       "instances": world, "parallelism": f"{world} independent SMPC instance(s), one per GPU",
+                       "sweep": args.sweep, "factors": args.factors,
+                       "cold_cache": f"factor matrices {info.factor_bytes / 1e6:.0f} MB > L2 (126 MB): inputs larger than L2"},
+            "ms_per_solve": ms_dev / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_solve": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(sum(a.nbytes for a in host_in)), "d2h_bytes_per_step": int(u0.nbytes),
+                    "api": "rn_control_action (SmpcController::controlAction(real_t*))"},
+            "gpu_launches": int(launches),
+            "launches_per_iteration": int(info.launches_per_iteration),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_stream", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": stream_bytes, "launch_ms": prof["stream"],
+                         "share_of_iteration": prof["stream"] / total_prof if total_prof > 0 else None,
+                         "iteration_ms_by_kernel": prof,
+                         "whole_iteration": {"bytes": info.apg_bytes_per_iteration,
+                                             "achieved": info.apg_bytes_per_iteration / (ms_dev / args.steps / iters * 1e-3) / 1e9,
+                                             "frac": info.apg_bytes_per_iteration / (ms_dev / args.steps / iters * 1e-3) / 1e9 / peak}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = max(4, min(iters, args.cpu_sample_iters))
+            v, dt = cpu_baseline(prob, sample, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{sample} APG iterations of the same workload ({dt:.1f} s, oracle port, OpenMP)"}
+        print(json.dumps(line), flush=True)
+    s.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -245,6 +245,19 @@ rn_status rn_write_buffer(rn_handle *h, rn_buffer_id id, const float *host, size
  * untouched: lambda = 0 makes the extrapolation the identity) and return the mean duration in ms */
 rn_status rn_profile_stream(rn_handle *h, int reps, float *mean_ms);
 
+/* kernel classes of one APG iteration, for rn_profile_kernels */
+typedef enum rn_prof_class {
+    RN_PROF_STREAM = 0,     /* factor-matrix stream (+ fused dual extrapolation)          */
+    RN_PROF_BACKWARD = 1,   /* backward tree sweep                                        */
+    RN_PROF_FORWARD = 2,    /* forward tree sweep + Hx + box projections                  */
+    RN_PROF_FINALIZE = 3,   /* distance branch, residual, dual update, infeasibility log  */
+    RN_PROF_COUNT_ = 4
+} rn_prof_class;
+/* one cold-started solve of `iterations` iterations launched kernel by kernel with CUDA events (on the
+ * launching stream) around each kernel class; ms_out[RN_PROF_COUNT_] = mean ms per iteration per class.
+ * Leaves the same state behind as rn_apg_solve(iterations). */
+rn_status rn_profile_kernels(rn_handle *h, int iterations, float *ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,7 @@ EXPORTS = [
     "rn_create", "rn_destroy", "rn_last_error", "rn_set_stream", "rn_get_stream", "rn_sync", "rn_set_modes",
     "rn_get_info", "rn_set_null_space", "rn_factor_step", "rn_update_state", "rn_eliminate_coupling",
     "rn_set_uncertainty", "rn_apg_init", "rn_step", "rn_apg_solve", "rn_control_action", "rn_move_forward",
-    "rn_buffer", "rn_read_buffer", "rn_write_buffer", "rn_profile_stream",
+    "rn_buffer", "rn_read_buffer", "rn_write_buffer", "rn_profile_stream", "rn_profile_kernels",
 ]
 
 
@@ -109,6 +109,7 @@ def load():
     lib.rn_read_buffer.argtypes = [H, C.c_int, FP, C.c_size_t]
     lib.rn_write_buffer.argtypes = [H, C.c_int, FP, C.c_size_t]
     lib.rn_profile_stream.argtypes = [H, C.c_int, FP]
+    lib.rn_profile_kernels.argtypes = [H, C.c_int, FP]
     for name in EXPORTS:
         if name != "rn_last_error":
             getattr(lib, name).restype = C.c_int
@@ -265,3 +266,11 @@ class Solver:
         ms = C.c_float()
         self._check(load().rn_profile_stream(self.h, int(reps), C.byref(ms)), "rn_profile_stream")
         return float(ms.value)
+
+    PROF_CLASSES = ("stream", "backward", "forward", "finalize")
+
+    def profile_kernels(self, iterations: int = 50) -> dict:
+        """mean ms per APG iteration of each kernel class (CUDA events on the launching stream)"""
+        out = np.zeros(len(self.PROF_CLASSES), dtype=np.float32)
+        self._check(load().rn_profile_kernels(self.h, int(iterations), _fp(out)), "rn_profile_kernels")
+        return dict(zip(self.PROF_CLASSES, (float(v) for v in out)))

@@ -767,7 +767,7 @@ static rn_status launch_stream(Handle *h, cudaStream_t st, bool extrapolate, boo
 }
 
 // the tree sweeps of solveStep; returns the number of kernels launched and the number of distance slots written
-static rn_status launch_sweeps(Handle *h, cudaStream_t st, bool fuse_prox, int *n_launch, int *n_slots) {
+static rn_status launch_sweeps(Handle *h, cudaStream_t st, bool fuse_prox, int *n_launch, int *n_slots, cudaEvent_t mid = nullptr) {
     const rn_dims &d = h->d;
     const bool chains = h->sweep_mode == RN_SWEEP_CHAIN && chain_fits(h);
     const int cs = chains ? h->chain_stage : d.N;   // stages [0, cs) go stage by stage, [cs, N) as chains
@@ -783,6 +783,7 @@ static rn_status launch_sweeps(Handle *h, cudaStream_t st, bool fuse_prox, int *
         k_bwd_stage<<<h->h_nps[s], kStageThreads, bwd_stage_smem(h), st>>>(S, h->h_cum[s]);
         launches++;
     }
+    if (mid) RN_CUDA(h, cudaEventRecord(mid, st));
     for (int s = 0; s < cs; s++) {
         const int branching = s > 0 && (h->h_nps[s] - h->h_nps[s - 1]) > 0;
         k_fwd_stage<<<h->h_nps[s], kStageThreads, fwd_stage_smem(h), st>>>(S, h->h_cum[s], branching, h->h_cum[s]);
@@ -850,17 +851,46 @@ static rn_status ensure_lambda(Handle *h, int iterations) {
 }
 
 // enqueue the kernels of ONE fused iteration on `st`
-static rn_status enqueue_iteration(Handle *h, cudaStream_t st, long long *count) {
+static rn_status enqueue_iteration(Handle *h, cudaStream_t st, long long *count, cudaEvent_t *ev = nullptr) {
     int nl = 0, slots = 0;
+    if (ev) RN_CUDA(h, cudaEventRecord(ev[0], st));
     RN_CHECK(launch_stream(h, st, true, false, h->yA_xi, h->yA_psi, h->yB_xi, h->yB_psi));
-    RN_CHECK(launch_sweeps(h, st, true, &nl, &slots));
+    if (ev) RN_CUDA(h, cudaEventRecord(ev[1], st));
+    RN_CHECK(launch_sweeps(h, st, true, &nl, &slots, ev ? ev[2] : nullptr));
+    if (ev) RN_CUDA(h, cudaEventRecord(ev[3], st));
     FinalArgs F = make_final_args(h);
     F.yA_xi = h->yA_xi; F.yA_psi = h->yA_psi; F.yB_xi = h->yB_xi; F.yB_psi = h->yB_psi;
     F.n_slots = slots;
     F.do_branch = 1; F.do_residual = 1; F.do_update = 1; F.parity_swap = 1; F.log_inf = 1;
     k_finalize<<<finalize_grid(h), kEwThreads, 0, st>>>(F);
     RN_CUDA(h, cudaGetLastError());
+    if (ev) RN_CUDA(h, cudaEventRecord(ev[4], st));
     *count = 1 + nl + 1;
+    return RN_OK;
+}
+
+// one cold-started solve of `iterations` iterations, launched kernel by kernel (no graph) with CUDA events on the
+// launching stream around each kernel class; ms_out[c] = mean duration per iteration of class c (rn_prof_class)
+rn_status profile_kernels(Handle *h, int iterations, float *ms_out) {
+    RN_CHECK(ensure_lambda(h, iterations));
+    RN_CHECK(apg_init(h));
+    std::vector<cudaEvent_t> ev((size_t)iterations * 5);
+    for (auto &e : ev) RN_CUDA(h, cudaEventCreate(&e));
+    long long per_iter = 0;
+    for (int k = 0; k < iterations; k++) RN_CHECK(enqueue_iteration(h, h->stream, &per_iter, &ev[(size_t)k * 5]));
+    RN_CUDA(h, cudaStreamSynchronize(h->stream));
+    double acc[RN_PROF_COUNT_] = {0, 0, 0, 0};
+    for (int k = 0; k < iterations; k++)
+        for (int c = 0; c < 4; c++) {
+            float ms = 0.f;
+            RN_CUDA(h, cudaEventElapsedTime(&ms, ev[(size_t)k * 5 + c], ev[(size_t)k * 5 + c + 1]));
+            acc[c] += ms;
+        }
+    for (auto &e : ev) cudaEventDestroy(e);
+    for (int c = 0; c < RN_PROF_COUNT_; c++) ms_out[c] = (float)(acc[c] / iterations);
+    h->launches += per_iter * iterations;
+    h->launches_per_iter = per_iter;
+    if (iterations & 1) { std::swap(h->upd_xi, h->xi); std::swap(h->upd_psi, h->psi); }
     return RN_OK;
 }
 

@@ -466,4 +466,12 @@ rn_status rn_profile_stream(rn_handle *hh, int reps, float *mean_ms) {
     return rn::profile_stream(h, reps, mean_ms);
 }
 
+rn_status rn_profile_kernels(rn_handle *hh, int iterations, float *ms_out) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || iterations <= 0 || !ms_out) return RN_ERR_INVALID;
+    if (!h->factored || !h->eliminated) return rn::fail(h, RN_ERR_STATE, "rn_profile_kernels before factor step / eliminate");
+    RN_CUDA(h, cudaSetDevice(h->device));
+    return rn::profile_kernels(h, iterations, ms_out);
+}
+
 }  // extern "C"

@@ -164,6 +164,7 @@ rn_status apg_step(Handle *h, rn_step_kind kind, float lambda);
 rn_status apg_enqueue(Handle *h, int iterations);
 rn_status apg_release_graph(Handle *h);
 rn_status profile_stream(Handle *h, int reps, float *mean_ms);
+rn_status profile_kernels(Handle *h, int iterations, float *ms_out);
 rn_status clamp_control(Handle *h);
 rn_status move_forward(Handle *h);
 void fill_lambda_table(std::vector<float> &tab, int iters);
