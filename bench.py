@@ -188,7 +188,7 @@ def main():
     ap.add_argument("--cpu-sample-iters", type=int, default=500)
     ap.add_argument("--cpu-reference", action="store_true", help="--impl reference: force the CPU oracle port")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep", default="chain", choices=["chain", "per_stage"])
+    ap.add_argument("--sweep", default="persistent", choices=["persistent", "chain", "per_stage"])
     ap.add_argument("--factors", default="full", choices=["full", "df"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -219,7 +219,7 @@ def main():
     s = cabi.Solver(prob, device=local)
     stream = torch.cuda.Stream()
     s.set_stream(stream.cuda_stream)          # torch.cuda.Event sees the stream the kernels are launched on
-    s.set_modes(cabi.SWEEP_CHAIN if args.sweep == "chain" else cabi.SWEEP_PER_STAGE,
+    s.set_modes({"persistent": cabi.SWEEP_PERSISTENT, "chain": cabi.SWEEP_CHAIN, "per_stage": cabi.SWEEP_PER_STAGE}[args.sweep],
                 cabi.FACTORS_FULL if args.factors == "full" else cabi.FACTORS_DF)
     s.factor_step()
     s.update_state()

@@ -86,8 +86,11 @@ typedef struct rn_config {
 typedef enum rn_sweep_mode {
     RN_SWEEP_PER_STAGE = 0,  /* one launch per stage, batched GEMV over the stage's nodes: the
                                 literal shape of SmpcController::solveStep (:593-741)           */
-    RN_SWEEP_CHAIN = 1       /* default: node-parallel factor stream, then one CTA per scenario
-                                chain below the last branching stage, per-stage launches above  */
+    RN_SWEEP_CHAIN = 1,      /* node-parallel factor stream, then one CTA per scenario chain below
+                                the last branching stage, per-stage launches above (CUDA graph)   */
+    RN_SWEEP_PERSISTENT = 2  /* default: the whole APG loop in ONE persistent cooperative kernel, grid
+                                barrier per crown stage, chains as scans + GEMMs across their stages;
+                                falls back to RN_SWEEP_CHAIN when the problem does not fit it       */
 } rn_sweep_mode;
 
 /* Which per-node factor matrices the stream kernel reads (DESIGN.md "formulations"). */

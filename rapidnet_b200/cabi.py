@@ -20,7 +20,7 @@ RN_OK = 0
 STATUS_NAMES = {0: "RN_OK", 1: "RN_ERR_INVALID", 2: "RN_ERR_CUDA", 3: "RN_ERR_STATE", 4: "RN_ERR_SINGULAR",
                 5: "RN_ERR_NOMEM"}
 
-SWEEP_PER_STAGE, SWEEP_CHAIN = 0, 1
+SWEEP_PER_STAGE, SWEEP_CHAIN, SWEEP_PERSISTENT = 0, 1, 2
 FACTORS_FULL, FACTORS_DF = 0, 1
 STEP_EXTRAPOLATE, STEP_SOLVE, STEP_PROX, STEP_RESIDUAL, STEP_DUAL_UPDATE = range(5)
 
@@ -186,7 +186,7 @@ class Solver:
     def sync(self):
         self._check(load().rn_sync(self.h), "rn_sync")
 
-    def set_modes(self, sweep=SWEEP_CHAIN, factors=FACTORS_FULL):
+    def set_modes(self, sweep=SWEEP_PERSISTENT, factors=FACTORS_FULL):
         self._check(load().rn_set_modes(self.h, sweep, factors), "rn_set_modes")
 
     def info(self) -> RnInfo:

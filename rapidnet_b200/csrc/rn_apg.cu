@@ -24,39 +24,9 @@
 #include <cstdlib>
 
 #include "rn_internal.h"
+#include "rn_device.cuh"
 
 namespace rn {
-
-// ============================================================================================
-// PTX helpers (mbarrier + 1-D bulk TMA)
-// ============================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// global -> shared bulk copy (TMA, no tensor map): 16-B aligned src/dst, size multiple of 16; SASS: UBLKCP
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 // ============================================================================================
 // k_stream
@@ -255,10 +225,6 @@ __device__ __forceinline__ void block_gemv(const float *__restrict__ A, int lda,
         }
         __syncthreads();
     }
-}
-
-__device__ __forceinline__ float clampf(float v, float lo, float hi) {   // projectionBox (Utilities.cu:237-254)
-    if (v < lo) return lo; else if (v > hi) return hi; return v;
 }
 
 struct SweepArgs {
@@ -555,19 +521,6 @@ struct FinalArgs {
     float step, inv_step, pen_x, pen_xs;
 };
 
-struct Cand { float a; float v; int idx; };
-__device__ __forceinline__ void cand_merge(Cand &x, const Cand &y) {   // Isamax: largest |.|, smallest index on ties
-    if (y.a > x.a || (y.a == x.a && y.idx < x.idx)) x = y;
-}
-__device__ __forceinline__ Cand cand_warp(Cand c) {
-    for (int o = 16; o > 0; o >>= 1) {
-        Cand y;
-        y.a = __shfl_xor_sync(0xffffffffu, c.a, o); y.v = __shfl_xor_sync(0xffffffffu, c.v, o); y.idx = __shfl_xor_sync(0xffffffffu, c.idx, o);
-        cand_merge(c, y);
-    }
-    return c;
-}
-
 // distance branch of proximalFunG (:792-797, :810-815; quirk SURVEY A.4-1), computeFixedPointResidual (:839-850),
 // dualUpdate (:854-864) and updatePrimalInfeasibity (:1480-1496) in one pass over the duals.
 __global__ void __launch_bounds__(kEwThreads) k_finalize(const __grid_constant__ FinalArgs F) {
@@ -710,6 +663,8 @@ double apg_bytes_per_iteration(const Handle *h) {
     return 4.0 * (d.nodes * (mats + ny + V) + (double)h->n_omega * (nv * nv + nv * nx) + nv * nx + nu * nv + nx * nu);
 }
 
+bool use_persistent(const Handle *h);
+static rn_status enqueue_persistent(Handle *h, int iterations);
 static bool chain_fits(const Handle *h) {
     return h->chain_stage < h->d.N && bwd_chain_smem(h) <= 200 * 1024 && fwd_chain_smem(h) <= 200 * 1024 &&
            h->d.nv <= kChainThreads && h->d.nu <= kChainThreads && h->d.nx <= kChainThreads;
@@ -769,7 +724,7 @@ static rn_status launch_stream(Handle *h, cudaStream_t st, bool extrapolate, boo
 // the tree sweeps of solveStep; returns the number of kernels launched and the number of distance slots written
 static rn_status launch_sweeps(Handle *h, cudaStream_t st, bool fuse_prox, int *n_launch, int *n_slots, cudaEvent_t mid = nullptr) {
     const rn_dims &d = h->d;
-    const bool chains = h->sweep_mode == RN_SWEEP_CHAIN && chain_fits(h);
+    const bool chains = h->sweep_mode != RN_SWEEP_PER_STAGE && chain_fits(h);
     const int cs = chains ? h->chain_stage : d.N;   // stages [0, cs) go stage by stage, [cs, N) as chains
     SweepArgs S = make_sweep_args(h, fuse_prox);
     int launches = 0;
@@ -829,6 +784,7 @@ rn_status apg_init(Handle *h) {
     RN_CUDA(h, cudaMemsetAsync(h->done_ctr, 0, sizeof(unsigned int), h->stream));
     // role pointers back to their home buffers
     h->upd_xi = h->yA_xi; h->upd_psi = h->yA_psi; h->xi = h->yB_xi; h->psi = h->yB_psi;
+    h->acc_xi = h->wA_xi; h->acc_psi = h->wA_psi;
     return RN_OK;
 }
 
@@ -874,6 +830,26 @@ static rn_status enqueue_iteration(Handle *h, cudaStream_t st, long long *count,
 rn_status profile_kernels(Handle *h, int iterations, float *ms_out) {
     RN_CHECK(ensure_lambda(h, iterations));
     RN_CHECK(apg_init(h));
+    if (use_persistent(h)) {
+        // phases of the persistent kernel, clocked by CTA 0 with %globaltimer at every grid barrier of the real run
+        cudaEvent_t e0, e1;
+        RN_CUDA(h, cudaEventCreate(&e0)); RN_CUDA(h, cudaEventCreate(&e1));
+        RN_CUDA(h, cudaEventRecord(e0, h->stream));
+        RN_CHECK(enqueue_persistent(h, iterations));
+        RN_CUDA(h, cudaEventRecord(e1, h->stream));
+        unsigned long long ns[4] = {0, 0, 0, 0};
+        RN_CUDA(h, cudaMemcpyAsync(ns, h->phase_ns, sizeof(ns), cudaMemcpyDeviceToHost, h->stream));
+        RN_CUDA(h, cudaStreamSynchronize(h->stream));
+        float total = 0.f;
+        RN_CUDA(h, cudaEventElapsedTime(&total, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        ms_out[RN_PROF_STREAM] = (float)(ns[0] * 1e-6 / iterations);
+        ms_out[RN_PROF_BACKWARD] = (float)(ns[1] * 1e-6 / iterations);
+        ms_out[RN_PROF_FORWARD] = (float)((ns[2] + ns[3]) * 1e-6 / iterations);
+        const double rest = total - (ns[0] + ns[1] + ns[2] + ns[3]) * 1e-6;
+        ms_out[RN_PROF_FINALIZE] = (float)((rest > 0 ? rest : 0) / iterations);   // launch + the one k_finalize
+        return RN_OK;
+    }
     std::vector<cudaEvent_t> ev((size_t)iterations * 5);
     for (auto &e : ev) RN_CUDA(h, cudaEventCreate(&e));
     long long per_iter = 0;
@@ -894,9 +870,34 @@ rn_status profile_kernels(Handle *h, int iterations, float *ms_out) {
     return RN_OK;
 }
 
+// the persistent cooperative kernel runs iterations 0..iters-1; the last iteration's finalisation (distance branch,
+// residual, dual update, infeasibility log) is one k_finalize launch
+static rn_status enqueue_persistent(Handle *h, int iterations) {
+    RN_CHECK(persistent_prepare(h));
+    RN_CUDA(h, cudaMemsetAsync(h->phase_ns, 0, 8 * sizeof(unsigned long long), h->stream));
+    if (iterations > 0) {
+        RN_CHECK(persistent_launch(h, h->stream, iterations));
+        const int last = (iterations - 1) & 1;
+        h->acc_xi = last ? h->wB_xi : h->wA_xi; h->acc_psi = last ? h->wB_psi : h->wA_psi;
+        FinalArgs F = make_final_args(h);
+        F.yA_xi = h->yA_xi; F.yA_psi = h->yA_psi; F.yB_xi = h->yB_xi; F.yB_psi = h->yB_psi;
+        F.n_slots = h->persist_grid;
+        F.do_branch = 1; F.do_residual = 1; F.do_update = 1; F.parity_swap = 1; F.log_inf = 1;
+        k_finalize<<<finalize_grid(h), kEwThreads, 0, h->stream>>>(F);
+        RN_CUDA(h, cudaGetLastError());
+        h->launches += 2;
+    }
+    h->launches_per_iter = 0;
+    if (iterations & 1) { std::swap(h->upd_xi, h->xi); std::swap(h->upd_psi, h->psi); }
+    return RN_OK;
+}
+
+bool use_persistent(const Handle *h) { return h->sweep_mode == RN_SWEEP_PERSISTENT && persistent_supported(h); }
+
 rn_status apg_enqueue(Handle *h, int iterations) {
     RN_CHECK(ensure_lambda(h, iterations));
     RN_CHECK(apg_init(h));
+    if (use_persistent(h)) return enqueue_persistent(h, iterations);
     static const bool no_graph = getenv("RN_NO_GRAPH") != nullptr;
     long long per_iter = 0;
     if (no_graph) {

@@ -90,15 +90,16 @@ static rn_status allocate(Handle *h) {
     RN_CHECK(dev_alloc(h, &h->beta, n * nv)); RN_CHECK(dev_alloc(h, &h->zeta, n * nu));
     RN_CHECK(dev_alloc(h, &h->X, n * nx)); RN_CHECK(dev_alloc(h, &h->U, n * nu)); RN_CHECK(dev_alloc(h, &h->V, n * nv));
     RN_CHECK(dev_alloc(h, &h->sigma, n * nv));
-    {   // slab: yA | yB | w | Hx | z  (xi part, psi part each), 256-B aligned pieces
+    {   // slab: yA | yB | wA | Hx | z | wB  (xi part, psi part each), 256-B aligned pieces
         const size_t cxi = (n * 2 * nx + 63) & ~size_t(63), cpsi = (n * nu + 63) & ~size_t(63);
-        const size_t total = 5 * (cxi + cpsi);
+        const size_t total = 6 * (cxi + cpsi);
         RN_CHECK(dev_alloc(h, &h->apg_slab, total));
         h->apg_slab_bytes = total * sizeof(float);
         float *p = h->apg_slab;
         h->yA_xi = p; p += cxi; h->yA_psi = p; p += cpsi; h->yB_xi = p; p += cxi; h->yB_psi = p; p += cpsi;
         h->acc_xi = p; p += cxi; h->acc_psi = p; p += cpsi; h->pri_xi = p; p += cxi; h->pri_psi = p; p += cpsi;
         h->dual_xi = p; p += cxi; h->dual_psi = p; p += cpsi;
+        h->wA_xi = h->acc_xi; h->wA_psi = h->acc_psi; h->wB_xi = p; p += cxi; h->wB_psi = p; p += cpsi;
         h->upd_xi = h->yA_xi; h->upd_psi = h->yA_psi; h->xi = h->yB_xi; h->psi = h->yB_psi;
     }
     RN_CHECK(dev_alloc(h, &h->res_xi, n * 2 * nx)); RN_CHECK(dev_alloc(h, &h->res_psi, n * nu));
@@ -106,7 +107,7 @@ static rn_status allocate(Handle *h) {
     RN_CHECK(dev_alloc(h, &h->control_action, nu)); RN_CHECK(dev_alloc(h, &h->state_update, nx));
     RN_CHECK(dev_alloc(h, &h->a, n * nv)); RN_CHECK(dev_alloc(h, &h->b, n * nv)); RN_CHECK(dev_alloc(h, &h->c, n * nx));
     RN_CHECK(dev_alloc(h, &h->q, n * nx)); RN_CHECK(dev_alloc(h, &h->r, n * nv));
-    h->dist_slots = d.nodes;
+    h->dist_slots = std::max(d.nodes, 1024);
     RN_CHECK(dev_alloc(h, &h->dist_part, 2 * (size_t)h->dist_slots));
     RN_CHECK(dev_alloc(h, &h->scal, 16));
     RN_CHECK(dev_alloc(h, &h->iter_dev, 4)); RN_CHECK(dev_alloc(h, &h->done_ctr, 8));
@@ -239,7 +240,7 @@ rn_status rn_sync(rn_handle *hh) {
 rn_status rn_set_modes(rn_handle *hh, rn_sweep_mode sweep, rn_factor_mode factors) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (!h) return RN_ERR_INVALID;
-    if ((sweep != RN_SWEEP_PER_STAGE && sweep != RN_SWEEP_CHAIN) || (factors != RN_FACTORS_FULL && factors != RN_FACTORS_DF))
+    if ((sweep != RN_SWEEP_PER_STAGE && sweep != RN_SWEEP_CHAIN && sweep != RN_SWEEP_PERSISTENT) || (factors != RN_FACTORS_FULL && factors != RN_FACTORS_DF))
         return rn::fail(h, RN_ERR_INVALID, "rn_set_modes: unknown mode");
     h->sweep_mode = sweep;
     h->factor_mode = factors;

@@ -47,7 +47,7 @@ struct Handle {
     int chain_stage = 0;             // first stage of the non-branching tail (N if none)
     bool demand_uncertainty = true, price_uncertainty = true;
     bool factored = false, state_set = false, eliminated = false;
-    int sweep_mode = RN_SWEEP_CHAIN, factor_mode = RN_FACTORS_FULL;
+    int sweep_mode = RN_SWEEP_PERSISTENT, factor_mode = RN_FACTORS_FULL;
 
     DevTree t;
     // network / config constants on the device
@@ -75,6 +75,7 @@ struct Handle {
     float *apg_slab = nullptr;
     size_t apg_slab_bytes = 0;
     float *yA_xi = nullptr, *yA_psi = nullptr, *yB_xi = nullptr, *yB_psi = nullptr;
+    float *wA_xi = nullptr, *wA_psi = nullptr, *wB_xi = nullptr, *wB_psi = nullptr;   // w double buffer (persistent kernel)
     int *cum_dev = nullptr;          // nodes_per_stage_cumul on the device
     // sweep scratch
     float *a = nullptr, *b = nullptr, *c = nullptr;   // hoisted per-node products: nodes*nv, nodes*nv, nodes*nx
@@ -93,6 +94,14 @@ struct Handle {
     int pinf_slots = 0;
     float *pinned = nullptr;         // pinned host staging
     size_t pinned_floats = 0;
+
+    // persistent cooperative kernel
+    float *part[4] = {nullptr, nullptr, nullptr, nullptr};   // D xi_w, F psi_w, Phi xi_w, Psi psi_w
+    float *LV = nullptr;
+    unsigned int *grid_bar = nullptr;
+    unsigned long long *phase_ns = nullptr;
+    bool persist_ready = false;
+    int persist_grid = 0;
 
     cudaGraphExec_t iter_graph = nullptr;
     int graph_sweep = -1, graph_factor = -1;
@@ -165,6 +174,9 @@ rn_status apg_enqueue(Handle *h, int iterations);
 rn_status apg_release_graph(Handle *h);
 rn_status profile_stream(Handle *h, int reps, float *mean_ms);
 rn_status profile_kernels(Handle *h, int iterations, float *ms_out);
+bool persistent_supported(const Handle *h);
+rn_status persistent_prepare(Handle *h);
+rn_status persistent_launch(Handle *h, cudaStream_t st, int iters);
 rn_status clamp_control(Handle *h);
 rn_status move_forward(Handle *h);
 void fill_lambda_table(std::vector<float> &tab, int iters);
