@@ -260,6 +260,9 @@ typedef enum rn_prof_class {
  * launching stream) around each kernel class; ms_out[RN_PROF_COUNT_] = mean ms per iteration per class.
  * Leaves the same state behind as rn_apg_solve(iterations). */
 rn_status rn_profile_kernels(rn_handle *h, int iterations, float *ms_out);
+/* fine-grained phase clock of the last rn_profile_kernels run in persistent mode: 32 accumulators (ns per
+ * iteration, CTA 0's %globaltimer); index meaning in DESIGN.md / rapidnet_b200/cabi.py PHASE_NAMES */
+rn_status rn_phase_times(rn_handle *h, double *ns_per_iteration /*[32]*/);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,7 @@ EXPORTS = [
     "rn_create", "rn_destroy", "rn_last_error", "rn_set_stream", "rn_get_stream", "rn_sync", "rn_set_modes",
     "rn_get_info", "rn_set_null_space", "rn_factor_step", "rn_update_state", "rn_eliminate_coupling",
     "rn_set_uncertainty", "rn_apg_init", "rn_step", "rn_apg_solve", "rn_control_action", "rn_move_forward",
-    "rn_buffer", "rn_read_buffer", "rn_write_buffer", "rn_profile_stream", "rn_profile_kernels",
+    "rn_buffer", "rn_read_buffer", "rn_write_buffer", "rn_profile_stream", "rn_profile_kernels", "rn_phase_times",
 ]
 
 
@@ -110,6 +110,7 @@ def load():
     lib.rn_write_buffer.argtypes = [H, C.c_int, FP, C.c_size_t]
     lib.rn_profile_stream.argtypes = [H, C.c_int, FP]
     lib.rn_profile_kernels.argtypes = [H, C.c_int, FP]
+    lib.rn_phase_times.argtypes = [H, C.POINTER(C.c_double)]
     for name in EXPORTS:
         if name != "rn_last_error":
             getattr(lib, name).restype = C.c_int
@@ -274,3 +275,16 @@ class Solver:
         out = np.zeros(len(self.PROF_CLASSES), dtype=np.float32)
         self._check(load().rn_profile_kernels(self.h, int(iterations), _fp(out)), "rn_profile_kernels")
         return dict(zip(self.PROF_CLASSES, (float(v) for v in out)))
+
+    PHASE_NAMES = {0: "S.stream", 1: "S.barrier", 2: "S.pinf", 3: "B.stage", 4: "B.qscan", 5: "B.gemm_Gq", 6: "B.rscan",
+                   7: "B.gemm_v", 8: "B.gemm_Lv", 9: "B.tail_end", 10: "B.barrier", 11: "B.crown", 12: "B.crown_barrier",
+                   13: "F.crown", 14: "F.crown_barrier", 15: "F.stage", 16: "F.uscan", 17: "F.gemm_Bu", 18: "F.xscan",
+                   19: "F.epilogue", 20: "F.tail_end", 21: "F.dist", 22: "F.barrier",
+                   23: "cyc.loader_total", 24: "cyc.gemv_wait_full", 25: "cyc.gemv_wait_w", 26: "cyc.gemv_wait_red", 27: "cyc.gemv_compute",
+                   28: "cyc.loader_wait_empty", 29: "cyc.loader_vec", 30: "cyc.ew_wait_red", 31: "cyc.ew_prologue"}
+
+    def phase_times(self) -> dict:
+        """ns per iteration of each phase of the persistent kernel in the last profile_kernels run (CTA 0's clock)"""
+        out = (C.c_double * 32)()
+        self._check(load().rn_phase_times(self.h, out), "rn_phase_times")
+        return {self.PHASE_NAMES.get(k, str(k)): out[k] for k in range(32) if out[k] > 0}

@@ -837,12 +837,18 @@ rn_status profile_kernels(Handle *h, int iterations, float *ms_out) {
         RN_CUDA(h, cudaEventRecord(e0, h->stream));
         RN_CHECK(enqueue_persistent(h, iterations));
         RN_CUDA(h, cudaEventRecord(e1, h->stream));
-        unsigned long long ns[4] = {0, 0, 0, 0};
-        RN_CUDA(h, cudaMemcpyAsync(ns, h->phase_ns, sizeof(ns), cudaMemcpyDeviceToHost, h->stream));
+        unsigned long long pn[32];
+        RN_CUDA(h, cudaMemcpyAsync(pn, h->phase_ns, sizeof(pn), cudaMemcpyDeviceToHost, h->stream));
         RN_CUDA(h, cudaStreamSynchronize(h->stream));
         float total = 0.f;
         RN_CUDA(h, cudaEventElapsedTime(&total, e0, e1));
         cudaEventDestroy(e0); cudaEventDestroy(e1);
+        // stream = fused element-wise pass + factor stream + its closing barrier; backward = chains + crown; forward = rest
+        unsigned long long ns[4] = {pn[0] + pn[1], 0, 0, 0};
+        for (int k = 2; k <= 12; k++) ns[1] += pn[k];
+        for (int k = 13; k <= 22; k++) ns[2] += pn[k];
+        memcpy(h->last_phase_ns, pn, sizeof(pn));
+        h->last_phase_iters = iterations;
         ms_out[RN_PROF_STREAM] = (float)(ns[0] * 1e-6 / iterations);
         ms_out[RN_PROF_BACKWARD] = (float)(ns[1] * 1e-6 / iterations);
         ms_out[RN_PROF_FORWARD] = (float)((ns[2] + ns[3]) * 1e-6 / iterations);
@@ -874,7 +880,7 @@ rn_status profile_kernels(Handle *h, int iterations, float *ms_out) {
 // residual, dual update, infeasibility log) is one k_finalize launch
 static rn_status enqueue_persistent(Handle *h, int iterations) {
     RN_CHECK(persistent_prepare(h));
-    RN_CUDA(h, cudaMemsetAsync(h->phase_ns, 0, 8 * sizeof(unsigned long long), h->stream));
+    RN_CUDA(h, cudaMemsetAsync(h->phase_ns, 0, 32 * sizeof(unsigned long long), h->stream));
     if (iterations > 0) {
         RN_CHECK(persistent_launch(h, h->stream, iterations));
         const int last = (iterations - 1) & 1;

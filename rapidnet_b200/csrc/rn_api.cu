@@ -475,4 +475,11 @@ rn_status rn_profile_kernels(rn_handle *hh, int iterations, float *ms_out) {
     return rn::profile_kernels(h, iterations, ms_out);
 }
 
+rn_status rn_phase_times(rn_handle *hh, double *out) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !out) return RN_ERR_INVALID;
+    for (int k = 0; k < 32; k++) out[k] = h->last_phase_iters > 0 ? (double)h->last_phase_ns[k] / h->last_phase_iters : 0.0;
+    return RN_OK;
+}
+
 }  // extern "C"

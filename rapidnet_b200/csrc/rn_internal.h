@@ -101,6 +101,8 @@ struct Handle {
     unsigned int *grid_bar = nullptr;
     unsigned long long *phase_ns = nullptr;
     bool persist_ready = false;
+    unsigned long long last_phase_ns[32] = {0};
+    int last_phase_iters = 0;
     int persist_grid = 0;
 
     cudaGraphExec_t iter_graph = nullptr;

@@ -21,15 +21,17 @@ if name == "toy":
     z = dict(np.load("tests/golden/toy.npz", allow_pickle=False)); prob = problem_from_npz_dict(z); slot = 1
 else:
     prob = named_problem(name); slot = 0
-s = cabi.Solver(prob); s.set_modes(cabi.SWEEP_PERSISTENT, factors)
+sweep = cabi.SWEEP_CHAIN if "chain" in sys.argv else (cabi.SWEEP_PER_STAGE if "per_stage" in sys.argv else cabi.SWEEP_PERSISTENT)
+s = cabi.Solver(prob); s.set_modes(sweep, factors)
 s.factor_step(); s.update_state(); s.eliminate_coupling(prob.forecast.demand[slot], prob.forecast.prices[slot])
 o = Oracle(prob, L=s.read("SYS_MAT_L"), Lhat=s.read("SYS_MAT_LHAT"))
 o.factor_step(); o.update_state(); o.eliminate(prob.forecast.demand[slot], prob.forecast.prices[slot])
 print("info: chain stage", s.info().chain_first_stage, "sweep", s.info().sweep_mode, flush=True)
-for iters in (1, 2, 3, 10, 100, 500):
+for iters in [int(x) for x in os.environ.get("DBG_ITERS", "1,10,100,500").split(",")]:
     u0, infs = s.apg_solve(iters, want_infs=True)
     oinf = o.apg(iters)
     errs = {g: rel(s.read(g), o.get(n)) for g, n in PAIRS}
     bad = {k: f"{v:.1e}" for k, v in errs.items() if not v < 1e-4}
-    print(f"{name} it={iters}: worst {max(errs.values()):.2e} bad={bad} pinf max diff {np.abs(infs-oinf).max():.3e}", flush=True)
+    print(f"{name} it={iters}: worst {max(errs.values()):.2e} bad={bad} pinf max diff {np.abs(infs-oinf).max():.3e} at {int(np.abs(infs-oinf).argmax())} ({infs[int(np.abs(infs-oinf).argmax())]:.4e} vs {oinf[int(np.abs(infs-oinf).argmax())]:.4e})", flush=True)
 print("profile", s.profile_kernels(50))
+print("phases ns/iter", {k: round(v) for k, v in s.phase_times().items()})
