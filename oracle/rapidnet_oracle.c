@@ -36,38 +36,52 @@
 #include <omp.h>
 #endif
 
+/* real = float: the oracle proper (fp32 like the reference).  -DORC_F64 builds the same code in double
+ * (librapidnet_oracle64.so): the rounding-free trajectory that tests use to measure the fp32 noise floor of
+ * the reference itself (tests/test_gpu_reference.py, DESIGN.md "tolerances"). */
+#ifdef ORC_F64
+typedef double real;
+#define r_sqrt sqrt
+#define r_abs fabs
+#else
+typedef float real;
+#define r_sqrt sqrtf
+#define r_abs fabsf
+#endif
+typedef float f32;
+
 typedef struct orc {
     int nx, nu, nd, ne, nv, N, K, nodes, n_nonleaf, fb;
     /* tree (copies) */
     int *stages, *nps, *cum, *ancestor, *nchild, *nchild_cum;
-    float *prob, *err_demand, *err_price;
+    real *prob, *err_demand, *err_price;
     /* network */
-    float *B, *Gd, *E, *Ed, *xmin, *xmax, *xsafe, *umin, *umax, *alpha1;
+    real *B, *Gd, *E, *Ed, *xmin, *xmax, *xsafe, *umin, *umax, *alpha1;
     /* config */
-    float *W, *precond, pen_x, pen_xs, step, w_econ;
+    real *W, *precond, pen_x, pen_xs, step, w_econ;
     /* factor-step outputs (reference layouts) */
-    float *L, *Lhat;                 /* nu*nv, nu*nd */
-    float *Wv;                       /* nu*nv  = W L        (devMatWv) */
-    float *Rbar;                     /* nv*nv  = L' W L     */
-    float *Bbar;                     /* nv*nx  = (B L)'     (= G) */
-    float *s_u, *s_x, *s_xs;         /* per node diagonals of sysG / sysF */
-    float *sxmin, *sxmax, *sxs, *sumin, *sumax; /* scaled bounds per node */
-    float *Omega, *Theta;            /* fbn * nv*nv, fbn * nv*nx */
+    real *L, *Lhat;                 /* nu*nv, nu*nd */
+    real *Wv;                       /* nu*nv  = W L        (devMatWv) */
+    real *Rbar;                     /* nv*nv  = L' W L     */
+    real *Bbar;                     /* nv*nx  = (B L)'     (= G) */
+    real *s_u, *s_x, *s_xs;         /* per node diagonals of sysG / sysF */
+    real *sxmin, *sxmax, *sxs, *sumin, *sumax; /* scaled bounds per node */
+    real *Omega, *Theta;            /* fbn * nv*nv, fbn * nv*nx */
     int fbn;                         /* number of distinct Omega/Theta */
-    float *Phi, *Psi, *D, *F;        /* per node */
+    real *Phi, *Psi, *D, *F;        /* per node */
     /* per-solve */
-    float *xcur, *uprev, *dprev, *uhat_prev;
-    float *e, *uhat, *alpha, *beta;
+    real *xcur, *uprev, *dprev, *uhat_prev;
+    real *e, *uhat, *alpha, *beta;
     /* APG state */
-    float *X, *U, *V, *sigma;
-    float *xi, *psi;                 /* y_{k-1} */
-    float *upd_xi, *upd_psi;         /* y_k */
-    float *acc_xi, *acc_psi;         /* w */
-    float *pri_xi, *pri_psi;         /* Hx */
-    float *dual_xi, *dual_psi;       /* z */
-    float *res_xi, *res_psi;
-    float *Q, *R;                    /* K*nx, K*nv */
-    float dist_x, dist_xs;           /* last prox distances */
+    real *X, *U, *V, *sigma;
+    real *xi, *psi;                 /* y_{k-1} */
+    real *upd_xi, *upd_psi;         /* y_k */
+    real *acc_xi, *acc_psi;         /* w */
+    real *pri_xi, *pri_psi;         /* Hx */
+    real *dual_xi, *dual_psi;       /* z */
+    real *res_xi, *res_psi;
+    real *Q, *R;                    /* K*nx, K*nv */
+    real dist_x, dist_xs;           /* last prox distances */
     int have_L;
 } orc;
 
@@ -76,9 +90,9 @@ static void *xcalloc(size_t n, size_t sz) {
     if (!p) { fprintf(stderr, "oracle: out of memory (%zu x %zu)\n", n, sz); abort(); }
     return p;
 }
-static float *fdup(const float *src, size_t n) {
-    float *p = (float *)xcalloc(n, sizeof(float));
-    if (src) memcpy(p, src, n * sizeof(float));
+static real *fdup(const real *src, size_t n) {
+    real *p = (real *)xcalloc(n, sizeof(real));
+    if (src) memcpy(p, src, n * sizeof(real));
     return p;
 }
 static int *idup(const int *src, size_t n) {
@@ -88,33 +102,33 @@ static int *idup(const int *src, size_t n) {
 }
 
 /* y(m) = alpha*A(m x n, ld)*x + beta_*y ; column-major, column-sweep accumulation */
-static void gemv_n(int m, int n, float alpha, const float *A, int ld, const float *x, float beta_, float *y) {
+static void gemv_n(int m, int n, real alpha, const real *A, int ld, const real *x, real beta_, real *y) {
     if (beta_ == 0.0f) { for (int r = 0; r < m; r++) y[r] = 0.0f; }
     else if (beta_ != 1.0f) { for (int r = 0; r < m; r++) y[r] *= beta_; }
     for (int j = 0; j < n; j++) {
-        const float xj = alpha * x[j];
-        const float *a = A + (size_t)j * ld;
+        const real xj = alpha * x[j];
+        const real *a = A + (size_t)j * ld;
         for (int r = 0; r < m; r++) y[r] += a[r] * xj;
     }
 }
 /* y(n) = alpha*A'(A is m x n) * x(m) + beta_*y */
-static void gemv_t(int m, int n, float alpha, const float *A, int ld, const float *x, float beta_, float *y) {
+static void gemv_t(int m, int n, real alpha, const real *A, int ld, const real *x, real beta_, real *y) {
     for (int j = 0; j < n; j++) {
-        const float *a = A + (size_t)j * ld;
-        float s = 0.0f;
+        const real *a = A + (size_t)j * ld;
+        real s = 0.0f;
         for (int r = 0; r < m; r++) s += a[r] * x[r];
         y[j] = alpha * s + (beta_ == 0.0f ? 0.0f : beta_ * y[j]);
     }
 }
 /* C(m x n) = alpha * op(A) * op(B) + beta_*C ; generic small gemm (setup only) */
-static void gemm(int ta, int tb, int m, int n, int k, float alpha, const float *A, int lda,
-                 const float *B, int ldb, float beta_, float *C, int ldc) {
+static void gemm(int ta, int tb, int m, int n, int k, real alpha, const real *A, int lda,
+                 const real *B, int ldb, real beta_, real *C, int ldc) {
     for (int j = 0; j < n; j++)
         for (int i = 0; i < m; i++) {
-            float s = 0.0f;
+            real s = 0.0f;
             for (int p = 0; p < k; p++) {
-                float a = ta ? A[p + (size_t)i * lda] : A[i + (size_t)p * lda];
-                float b = tb ? B[j + (size_t)p * ldb] : B[p + (size_t)j * ldb];
+                real a = ta ? A[p + (size_t)i * lda] : A[i + (size_t)p * lda];
+                real b = tb ? B[j + (size_t)p * ldb] : B[p + (size_t)j * ldb];
                 s += a * b;
             }
             C[i + (size_t)j * ldc] = alpha * s + (beta_ == 0.0f ? 0.0f : beta_ * C[i + (size_t)j * ldc]);
@@ -122,28 +136,28 @@ static void gemm(int ta, int tb, int m, int n, int k, float alpha, const float *
 }
 
 /* fp32 LU with partial pivoting + inverse (cublasSgetrfBatched/SgetriBatched semantics). returns 0 ok */
-static int inverse_lu(int n, float *A /* destroyed */, float *inv) {
+static int inverse_lu(int n, real *A /* destroyed */, real *inv) {
     int *piv = (int *)xcalloc(n, sizeof(int));
     for (int k = 0; k < n; k++) {
-        int p = k; float mx = fabsf(A[k + (size_t)k * n]);
-        for (int i = k + 1; i < n; i++) { float v = fabsf(A[i + (size_t)k * n]); if (v > mx) { mx = v; p = i; } }
+        int p = k; real mx = r_abs(A[k + (size_t)k * n]);
+        for (int i = k + 1; i < n; i++) { real v = r_abs(A[i + (size_t)k * n]); if (v > mx) { mx = v; p = i; } }
         piv[k] = p;
         if (mx == 0.0f) { free(piv); return k + 1; }
-        if (p != k) for (int j = 0; j < n; j++) { float t = A[k + (size_t)j * n]; A[k + (size_t)j * n] = A[p + (size_t)j * n]; A[p + (size_t)j * n] = t; }
-        float d = 1.0f / A[k + (size_t)k * n];
+        if (p != k) for (int j = 0; j < n; j++) { real t = A[k + (size_t)j * n]; A[k + (size_t)j * n] = A[p + (size_t)j * n]; A[p + (size_t)j * n] = t; }
+        real d = 1.0f / A[k + (size_t)k * n];
         for (int i = k + 1; i < n; i++) A[i + (size_t)k * n] *= d;
         for (int j = k + 1; j < n; j++) {
-            float akj = A[k + (size_t)j * n];
+            real akj = A[k + (size_t)j * n];
             for (int i = k + 1; i < n; i++) A[i + (size_t)j * n] -= A[i + (size_t)k * n] * akj;
         }
     }
     /* solve A X = I column by column: P A = L U */
     for (int c = 0; c < n; c++) {
-        float *x = inv + (size_t)c * n;
+        real *x = inv + (size_t)c * n;
         for (int i = 0; i < n; i++) x[i] = (i == c) ? 1.0f : 0.0f;
-        for (int k = 0; k < n; k++) if (piv[k] != k) { float t = x[k]; x[k] = x[piv[k]]; x[piv[k]] = t; }
-        for (int k = 0; k < n; k++) { float xk = x[k]; if (xk != 0.0f) for (int i = k + 1; i < n; i++) x[i] -= A[i + (size_t)k * n] * xk; }
-        for (int k = n - 1; k >= 0; k--) { x[k] /= A[k + (size_t)k * n]; float xk = x[k]; for (int i = 0; i < k; i++) x[i] -= A[i + (size_t)k * n] * xk; }
+        for (int k = 0; k < n; k++) if (piv[k] != k) { real t = x[k]; x[k] = x[piv[k]]; x[piv[k]] = t; }
+        for (int k = 0; k < n; k++) { real xk = x[k]; if (xk != 0.0f) for (int i = k + 1; i < n; i++) x[i] -= A[i + (size_t)k * n] * xk; }
+        for (int k = n - 1; k >= 0; k--) { x[k] /= A[k + (size_t)k * n]; real xk = x[k]; for (int i = 0; i < k; i++) x[i] -= A[i + (size_t)k * n] * xk; }
     }
     free(piv);
     return 0;
@@ -151,12 +165,12 @@ static int inverse_lu(int n, float *A /* destroyed */, float *inv) {
 
 orc *orc_create(int nx, int nu, int nd, int ne, int nv, int N, int K, int nodes, int n_nonleaf,
                 const int *stages, const int *nps /*N+1*/, const int *cum /*N+2*/, const int *ancestor,
-                const int *nchild, const int *nchild_cum, const float *prob,
-                const float *err_demand, const float *err_price,
-                const float *B, const float *Gd, const float *E, const float *Ed,
-                const float *xmin, const float *xmax, const float *xsafe, const float *umin,
-                const float *umax, const float *alpha1,
-                const float *W, const float *precond, float pen_x, float pen_xs, float step) {
+                const int *nchild, const int *nchild_cum, const real *prob,
+                const real *err_demand, const real *err_price,
+                const real *B, const real *Gd, const real *E, const real *Ed,
+                const real *xmin, const real *xmax, const real *xsafe, const real *umin,
+                const real *umax, const real *alpha1,
+                const real *W, const real *precond, real pen_x, real pen_xs, real step) {
     orc *o = (orc *)xcalloc(1, sizeof(orc));
     o->nx = nx; o->nu = nu; o->nd = nd; o->ne = ne; o->nv = nv; o->N = N; o->K = K; o->nodes = nodes;
     o->n_nonleaf = n_nonleaf;
@@ -211,9 +225,9 @@ void orc_destroy(orc *o) {
     free(o);
 }
 
-void orc_set_L(orc *o, const float *L, const float *Lhat) {
-    memcpy(o->L, L, (size_t)o->nu * o->nv * sizeof(float));
-    memcpy(o->Lhat, Lhat, (size_t)o->nu * o->nd * sizeof(float));
+void orc_set_L(orc *o, const real *L, const real *Lhat) {
+    memcpy(o->L, L, (size_t)o->nu * o->nv * sizeof(real));
+    memcpy(o->Lhat, Lhat, (size_t)o->nu * o->nd * sizeof(real));
     o->have_L = 1;
 }
 
@@ -246,7 +260,7 @@ int orc_null_space(orc *o) {
             for (int i = k; i < nu; i++) Q[j + (size_t)i * nu] -= s * v[i];
         }
     }
-    for (int c = 0; c < nv; c++) for (int r = 0; r < nu; r++) o->L[r + (size_t)c * nu] = (float)Q[r + (size_t)(ne + c) * nu];
+    for (int c = 0; c < nv; c++) for (int r = 0; r < nu; r++) o->L[r + (size_t)c * nu] = (real)Q[r + (size_t)(ne + c) * nu];
     /* Lhat = -Q1 R^-T Ed : solve R' Y = Ed (ne x nd), then Q1 Y */
     double *Y = (double *)xcalloc((size_t)ne * nd, sizeof(double));
     for (int c = 0; c < nd; c++) {
@@ -255,7 +269,7 @@ int orc_null_space(orc *o) {
             for (int p = 0; p < i; p++) s -= A[p + (size_t)i * nu] * Y[p + (size_t)c * ne]; /* R'(i,p) = R(p,i) */
             Y[i + (size_t)c * ne] = s / A[i + (size_t)i * nu];
         }
-        for (int r = 0; r < nu; r++) { double s = 0; for (int p = 0; p < ne; p++) s += Q[r + (size_t)p * nu] * Y[p + (size_t)c * ne]; o->Lhat[r + (size_t)c * nu] = (float)(-s); }
+        for (int r = 0; r < nu; r++) { double s = 0; for (int p = 0; p < ne; p++) s += Q[r + (size_t)p * nu] * Y[p + (size_t)c * ne]; o->Lhat[r + (size_t)c * nu] = (real)(-s); }
     }
     free(A); free(Q); free(v); free(Y);
     o->have_L = 1;
@@ -271,18 +285,18 @@ int orc_factor_step(orc *o) {
     gemm(1, 0, nv, nv, nu, 1.0f, o->L, nu, o->Wv, nu, 0.0f, o->Rbar, nv);
     /* bounds and preconditioning (Engine.cu:421-451, Utilities.cu:33-58, 360-405) */
     for (int s = 0; s < N; s++) {
-        const float *pc = o->precond + (size_t)s * (2 * nx + nu);
+        const real *pc = o->precond + (size_t)s * (2 * nx + nu);
         for (int j = 0; j < o->nps[s]; j++) {
             int i = o->cum[s] + j;
-            float sp = sqrtf(o->prob[i]);
+            real sp = r_sqrt(o->prob[i]);
             for (int t = 0; t < nu; t++) {
-                float sc = sp * pc[t];
+                real sc = sp * pc[t];
                 o->s_u[(size_t)i * nu + t] = sc;
                 o->sumax[(size_t)i * nu + t] = sc * o->umax[t];
                 o->sumin[(size_t)i * nu + t] = sc * o->umin[t];
             }
             for (int t = 0; t < nx; t++) {
-                float scx = sp * pc[nu + t], scs = sp * pc[nu + nx + t];
+                real scx = sp * pc[nu + t], scs = sp * pc[nu + nx + t];
                 o->s_x[(size_t)i * nx + t] = scx; o->s_xs[(size_t)i * nx + t] = scs;
                 o->sxmax[(size_t)i * nx + t] = scx * o->xmax[t];
                 o->sxmin[(size_t)i * nx + t] = scx * o->xmin[t];
@@ -296,7 +310,7 @@ int orc_factor_step(orc *o) {
     int bad = 0;
     #pragma omp parallel for schedule(dynamic)
     for (int i = 0; i < o->fbn; i++) {
-        float *tmp = (float *)xcalloc((size_t)nv * nv, sizeof(float));
+        real *tmp = (real *)xcalloc((size_t)nv * nv, sizeof(real));
         for (int t = 0; t < nv * nv; t++) tmp[t] = o->Rbar[t] * o->prob[i];   /* Sscal by p (Engine.cu:434) */
         if (inverse_lu(nv, tmp, o->Omega + (size_t)i * nv * nv)) bad = 1;
         free(tmp);
@@ -311,8 +325,8 @@ int orc_factor_step(orc *o) {
     for (int i = 0; i < nodes; i++) {
         int s = o->stages[i], rel = i - o->cum[s];
         int oi = (o->fb > 0 && o->fb <= o->cum[s]) ? o->fb - K + rel : i;   /* Engine.cu:210-221 */
-        const float *Om = o->Omega + (size_t)oi * nv * nv;
-        float *Fi = o->F + (size_t)i * nv * nu, *Di = o->D + (size_t)i * 2 * nv * nx;
+        const real *Om = o->Omega + (size_t)oi * nv * nv;
+        real *Fi = o->F + (size_t)i * nv * nu, *Di = o->D + (size_t)i * 2 * nv * nx;
         for (int c = 0; c < nu; c++) for (int r = 0; r < nv; r++)
             Fi[r + (size_t)c * nv] = o->L[c + (size_t)r * nu] * o->s_u[(size_t)i * nu + c];
         for (int c = 0; c < nx; c++) for (int r = 0; r < nv; r++) {
@@ -326,29 +340,29 @@ int orc_factor_step(orc *o) {
 }
 
 /* Engine::updateStateControl (Engine.cu:1300-1316) */
-void orc_update_state(orc *o, const float *x, const float *uprev, const float *dprev) {
-    memcpy(o->xcur, x, o->nx * sizeof(float));
-    memcpy(o->uprev, uprev, o->nu * sizeof(float));
-    memcpy(o->dprev, dprev, o->nd * sizeof(float));
+void orc_update_state(orc *o, const real *x, const real *uprev, const real *dprev) {
+    memcpy(o->xcur, x, o->nx * sizeof(real));
+    memcpy(o->uprev, uprev, o->nu * sizeof(real));
+    memcpy(o->dprev, dprev, o->nd * sizeof(real));
     gemv_n(o->nu, o->nd, 1.0f, o->Lhat, o->nu, o->dprev, 0.0f, o->uhat_prev);
 }
 
 /* Engine::eliminateInputDistubanceCoupling (Engine.cu:1147-1298) */
-void orc_eliminate(orc *o, const float *dhat /*N*nd*/, const float *alphahat /*N*nu*/,
+void orc_eliminate(orc *o, const real *dhat /*N*nd*/, const real *alphahat /*N*nu*/,
                    int demand_uncertainty, int price_uncertainty) {
     const int nx = o->nx, nu = o->nu, nv = o->nv, nd = o->nd, N = o->N, nodes = o->nodes;
-    float *ah = fdup(alphahat, (size_t)N * nu);
+    real *ah = fdup(alphahat, (size_t)N * nu);
     for (int s = 0; s < N; s++) for (int t = 0; t < nu; t++) ah[(size_t)s * nu + t] += o->alpha1[t];
-    float *dU = fdup(NULL, (size_t)nodes * nu), *zeta = fdup(NULL, (size_t)nodes * nu);
+    real *dU = fdup(NULL, (size_t)nodes * nu), *zeta = fdup(NULL, (size_t)nodes * nu);
     #pragma omp parallel for schedule(static)
     for (int i = 0; i < nodes; i++) {
         int s = o->stages[i];
-        float *d = (float *)xcalloc(nd, sizeof(float));
+        real *d = (real *)xcalloc(nd, sizeof(real));
         for (int t = 0; t < nd; t++) d[t] = (demand_uncertainty ? o->err_demand[(size_t)i * nd + t] : 0.0f) + dhat[(size_t)s * nd + t];
         gemv_n(nx, nd, 1.0f, o->Gd, nx, d, 0.0f, o->e + (size_t)i * nx);
         gemv_n(nu, nd, 1.0f, o->Lhat, nu, d, 0.0f, o->uhat + (size_t)i * nu);
         for (int t = 0; t < nu; t++) {
-            float a = (price_uncertainty ? o->err_price[(size_t)i * nu + t] : 0.0f) + ah[(size_t)s * nu + t];
+            real a = (price_uncertainty ? o->err_price[(size_t)i * nu + t] : 0.0f) + ah[(size_t)s * nu + t];
             o->alpha[(size_t)i * nu + t] = o->w_econ * a;
         }
         free(d);
@@ -360,9 +374,9 @@ void orc_eliminate(orc *o, const float *dhat /*N*nd*/, const float *alphahat /*N
     }
     #pragma omp parallel for schedule(static)
     for (int i = 0; i < nodes; i++) {
-        float *ab = (float *)xcalloc(nv, sizeof(float));
+        real *ab = (real *)xcalloc(nv, sizeof(real));
         for (int t = 0; t < nu; t++) {
-            float z = o->prob[i] * dU[(size_t)i * nu + t];
+            real z = o->prob[i] * dU[(size_t)i * nu + t];
             if (i < o->n_nonleaf) {
                 int c0 = (i == 0) ? 1 : o->nchild_cum[i - 1] + 1;
                 int nc = (i == 0) ? o->nchild_cum[0] : o->nchild_cum[i] - o->nchild_cum[i - 1];
@@ -382,50 +396,50 @@ void orc_eliminate(orc *o, const float *dhat /*N*nd*/, const float *alphahat /*N
 /* SmpcController::initialiseAlgorithm (SmpcController.cu:420-450) */
 void orc_apg_init(orc *o) {
     size_t n = (size_t)o->nodes;
-    memset(o->xi, 0, n * 2 * o->nx * 4); memset(o->psi, 0, n * o->nu * 4);
-    memset(o->acc_xi, 0, n * 2 * o->nx * 4); memset(o->acc_psi, 0, n * o->nu * 4);
-    memset(o->pri_xi, 0, n * 2 * o->nx * 4); memset(o->pri_psi, 0, n * o->nu * 4);
-    memset(o->dual_xi, 0, n * 2 * o->nx * 4); memset(o->dual_psi, 0, n * o->nu * 4);
-    memset(o->upd_xi, 0, n * 2 * o->nx * 4); memset(o->upd_psi, 0, n * o->nu * 4);
+    memset(o->xi, 0, n * 2 * o->nx * sizeof(real)); memset(o->psi, 0, n * o->nu * sizeof(real));
+    memset(o->acc_xi, 0, n * 2 * o->nx * sizeof(real)); memset(o->acc_psi, 0, n * o->nu * sizeof(real));
+    memset(o->pri_xi, 0, n * 2 * o->nx * sizeof(real)); memset(o->pri_psi, 0, n * o->nu * sizeof(real));
+    memset(o->dual_xi, 0, n * 2 * o->nx * sizeof(real)); memset(o->dual_psi, 0, n * o->nu * sizeof(real));
+    memset(o->upd_xi, 0, n * 2 * o->nx * sizeof(real)); memset(o->upd_psi, 0, n * o->nu * sizeof(real));
 }
 
 /* SmpcController::dualExtrapolationStep (SmpcController.cu:535-557) */
-void orc_extrapolate(orc *o, float lambda) {
+void orc_extrapolate(orc *o, real lambda) {
     size_t nxi = (size_t)o->nodes * 2 * o->nx, nps = (size_t)o->nodes * o->nu;
-    float a1 = 1 + lambda, a2 = -lambda;
+    real a1 = 1 + lambda, a2 = -lambda;
     #pragma omp parallel for schedule(static)
-    for (size_t t = 0; t < nxi; t++) { float w = o->upd_xi[t] * a1; w += a2 * o->xi[t]; o->acc_xi[t] = w; o->xi[t] = o->upd_xi[t]; }
+    for (size_t t = 0; t < nxi; t++) { real w = o->upd_xi[t] * a1; w += a2 * o->xi[t]; o->acc_xi[t] = w; o->xi[t] = o->upd_xi[t]; }
     #pragma omp parallel for schedule(static)
-    for (size_t t = 0; t < nps; t++) { float w = o->upd_psi[t] * a1; w += a2 * o->psi[t]; o->acc_psi[t] = w; o->psi[t] = o->upd_psi[t]; }
+    for (size_t t = 0; t < nps; t++) { real w = o->upd_psi[t] * a1; w += a2 * o->psi[t]; o->acc_psi[t] = w; o->psi[t] = o->upd_psi[t]; }
 }
 
 /* SmpcController::solveStep (SmpcController.cu:563-755) */
 void orc_solve_step(orc *o) {
     const int nx = o->nx, nu = o->nu, nv = o->nv, N = o->N, nodes = o->nodes, K = o->K;
-    memcpy(o->sigma, o->beta, (size_t)nodes * nv * sizeof(float));
+    memcpy(o->sigma, o->beta, (size_t)nodes * nv * sizeof(real));
     int widest = 1; for (int s = 0; s < N; s++) if (o->nps[s] > widest) widest = o->nps[s];
-    float *tq = fdup(NULL, (size_t)widest * nx), *tr = fdup(NULL, (size_t)widest * nv);
+    real *tq = fdup(NULL, (size_t)widest * nx), *tr = fdup(NULL, (size_t)widest * nv);
     for (int s = N - 1; s >= 0; s--) {
         const int c0 = o->cum[s], ns = o->nps[s];
         #pragma omp parallel for schedule(static)
         for (int j = 0; j < ns; j++) {
             const int i = c0 + j;
             const int oi = (o->fb > 0 && o->fb <= c0) ? o->fb - K + j : i;
-            float *sg = o->sigma + (size_t)i * nv, *v = o->V + (size_t)i * nv;
-            float *r = o->R + (size_t)j * nv, *q = o->Q + (size_t)j * nx;
-            const float *wxi = o->acc_xi + (size_t)i * 2 * nx, *wps = o->acc_psi + (size_t)i * nu;
+            real *sg = o->sigma + (size_t)i * nv, *v = o->V + (size_t)i * nv;
+            real *r = o->R + (size_t)j * nv, *q = o->Q + (size_t)j * nx;
+            const real *wxi = o->acc_xi + (size_t)i * 2 * nx, *wps = o->acc_psi + (size_t)i * nu;
             if (s < N - 1) for (int t = 0; t < nv; t++) sg[t] += r[t];
             gemv_n(nv, nv, -0.5f, o->Omega + (size_t)oi * nv * nv, nv, sg, 0.0f, v);
             if (s < N - 1) gemv_n(nv, nx, 1.0f, o->Theta + (size_t)oi * nv * nx, nv, q, 1.0f, v);
             gemv_n(nv, nu, 1.0f, o->Psi + (size_t)i * nv * nu, nv, wps, 1.0f, v);
             gemv_n(nv, 2 * nx, 1.0f, o->Phi + (size_t)i * 2 * nv * nx, nv, wxi, 1.0f, v);
-            memcpy(r, sg, nv * sizeof(float));
+            memcpy(r, sg, nv * sizeof(real));
             gemv_n(nv, 2 * nx, 1.0f, o->D + (size_t)i * 2 * nv * nx, nv, wxi, 1.0f, r);
             gemv_n(nv, nu, 1.0f, o->F + (size_t)i * nv * nu, nv, wps, 1.0f, r);
             if (s < N - 1) gemv_n(nv, nx, 1.0f, o->Bbar, nv, q, 1.0f, r);
             /* q = sysF' xi (+ q): sysF = [diag(s_x); diag(s_xs)] */
             for (int t = 0; t < nx; t++) {
-                float acc = o->s_x[(size_t)i * nx + t] * wxi[t] + o->s_xs[(size_t)i * nx + t] * wxi[nx + t];
+                real acc = o->s_x[(size_t)i * nx + t] * wxi[t] + o->s_xs[(size_t)i * nx + t] * wxi[nx + t];
                 q[t] = (s < N - 1) ? acc + q[t] : acc;
             }
         }
@@ -436,16 +450,16 @@ void orc_solve_step(orc *o) {
                     int node = pc0 + p;
                     int first = (node == 0 ? 0 : o->nchild_cum[node - 1]) - (pc0 == 0 ? 0 : o->nchild_cum[pc0 - 1]);
                     int nc = o->nchild[node];
-                    for (int t = 0; t < nx; t++) { float a = o->Q[(size_t)first * nx + t]; for (int c = 1; c < nc; c++) a += o->Q[(size_t)(first + c) * nx + t]; tq[(size_t)p * nx + t] = a; }
-                    for (int t = 0; t < nv; t++) { float a = o->R[(size_t)first * nv + t]; for (int c = 1; c < nc; c++) a += o->R[(size_t)(first + c) * nv + t]; tr[(size_t)p * nv + t] = a; }
+                    for (int t = 0; t < nx; t++) { real a = o->Q[(size_t)first * nx + t]; for (int c = 1; c < nc; c++) a += o->Q[(size_t)(first + c) * nx + t]; tq[(size_t)p * nx + t] = a; }
+                    for (int t = 0; t < nv; t++) { real a = o->R[(size_t)first * nv + t]; for (int c = 1; c < nc; c++) a += o->R[(size_t)(first + c) * nv + t]; tr[(size_t)p * nv + t] = a; }
                 }
-                memcpy(o->R, tr, (size_t)pn * nv * sizeof(float));
-                memcpy(o->Q, tq, (size_t)pn * nx * sizeof(float));
+                memcpy(o->R, tr, (size_t)pn * nv * sizeof(real));
+                memcpy(o->Q, tq, (size_t)pn * nx * sizeof(real));
             }
         }
     }
     /* forward substitution (SmpcController.cu:675-741) */
-    memcpy(o->U, o->uhat, (size_t)nodes * nu * sizeof(float));
+    memcpy(o->U, o->uhat, (size_t)nodes * nu * sizeof(real));
     for (int s = 0; s < N; s++) {
         const int c0 = o->cum[s], ns = o->nps[s];
         if (s == 0) {
@@ -460,12 +474,12 @@ void orc_solve_step(orc *o) {
             for (int j = 0; j < ns; j++) {
                 const int i = c0 + j;
                 const int par = branching ? o->ancestor[i] - 1 : pc0 + j;
-                float *u = o->U + (size_t)i * nu, *x = o->X + (size_t)i * nx;
-                const float *up = o->U + (size_t)par * nu, *uhp = o->uhat + (size_t)par * nu;
-                const float *xp = o->X + (size_t)par * nx, *ei = o->e + (size_t)i * nx;
+                real *u = o->U + (size_t)i * nu, *x = o->X + (size_t)i * nx;
+                const real *up = o->U + (size_t)par * nu, *uhp = o->uhat + (size_t)par * nu;
+                const real *xp = o->X + (size_t)par * nx, *ei = o->e + (size_t)i * nx;
                 if (branching) {
                     gemv_n(nu, nv, 1.0f, o->L, nu, o->V + (size_t)i * nv, 1.0f, u);
-                    for (int t = 0; t < nu; t++) { float lv = up[t] + -1.0f * uhp[t]; u[t] = lv + u[t]; }
+                    for (int t = 0; t < nu; t++) { real lv = up[t] + -1.0f * uhp[t]; u[t] = lv + u[t]; }
                     for (int t = 0; t < nx; t++) x[t] = ei[t];
                     gemv_n(nx, nu, 1.0f, o->B, nx, u, 1.0f, x);
                     for (int t = 0; t < nx; t++) x[t] = xp[t] + x[t];
@@ -490,47 +504,47 @@ void orc_solve_step(orc *o) {
     free(tq); free(tr);
 }
 
-static float clampf(float v, float lo, float hi) { if (v < lo) return lo; else if (v > hi) return hi; return v; }
+static real clampf(real v, real lo, real hi) { if (v < lo) return lo; else if (v > hi) return hi; return v; }
 
 /* SmpcController::proximalFunG (SmpcController.cu:759-835), incl. the scratch-clobber quirk */
 void orc_prox(orc *o) {
     const int nx = o->nx, nu = o->nu, nodes = o->nodes;
-    const float inv_lambda = 1 / o->step;
-    union { unsigned u; float f; } up; up.u = 0x7F7F7F7Fu;   /* cudaMemset(.., 127, ..): Engine.cu:454-455 */
-    const float xs_upper = up.f;
+    const real inv_lambda = 1 / o->step;
+    union { unsigned u; f32 f; } up; up.u = 0x7F7F7F7Fu;   /* cudaMemset(.., 127, ..): Engine.cu:454-455 */
+    const real xs_upper = up.f;
     size_t nxi = (size_t)nodes * 2 * nx;
-    float *diff = fdup(NULL, nxi);
+    real *diff = fdup(NULL, nxi);
     double s1 = 0.0, s2 = 0.0;
     #pragma omp parallel for schedule(static) reduction(+:s1,s2)
     for (int i = 0; i < nodes; i++) {
         for (int t = 0; t < nx; t++) {
             size_t k1 = (size_t)i * 2 * nx + t, k2 = k1 + nx;
-            float t1 = o->pri_xi[k1] + inv_lambda * o->acc_xi[k1];
-            float t2 = o->pri_xi[k2] + inv_lambda * o->acc_xi[k2];
-            float z1 = clampf(t1, o->sxmin[(size_t)i * nx + t], o->sxmax[(size_t)i * nx + t]);
-            float z2 = clampf(t2, o->sxs[(size_t)i * nx + t], xs_upper);
+            real t1 = o->pri_xi[k1] + inv_lambda * o->acc_xi[k1];
+            real t2 = o->pri_xi[k2] + inv_lambda * o->acc_xi[k2];
+            real z1 = clampf(t1, o->sxmin[(size_t)i * nx + t], o->sxmax[(size_t)i * nx + t]);
+            real z2 = clampf(t2, o->sxs[(size_t)i * nx + t], xs_upper);
             o->dual_xi[k1] = z1; o->dual_xi[k2] = z2;
             diff[k1] = t1 + -1.0f * z1; diff[k2] = t2 + -1.0f * z2;
             s1 += (double)diff[k1] * diff[k1]; s2 += (double)diff[k2] * diff[k2];
         }
         for (int t = 0; t < nu; t++) {
             size_t k = (size_t)i * nu + t;
-            float tu = o->pri_psi[k] + inv_lambda * o->acc_psi[k];
+            real tu = o->pri_psi[k] + inv_lambda * o->acc_psi[k];
             o->dual_psi[k] = clampf(tu, o->sumin[k], o->sumax[k]);
         }
     }
-    float d1 = (float)sqrt(s1), d2 = (float)sqrt(s2);
+    real d1 = (real)sqrt(s1), d2 = (real)sqrt(s2);
     o->dist_x = d1; o->dist_xs = d2;
     if (d1 > inv_lambda * o->pen_x) {
-        float sc = 1 - inv_lambda * o->pen_x / d1;
+        real sc = 1 - inv_lambda * o->pen_x / d1;
         for (int i = 0; i < nodes; i++) for (int t = 0; t < nx; t++) { size_t k = (size_t)i * 2 * nx + t; o->dual_xi[k] = o->dual_xi[k] + sc * diff[k]; }
         /* :800-802 -- scratch reused for g(xBox): node 0 copied, part 1 clamped, then diff -= z everywhere */
-        memcpy(diff, o->dual_xi, (size_t)2 * nx * sizeof(float));
+        memcpy(diff, o->dual_xi, (size_t)2 * nx * sizeof(real));
         for (int i = 0; i < nodes; i++) for (int t = 0; t < nx; t++) { size_t k = (size_t)i * 2 * nx + t; diff[k] = clampf(diff[k], o->sxmin[(size_t)i * nx + t], o->sxmax[(size_t)i * nx + t]); }
         for (size_t k = 0; k < nxi; k++) diff[k] += -1.0f * o->dual_xi[k];
     }
     if (d2 > inv_lambda * o->pen_xs) {
-        float sc = 1 - inv_lambda * o->pen_xs / d2;
+        real sc = 1 - inv_lambda * o->pen_xs / d2;
         for (int i = 0; i < nodes; i++) for (int t = 0; t < nx; t++) { size_t k = (size_t)i * 2 * nx + nx + t; o->dual_xi[k] = o->dual_xi[k] + sc * diff[k]; }
     }
     free(diff);
@@ -551,28 +565,28 @@ void orc_dual_update(orc *o) {
 }
 
 /* updatePrimalInfeasibity (:1480-1496): signed value at the first arg-max-abs, max over the two blocks */
-float orc_primal_infeasibility(orc *o) {
+real orc_primal_infeasibility(orc *o) {
     size_t nxi = (size_t)o->nodes * 2 * o->nx, nps = (size_t)o->nodes * o->nu;
     size_t ix = 0, ip = 0;
-    for (size_t t = 1; t < nxi; t++) if (fabsf(o->res_xi[t]) > fabsf(o->res_xi[ix])) ix = t;
-    for (size_t t = 1; t < nps; t++) if (fabsf(o->res_psi[t]) > fabsf(o->res_psi[ip])) ip = t;
-    float a = o->res_xi[ix], b = o->res_psi[ip];
+    for (size_t t = 1; t < nxi; t++) if (r_abs(o->res_xi[t]) > r_abs(o->res_xi[ix])) ix = t;
+    for (size_t t = 1; t < nps; t++) if (r_abs(o->res_psi[t]) > r_abs(o->res_psi[ip])) ip = t;
+    real a = o->res_xi[ix], b = o->res_psi[ip];
     return a > b ? a : b;
 }
 
-/* lambda table exactly as the host loop computes it (SmpcController.cu:1505-1520): float theta, double update */
-void orc_lambda_table(int iters, float *lambda_out) {
-    float theta0 = 1, theta1 = 1;
+/* lambda table exactly as the host loop computes it (SmpcController.cu:1505-1520): real theta, double update */
+void orc_lambda_table(int iters, real *lambda_out) {
+    f32 theta0 = 1, theta1 = 1;
     for (int k = 0; k < iters; k++) {
-        lambda_out[k] = theta1 * (1 / theta0 - 1);
+        lambda_out[k] = (f32)(theta1 * (1 / theta0 - 1));
         theta0 = theta1;
         theta1 = 0.5 * (sqrt(pow(theta1, 4) + 4 * pow(theta1, 2)) - pow(theta1, 2));
     }
 }
 
 /* SmpcController::algorithmApg (:1500-1525) */
-void orc_apg(orc *o, int iters, float *primal_infs /* nullable */) {
-    float *lam = (float *)xcalloc(iters, sizeof(float));
+void orc_apg(orc *o, int iters, real *primal_infs /* nullable */) {
+    real *lam = (real *)xcalloc(iters, sizeof(real));
     orc_lambda_table(iters, lam);
     orc_apg_init(o);
     for (int k = 0; k < iters; k++) {
@@ -581,14 +595,14 @@ void orc_apg(orc *o, int iters, float *primal_infs /* nullable */) {
         orc_prox(o);
         orc_residual(o);
         orc_dual_update(o);
-        float pi = orc_primal_infeasibility(o);
+        real pi = orc_primal_infeasibility(o);
         if (primal_infs) primal_infs[k] = pi;
     }
     free(lam);
 }
 
 /* ---- named buffer access ---- */
-static float *orc_buf(orc *o, const char *name, size_t *count) {
+static real *orc_buf(orc *o, const char *name, size_t *count) {
     size_t n = (size_t)o->nodes; const int nx = o->nx, nu = o->nu, nv = o->nv, nd = o->nd;
 #define B_(nm, ptr, cnt) if (!strcmp(name, nm)) { *count = (cnt); return (ptr); }
     B_("L", o->L, (size_t)nu * nv) B_("Lhat", o->Lhat, (size_t)nu * nd) B_("Wv", o->Wv, (size_t)nu * nv)
@@ -611,18 +625,18 @@ static float *orc_buf(orc *o, const char *name, size_t *count) {
     *count = 0; return NULL;
 }
 long orc_count(orc *o, const char *name) { size_t c; return orc_buf(o, name, &c) ? (long)c : -1; }
-int orc_get(orc *o, const char *name, float *out, long count) {
-    size_t c; float *p = orc_buf(o, name, &c);
+int orc_get(orc *o, const char *name, real *out, long count) {
+    size_t c; real *p = orc_buf(o, name, &c);
     if (!p || (size_t)count > c) return 1;
-    memcpy(out, p, (size_t)count * sizeof(float)); return 0;
+    memcpy(out, p, (size_t)count * sizeof(real)); return 0;
 }
-int orc_set(orc *o, const char *name, const float *in, long count) {
-    size_t c; float *p = orc_buf(o, name, &c);
+int orc_set(orc *o, const char *name, const real *in, long count) {
+    size_t c; real *p = orc_buf(o, name, &c);
     if (!p || (size_t)count > c) return 1;
-    memcpy(p, in, (size_t)count * sizeof(float)); return 0;
+    memcpy(p, in, (size_t)count * sizeof(real)); return 0;
 }
 int orc_final_branch_node(orc *o) { return o->fb; }
-float orc_distance(orc *o, int which) { return which ? o->dist_xs : o->dist_x; }
+real orc_distance(orc *o, int which) { return which ? o->dist_xs : o->dist_x; }
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
