@@ -276,12 +276,12 @@ class Solver:
         self._check(load().rn_profile_kernels(self.h, int(iterations), _fp(out)), "rn_profile_kernels")
         return dict(zip(self.PROF_CLASSES, (float(v) for v in out)))
 
-    PHASE_NAMES = {0: "S.stream", 1: "S.barrier", 2: "S.pinf", 3: "B.stage", 4: "B.qscan", 5: "B.gemm_Gq", 6: "B.rscan",
-                   7: "B.gemm_v", 8: "B.gemm_Lv", 9: "B.tail_end", 10: "B.barrier", 11: "B.crown", 12: "B.crown_barrier",
-                   13: "F.crown", 14: "F.crown_barrier", 15: "F.stage", 16: "F.uscan", 17: "F.gemm_Bu", 18: "F.xscan",
-                   19: "F.epilogue", 20: "F.tail_end", 21: "F.dist", 22: "F.barrier",
-                   23: "cyc.loader_total", 24: "cyc.gemv_wait_full", 25: "cyc.gemv_wait_w", 26: "cyc.gemv_wait_red", 27: "cyc.gemv_compute",
-                   28: "cyc.loader_wait_empty", 29: "cyc.loader_vec", 30: "cyc.ew_wait_red", 31: "cyc.ew_prologue"}
+    PHASE_NAMES = {0: "S.stream", 1: "S.barrier", 2: "S.pinf", 3: "B.qscan", 4: "B.gemm_Gq", 5: "B.rscan", 6: "B.gemm_OT",
+                   7: "B.vcombine", 8: "B.gemm_Lv", 9: "B.out", 10: "B.idle", 11: "C.sums", 12: "C.gemm_G", 13: "F.crown_path",
+                   14: "F.crown_rest", 15: "F.columns", 16: "F.uscan", 17: "F.gemm_Bu", 18: "F.xscan", 19: "F.epilogue",
+                   20: "C.barrier_in", 21: "C.idle", 22: "C.barrier_out", 23: "F.idle", 24: "cyc.gemv_wait_full",
+                   25: "cyc.gemv_wait_w", 26: "cyc.gemv_wait_red", 27: "cyc.gemv_compute", 28: "F.dist", 29: "F.barrier",
+                   30: "cyc.ew_wait_red", 31: "cyc.ew_prologue"}
 
     def phase_times(self) -> dict:
         """ns per iteration of each phase of the persistent kernel in the last profile_kernels run (CTA 0's clock)"""

@@ -843,10 +843,13 @@ rn_status profile_kernels(Handle *h, int iterations, float *ms_out) {
         float total = 0.f;
         RN_CUDA(h, cudaEventElapsedTime(&total, e0, e1));
         cudaEventDestroy(e0); cudaEventDestroy(e1);
-        // stream = fused element-wise pass + factor stream + its closing barrier; backward = chains + crown; forward = rest
+        // stream = fused element-wise pass + factor stream + its closing barrier; backward = chains + crown (+ their
+        // barriers); forward = crown + chains + prox boxes + the closing barrier.  Indices: cabi.PHASE_NAMES
         unsigned long long ns[4] = {pn[0] + pn[1], 0, 0, 0};
         for (int k = 2; k <= 12; k++) ns[1] += pn[k];
-        for (int k = 13; k <= 22; k++) ns[2] += pn[k];
+        for (int k = 20; k <= 22; k++) ns[1] += pn[k];
+        for (int k = 13; k <= 19; k++) ns[2] += pn[k];
+        ns[2] += pn[23] + pn[28] + pn[29];
         memcpy(h->last_phase_ns, pn, sizeof(pn));
         h->last_phase_iters = iterations;
         ms_out[RN_PROF_STREAM] = (float)(ns[0] * 1e-6 / iterations);

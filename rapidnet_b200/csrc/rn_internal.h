@@ -97,7 +97,8 @@ struct Handle {
 
     // persistent cooperative kernel
     float *part[4] = {nullptr, nullptr, nullptr, nullptr};   // D xi_w, F psi_w, Phi xi_w, Psi psi_w
-    float *LV = nullptr;
+    float *LV = nullptr, *qh = nullptr, *rh = nullptr, *sweep_pack = nullptr;
+    int *crown_rng = nullptr;
     unsigned int *grid_bar = nullptr;
     unsigned long long *phase_ns = nullptr;
     bool persist_ready = false;
