@@ -1,0 +1,263 @@
+// engine.cpp -- Engine and SmpcController of the reference as thin host code over the C ABI.
+//   Engine          /root/reference/src/Engine.cu:126-163 (ctor), :671-774 (factorStep), :1147-1316 (per-solve terms)
+//   SmpcController  /root/reference/src/SmpcController.cu:32-116 (ctors), :476-487, :535-864 (steps), :1500-1525 (APG),
+//                   :1593-1667 (controller calls), :1679-1717 (moveForewardInTime), :1778-1859 (KPIs)
+// Error behaviour as in the reference (_CUDA / _CUBLAS / _ASSERT, src/Configuration.h:38-81): print and exit.
+#include <cmath>
+#include <cstdlib>
+#include <iostream>
+
+#include "rapidnet_host.hpp"
+
+namespace rapidnet {
+
+// ---- Engine ------------------------------------------------------------------------------------------------------------
+void Engine::check(rn_status rc, const char *what) {
+    if (rc == RN_OK) return;
+    std::cerr << "rapidnet_b200: " << what << " failed (" << rc << "): " << rn_last_error(h) << std::endl;
+    std::exit(EXIT_FAILURE);
+}
+
+Engine::Engine(SmpcConfiguration *smpcConfig) {
+    ptrMySmpcConfig = smpcConfig;
+    ptrMyNetwork = new DwnNetwork(smpcConfig->getPathToNetwork());
+    ptrMyScenarioTree = new ScenarioTree(smpcConfig->getPathToScenarioTree());
+    const std::string algorithmName = smpcConfig->getOptimisationAlgorithm();
+    std::cout << "Number of scenarios " << ptrMyScenarioTree->getNumScenarios() << std::endl;
+    globalFbeFlag = algorithmName == "globalFbeAlgorithm";
+    namaFlag = algorithmName == "namaAlgorithm";
+    apgFlag = !globalFbeFlag && !namaFlag;
+    std::cout << "algorithm based on SMPC " << algorithmName << std::endl;
+
+    DwnNetwork *n = ptrMyNetwork;
+    ScenarioTree *t = ptrMyScenarioTree;
+    rn_dims d{};
+    d.nx = n->getNumTanks(); d.nu = n->getNumControls(); d.nd = n->getNumDemands(); d.ne = n->getNumMixNodes();
+    d.nv = smpcConfig->getNV(); d.N = t->getPredHorizon(); d.K = t->getNumScenarios(); d.nodes = t->getNumNodes();
+    d.n_nonleaf = t->getNumNonleafNodes(); d.n_children_tot = t->getNumChildrenTot();
+    rn_tree tr{};
+    tr.stages = t->getStageNodes(); tr.nodes_per_stage = t->getNodesPerStage();
+    tr.nodes_per_stage_cumul = t->getNodesPerStageCumul(); tr.leaves = t->getLeaveArray(); tr.children = t->getChildArray();
+    tr.ancestor = t->getAncestorArray(); tr.n_children = t->getNumChildren(); tr.n_children_cumul = t->getNumChildrenCumul();
+    tr.prob = t->getProbArray(); tr.err_demand = t->getErrorDemandArray(); tr.err_price = t->getErrorPriceArray();
+    rn_network nw{};
+    nw.B = n->getMatB(); nw.Gd = n->getMatGd(); nw.E = n->getMatE(); nw.Ed = n->getMatEd();
+    nw.xmin = n->getXmin(); nw.xmax = n->getXmax(); nw.xsafe = n->getXsafe(); nw.umin = n->getUmin(); nw.umax = n->getUmax();
+    nw.alpha1 = n->getAlpha();
+    rn_config c{};
+    c.costW = smpcConfig->getCostW(); c.precond = smpcConfig->getMatPrcndDiag();
+    c.penalty_x = smpcConfig->getPenaltyState(); c.penalty_xs = smpcConfig->getPenaltySafety();
+    c.step_size = smpcConfig->getStepSize(); c.weight_economical = smpcConfig->getWeightEconomical();
+    c.max_iterations = smpcConfig->getMaxIterations();
+    int device = 0;
+    if (const char *e = std::getenv("RAPIDNET_DEVICE")) device = std::atoi(e);
+    rn_status rc = rn_create(&d, &tr, &nw, &c, device, &h);
+    if (rc != RN_OK) {
+        std::cerr << "rapidnet_b200: rn_create failed (" << rc << "): " << rn_last_error(nullptr) << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
+}
+
+Engine::~Engine() {
+    if (h) rn_destroy(h);
+    delete ptrMyNetwork;
+    delete ptrMyScenarioTree;
+}
+
+real_t *Engine::buf(rn_buffer_id id) {
+    void *p = nullptr;
+    size_t bytes = 0;
+    check(rn_buffer(h, id, &p, &bytes), "rn_buffer");
+    return static_cast<real_t *>(p);
+}
+
+void Engine::factorStep() { check(rn_factor_step(h), "Engine::factorStep"); }
+
+void Engine::updateStateControl(real_t *currentX, real_t *prevU, real_t *prevDemand) {
+    check(rn_update_state(h, currentX, prevU, prevDemand), "Engine::updateStateControl");
+}
+
+void Engine::eliminateInputDistubanceCoupling(real_t *nominalDemand, real_t *nominalPrices) {
+    check(rn_eliminate_coupling(h, nominalDemand, nominalPrices), "Engine::eliminateInputDistubanceCoupling");
+}
+
+void Engine::setPriceUncertaintyFlag(bool inputFlag) {
+    priceUncertaintyFlag = inputFlag;
+    check(rn_set_uncertainty(h, demandUncertaintyFlag, priceUncertaintyFlag), "Engine::setPriceUncertaintyFlag");
+}
+
+void Engine::setDemandUncertaintyFlag(bool inputFlag) {
+    demandUncertaintyFlag = inputFlag;
+    check(rn_set_uncertainty(h, demandUncertaintyFlag, priceUncertaintyFlag), "Engine::setDemandUncertaintyFlag");
+}
+
+// ---- SmpcController ----------------------------------------------------------------------------------------------------
+void SmpcController::check(rn_status rc, const char *what) {
+    if (rc == RN_OK) return;
+    std::cerr << "rapidnet_b200: " << what << " failed (" << rc << "): " << rn_last_error(ptrMyEngine->handle()) << std::endl;
+    std::exit(EXIT_FAILURE);
+}
+
+void SmpcController::construct() {
+    stepSize = ptrMySmpcConfig->getStepSize();
+    factorStepFlag = false;
+    simulatorFlag = true;
+    vecPrimalInfs.assign((size_t)ptrMySmpcConfig->getMaxIterations() + 1, 0.f);
+    economicKpi = smoothKpi = safeKpi = networkKpi = 0;
+    if (!ptrMyEngine->getApgFlag())
+        std::cerr << "rapidnet_b200: algorithmName selects FBE/NAMA buffers in the reference; controlAction always runs APG "
+                     "(SmpcController.cu:1617, 1646) and so does this build" << std::endl;
+    refreshDevicePointers();
+}
+
+SmpcController::SmpcController(Forecaster *myForecaster, Engine *myEngine, SmpcConfiguration *mySmpcConfig) {
+    ptrMyForecaster = myForecaster;
+    ptrMyEngine = myEngine;
+    ptrMySmpcConfig = mySmpcConfig;
+    construct();
+}
+
+SmpcController::SmpcController(std::string pathToConfigFile) {
+    ptrMySmpcConfig = new SmpcConfiguration(pathToConfigFile);
+    ptrMyForecaster = new Forecaster(ptrMySmpcConfig->getPathToForecaster());
+    ptrMyEngine = new Engine(ptrMySmpcConfig);
+    ownsObjects = true;   // the reference never deletes them (SmpcController.cu:2091-2102); this build does
+    construct();
+}
+
+SmpcController::~SmpcController() {
+    if (ownsObjects) {
+        delete ptrMyEngine;
+        delete ptrMyForecaster;
+        delete ptrMySmpcConfig;
+    }
+}
+
+void SmpcController::refreshDevicePointers() {
+    rn_handle *h = ptrMyEngine->handle();
+    auto get = [&](rn_buffer_id id) {
+        void *p = nullptr;
+        size_t bytes = 0;
+        check(rn_buffer(h, id, &p, &bytes), "rn_buffer");
+        return static_cast<real_t *>(p);
+    };
+    devVecX = get(RN_BUF_VEC_X); devVecU = get(RN_BUF_VEC_U); devVecV = get(RN_BUF_VEC_V);
+    devVecXi = get(RN_BUF_VEC_XI); devVecPsi = get(RN_BUF_VEC_PSI);
+    devVecAcceleratedXi = get(RN_BUF_VEC_ACCEL_XI); devVecAcceleratedPsi = get(RN_BUF_VEC_ACCEL_PSI);
+    devVecPrimalXi = get(RN_BUF_VEC_PRIMAL_XI); devVecPrimalPsi = get(RN_BUF_VEC_PRIMAL_PSI);
+    devVecDualXi = get(RN_BUF_VEC_DUAL_XI); devVecDualPsi = get(RN_BUF_VEC_DUAL_PSI);
+    devVecUpdateXi = get(RN_BUF_VEC_UPDATE_XI); devVecUpdatePsi = get(RN_BUF_VEC_UPDATE_PSI);
+    devVecFixedPointResidualXi = get(RN_BUF_VEC_RESIDUAL_XI); devVecFixedPointResidualPsi = get(RN_BUF_VEC_RESIDUAL_PSI);
+    devControlAction = get(RN_BUF_CONTROL_ACTION); devStateUpdate = get(RN_BUF_STATE_UPDATE);
+}
+
+void SmpcController::initialiseSmpcController() {
+    factorStepFlag = true;
+    ptrMyEngine->factorStep();
+    ptrMyEngine->updateStateControl(ptrMySmpcConfig->getCurrentX(), ptrMySmpcConfig->getPrevU(), ptrMySmpcConfig->getPrevDemand());
+    ptrMyEngine->eliminateInputDistubanceCoupling(ptrMyForecaster->getNominalDemand(), ptrMyForecaster->getNominalPrices());
+    refreshDevicePointers();
+}
+
+void SmpcController::initialiseAlgorithm() {
+    check(rn_apg_init(ptrMyEngine->handle()), "SmpcController::initialiseAlgorithm");
+    refreshDevicePointers();
+}
+
+void SmpcController::dualExtrapolationStep(real_t lambda) {
+    check(rn_step(ptrMyEngine->handle(), RN_STEP_EXTRAPOLATE, lambda), "SmpcController::dualExtrapolationStep");
+}
+void SmpcController::solveStep() { check(rn_step(ptrMyEngine->handle(), RN_STEP_SOLVE, 0.f), "SmpcController::solveStep"); }
+void SmpcController::proximalFunG() { check(rn_step(ptrMyEngine->handle(), RN_STEP_PROX, 0.f), "SmpcController::proximalFunG"); }
+void SmpcController::computeFixedPointResidual() {
+    check(rn_step(ptrMyEngine->handle(), RN_STEP_RESIDUAL, 0.f), "SmpcController::computeFixedPointResidual");
+}
+void SmpcController::dualUpdate() { check(rn_step(ptrMyEngine->handle(), RN_STEP_DUAL_UPDATE, 0.f), "SmpcController::dualUpdate"); }
+
+uint_t SmpcController::algorithmApg() {
+    const uint_t iters = ptrMySmpcConfig->getMaxIterations();
+    check(rn_apg_solve(ptrMyEngine->handle(), iters, nullptr, vecPrimalInfs.data()), "SmpcController::algorithmApg");
+    refreshDevicePointers();
+    return 1;
+}
+
+void SmpcController::controllerSmpc() {
+    ptrMyEngine->updateStateControl(ptrMySmpcConfig->getCurrentX(), ptrMySmpcConfig->getPrevU(), ptrMySmpcConfig->getPrevDemand());
+    ptrMyEngine->eliminateInputDistubanceCoupling(ptrMyForecaster->getNominalDemand(), ptrMyForecaster->getNominalPrices());
+    algorithmApg();
+}
+
+uint_t SmpcController::controlAction(real_t *u) {
+    check(rn_control_action(ptrMyEngine->handle(), ptrMySmpcConfig->getCurrentX(), ptrMySmpcConfig->getPrevU(),
+                            ptrMySmpcConfig->getPrevDemand(), ptrMyForecaster->getNominalDemand(),
+                            ptrMyForecaster->getNominalPrices(), ptrMySmpcConfig->getMaxIterations(), /*clamp=*/0, u),
+          "SmpcController::controlAction");
+    refreshDevicePointers();
+    return 1;   // the reference returns 0 only when cudaMemGetInfo sees a leak (:1619-1624); nothing is allocated here
+}
+
+uint_t SmpcController::controlAction(std::fstream &controlOutputJson) {
+    if (!controlOutputJson.is_open()) return 0;
+    const uint_t nu = ptrMySmpcConfig->getNU();
+    std::vector<real_t> currentControl(nu);
+    check(rn_control_action(ptrMyEngine->handle(), ptrMySmpcConfig->getCurrentX(), ptrMySmpcConfig->getPrevU(),
+                            ptrMySmpcConfig->getPrevDemand(), ptrMyForecaster->getNominalDemand(),
+                            ptrMyForecaster->getNominalPrices(), ptrMySmpcConfig->getMaxIterations(), /*clamp=*/1,
+                            currentControl.data()),
+          "SmpcController::controlAction");
+    refreshDevicePointers();
+    controlOutputJson << "\"control\" : [";   // same pseudo-JSON fragment as the reference (:1651-1658)
+    for (uint_t i = 0; i < nu; i++) controlOutputJson << currentControl[i] << ", ";
+    controlOutputJson << "]" << std::endl;
+    return 1;
+}
+
+void SmpcController::moveForewardInTime() {
+    if (simulatorFlag) {
+        const uint_t nx = ptrMySmpcConfig->getNX(), nu = ptrMySmpcConfig->getNU();
+        std::vector<real_t> stateUpdate(nx), previousControl(nu);
+        check(rn_move_forward(ptrMyEngine->handle(), stateUpdate.data(), previousControl.data()), "SmpcController::moveForewardInTime");
+        updateKpi(stateUpdate.data(), previousControl.data());
+        ptrMySmpcConfig->setCurrentState(stateUpdate.data());
+        ptrMySmpcConfig->setPreviousControl(previousControl.data());
+        ptrMySmpcConfig->setpreviousdemand(ptrMyForecaster->getNominalDemand());
+    } else {
+        ptrMySmpcConfig->setCurrentState();
+        ptrMySmpcConfig->setPreviousControl();
+        ptrMySmpcConfig->setPreviousDemand();
+    }
+}
+
+void SmpcController::updateKpi(real_t *state, real_t *control) {
+    const uint_t nx = ptrMySmpcConfig->getNX(), nu = ptrMySmpcConfig->getNU();
+    real_t *safeX = ptrMyEngine->getDwnNetwork()->getXsafe();
+    real_t *constantPrice = ptrMyEngine->getDwnNetwork()->getAlpha();
+    real_t *variablePrice = ptrMyForecaster->getNominalPrices();
+    real_t *previousControl = ptrMySmpcConfig->getPrevU();
+    const real_t weightEconomic = ptrMySmpcConfig->getWeightEconomical();
+    real_t ecoKpi = 0, smKpi = 0, saKpi = 0, netKpi = 0;
+    for (uint_t i = 0; i < nu; i++) {
+        ecoKpi = ecoKpi + weightEconomic * (constantPrice[i] + variablePrice[i]) * std::fabs(control[i]);
+        const real_t deltaU = previousControl[i] - control[i];
+        smKpi = smKpi + deltaU * deltaU;
+    }
+    for (uint_t i = 0; i < nx; i++) {
+        real_t waterLevel = state[i] - safeX[i];
+        if (waterLevel > 0) waterLevel = 0;
+        saKpi = saKpi + std::fabs(waterLevel);
+        netKpi = netKpi + std::fabs(state[i]);
+    }
+    economicKpi += ecoKpi; smoothKpi += smKpi; safeKpi += saKpi; networkKpi += netKpi;
+}
+
+real_t SmpcController::getEconomicKpi(uint_t simulationTime) { return economicKpi / 3600 / simulationTime; }
+real_t SmpcController::getSmoothKpi(uint_t simulationTime) { return smoothKpi / 3600 / simulationTime; }
+real_t SmpcController::getNetworkKpi(uint_t simulationTime) {
+    real_t safeLevelNorm = 0;
+    const uint_t nx = ptrMySmpcConfig->getNX();
+    for (uint_t i = 0; i < nx; i++) safeLevelNorm += getDwnNetwork()->getXsafe()[i];
+    return 100 * simulationTime * safeLevelNorm / networkKpi;
+}
+real_t SmpcController::getSafetyKpi(uint_t) { return safeKpi; }
+
+}  // namespace rapidnet

@@ -1,0 +1,104 @@
+"""The C++ host facade (rapidnet_b200/host: the reference's six classes over the C ABI) against the reference's own
+test suite, replayed by rapidnet_b200/host/host_tests.cpp:
+  * loaders (CPU): Testing.cu:78-335 -- every getter against a second parse of the JSON
+  * engine / smpc (GPU): Testing.cu:340-531, TestSmpcController.cu:114-398 -- golden vectors, reference tolerances
+  * closedloop (GPU): main.cu:27-69 -- two receding-horizon steps; u0 / next state against the ctypes path
+The golden JSON files are re-created from tests/golden/toy.npz (same keys as engineTest.json / smpcTest.json)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from rapidnet_b200.problem import write_problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "rapidnet_b200", "host", "host_tests")
+
+
+def _build():
+    if not os.path.exists(BIN):
+        subprocess.check_call(["bash", os.path.join(ROOT, "tools", "build_host.sh")], stdout=subprocess.DEVNULL)
+    return BIN
+
+
+def _golden_json(path, d):
+    with open(path, "w") as f:
+        json.dump({k: np.asarray(v, dtype=np.float64).reshape(-1).tolist() for k, v in d.items()}, f)
+    return str(path)
+
+
+def _run(*args, timeout=600):
+    out = subprocess.run([_build(), *map(str, args)], capture_output=True, text=True, timeout=timeout)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    return out.stdout
+
+
+def test_host_library_exports_reference_classes():
+    _build()
+    syms = subprocess.run(["nm", "-DC", os.path.join(ROOT, "rapidnet_b200", "host", "librapidnet_host.so")],
+                          capture_output=True, text=True).stdout
+    for name in ("rapidnet::DwnNetwork::DwnNetwork", "rapidnet::ScenarioTree::getFinalBranchNode", "rapidnet::Forecaster::predictDemand",
+                 "rapidnet::SmpcConfiguration::setpreviousdemand", "rapidnet::Engine::factorStep",
+                 "rapidnet::Engine::eliminateInputDistubanceCoupling", "rapidnet::SmpcController::controlAction",
+                 "rapidnet::SmpcController::moveForewardInTime", "rapidnet::SmpcController::algorithmApg",
+                 "rapidnet::SmpcController::dualExtrapolationStep", "rapidnet::SmpcController::getEconomicKpi"):
+        assert name in syms, name
+
+
+def test_loaders_cpu(toy, tmp_path):
+    cfg = write_problem(toy[0], str(tmp_path))
+    assert "loaders: ok" in _run("loaders", cfg)
+
+
+def test_loaders_barcelona_cpu(tmp_path):
+    from rapidnet_b200.datagen import named_problem
+    cfg = write_problem(named_problem("C1r6"), str(tmp_path))
+    assert "loaders: ok" in _run("loaders", cfg)
+
+
+def test_missing_file_exits_100(tmp_path):
+    out = subprocess.run([_build(), "loaders", str(tmp_path / "nope.json")], capture_output=True, text=True)
+    assert out.returncode == 100          # the reference's loaders exit(100) (e.g. DwnNetwork.cu:43-50)
+
+
+@pytest.mark.gpu
+def test_engine_golden_gpu(toy, tmp_path):
+    prob, engine, _ = toy
+    cfg = write_problem(prob, str(tmp_path))
+    assert "engine: ok" in _run("engine", cfg, _golden_json(tmp_path / "engineTest.json", engine))
+
+
+@pytest.mark.gpu
+def test_apg_steps_golden_gpu(toy, tmp_path):
+    prob, engine, smpc = toy
+    cfg = write_problem(prob, str(tmp_path))
+    assert "smpc: ok" in _run("smpc", cfg, _golden_json(tmp_path / "engineTest.json", engine),
+                              _golden_json(tmp_path / "smpcTest.json", smpc))
+
+
+@pytest.mark.gpu
+def test_closed_loop_matches_ctypes_path(tmp_path):
+    """main.cu's closed loop through the C++ classes == the same calls through the ctypes binding (bit-identical: both
+    sit on the same C ABI), and the plant update is x+ = x + B u0_clamped."""
+    from rapidnet_b200 import cabi
+    from rapidnet_b200.datagen import named_problem
+    prob = named_problem("C1", max_iter=40)
+    cfg = write_problem(prob, str(tmp_path))
+    out = tmp_path / "loop.json"
+    _run("closedloop", cfg, 2, out)
+    res = json.load(open(out))
+    c, fc = prob.config, prob.forecast
+    s = cabi.Solver(prob)
+    s.factor_step()
+    x, up, dp = c.current_x.copy(), c.prev_u.copy(), c.prev_demand.copy()
+    for t in range(2):
+        u0 = s.control_action(x, up, dp, fc.demand[t], fc.prices[t], 40)
+        assert np.array_equal(np.float32(res["steps"][t]["u0"]), u0)
+        s.control_action(x, up, dp, fc.demand[t], fc.prices[t], 40, clamp=True)
+        xn, ua = s.move_forward()
+        assert np.allclose(np.float32(res["steps"][t]["x_next"]), xn, rtol=1e-6, atol=1e-4)
+        x, up, dp = xn, ua, fc.demand[t][: prob.network.nd].astype(np.float32)
+    assert np.isfinite(res["economic_kpi"]) and res["steps"][0]["ms"] > 0
+    s.close()
