@@ -97,8 +97,9 @@ struct Handle {
 
     // persistent cooperative kernel
     float *part[4] = {nullptr, nullptr, nullptr, nullptr};   // D xi_w, F psi_w, Phi xi_w, Psi psi_w
-    float *LV = nullptr, *qh = nullptr, *rh = nullptr, *sweep_pack = nullptr;
-    int *crown_rng = nullptr;
+    float *qh = nullptr, *rh = nullptr, *sweep_pack = nullptr;
+    float *cm_c = nullptr, *cm_lv = nullptr, *cm_beta = nullptr, *cm_uhat = nullptr, *cm_e = nullptr;   // chain-major arrays
+    int *crown_rng = nullptr, *pos_dev = nullptr;
     unsigned int *grid_bar = nullptr;
     unsigned long long *phase_ns = nullptr;
     bool persist_ready = false;

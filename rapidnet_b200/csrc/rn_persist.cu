@@ -36,9 +36,8 @@ namespace rn {
 
 constexpr int kPC = 512;                        // threads per CTA: 16 warps -> 128 registers per thread
 constexpr int kPT = kPC;                        // phase S roles: 11 GEMV warps, 4 element-wise warps, 1 loader warp
-constexpr int kPStages = 6;
-constexpr int kPStageFloats = 4096;
-constexpr int kPStageStride = kPStageFloats + 32;
+constexpr int kPStages = 8;                     // most ring stages (mbarrier slots); the launch picks n_stages x stage_stride
+constexpr int kPStageMinFloats = 4096;          // smallest stage payload (16 KB)
 constexpr int kGemvWarps = 11;                  // phase S: warps that multiply the streamed matrices
 constexpr int kEwWarps = 4;                     // phase S: warps that run the fused element-wise pass
 constexpr int kLoaderWarp = kGemvWarps + kEwWarps;   // phase S: the warp that drives the TMA ring and the vector ring
@@ -53,16 +52,21 @@ constexpr int kDimMax = 128;                    // max(2nx, nu, nv) supported by
 
 struct PArgs {
     const int *parent, *child_first, *child_count, *omega_idx, *cum, *stages;
+    const int *pos;                             // [nodes] chain-major row of a node (crown: its id; chain j, stage s: n_crown + j T + s)
     const int *crown_rng;                       // [n_crown][kMaxCs + 1][2]: descendant id range of a crown node per stage
     int N, cs, K, nodes, n_crown, n_mats, df_mode, iters, nx, nu, nv, cols_per_chunk, clock_cta;
+    int n_stages, stage_stride;                 // matrix ring: stages and floats per stage (payload + 32 floats of slack)
     const float *mat[4];                        // D, F, Phi, Psi (packed per node, Engine.cu:201-207)
-    const float *pack;                          // G | OmegaBar ThetaBar | L | B, each padded to 16 B (sweeps)
+    const float *pack;                          // G | OmegaBar | L | B, each padded to 16 B (sweeps)
+    int nxp, nup, nvp;                          // row lengths of the chain-major arrays (nx, nu, nv rounded up to 4 floats)
+    float *cm_c, *cm_lv;                        // chain-major: c = sysF' xi_w [nodes][nxp], L v [nodes][nup]
+    const float *cm_beta, *cm_uhat, *cm_e;      // chain-major copies of beta, uhat, e (refreshed at every launch)
     const float *diag, *prob;
     const float *beta, *uhat, *e, *xcur, *uprev, *uhat_prev, *sxmin, *sxmax, *sxs, *sumin, *sumax;
     float *Yxi[2], *Ypsi[2], *Wxi[2], *Wpsi[2];
     float *pri_xi, *pri_psi, *dual_xi, *dual_psi;
-    float *part[4];                             // D xi_w, F psi_w, Phi xi_w, Psi psi_w   [nodes*nv] each
-    float *c, *qh, *rh, *sigma, *V, *U, *X, *LV; // qh, rh: q and r of the chain heads  [K*nx], [K*nv]
+    float *part[4];                             // D xi_w, F psi_w, Phi xi_w, Psi psi_w   chain-major [nodes][nvp] each
+    float *qh, *rh, *V, *U, *X;                 // qh, rh: q and r of the chain heads  [K*nx], [K*nv]
     double *dist_part;                          // [2*grid]
     float *pinf, *pinf_part;                    // [iters], [grid*6]
     const float *lambda_tab;
@@ -71,14 +75,15 @@ struct PArgs {
     unsigned long long *phase_ns;               // [32] fine-grained phase clock of one CTA (see cabi.PHASE_NAMES)
     float step, inv_step, pen_x, pen_xs;
     // sweep shared-memory layout (float offsets from the dynamic shared-memory base) and the pack's pieces
-    int oG, oOT, oL, oB, oX1, oY, oV, oScr2;
-    unsigned int bG, bOT, bL, bB;               // bytes of the four bulk copies
-    int pG, pOT, pL, pB;                        // float offsets inside the pack
+    int oG, oOm, oL, oX1, oY, oV, oScr2, oStg;
+    unsigned int bG, bOm, bL, bB;               // bytes of the four bulk copies
+    int pG, pOm, pL, pB;                        // float offsets inside the pack
 };
 
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kPC) : "memory"); }
 __device__ __forceinline__ void ewbar() { asm volatile("bar.sync 2, %0;" ::"n"(kEwWarps * 32) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     unsigned int v;
@@ -90,13 +95,17 @@ __device__ __forceinline__ unsigned long long globaltimer() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// fine-grained clock of one CTA (thread 0): accumulates the time since the previous stamp into phase_ns[idx]
-__device__ unsigned long long g_t_prev;
+// fine-grained clock of one CTA (thread 0): accumulates the time since the previous stamp into a shared-memory slot
+// (flushed to phase_ns at the end of the kernel; a global read-modify-write per stamp would cost a microsecond each)
+__device__ __forceinline__ unsigned long long *clk_smem();
 __device__ __forceinline__ void dstamp(const PArgs &P, int idx) {
-    if (blockIdx.x == P.clock_cta && threadIdx.x == 0) {
-        const unsigned long long now = globaltimer();
-        P.phase_ns[idx] += now - g_t_prev;
-        g_t_prev = now;
+    if (threadIdx.x == 0) {
+        unsigned long long *c = clk_smem();
+        if (c[33]) {   // this CTA is the clock CTA
+            const unsigned long long now = globaltimer();
+            c[idx] += now - c[32];
+            c[32] = now;
+        }
     }
 }
 __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) {
@@ -128,55 +137,107 @@ constexpr int kOffScr = 0;                                              // kPC f
 constexpr int kOffDsh = kOffScr + kPC;                                  // 2 x 16 doubles
 constexpr int kOffCsh = kOffDsh + 2 * 2 * (kPC / 32);                   // 2 x 16 candidates (3 words each)
 constexpr int kOffSd = kOffCsh + 3 * 2 * (kPC / 32);                    // d1, d2
-constexpr int kOffMisc = kOffSd + 4;                                    // 64 ints: column -> node map etc.
-constexpr int kOffBar = kOffMisc + 64;                                  // mbarriers
-constexpr int kNumBars = 2 * kPStages + 2 * kVecSlots + 8 + 4;
-constexpr int kOffRing = (kOffBar + 2 * kNumBars + 31) & ~31;           // 128-byte aligned: TMA destination
-constexpr int kOffVec = kOffRing + kPStages * kPStageStride;            // kVecSlots x kVecCount x kVStride
+constexpr int kOffMisc = kOffSd + 4;                                    // 4 x kTP words: column -> row / node maps etc.
+constexpr int kOffClk = (kOffMisc + 4 * kTP + 1) & ~1;                   // 34 x u64: phase clock accumulators, t_prev, enabled
+constexpr int kOffPArgs = kOffClk + 2 * 34;                            // a copy of the kernel arguments (see k_apg_persistent)
+constexpr int kPArgsWords = 256;
+constexpr int kOffBar = kOffPArgs + kPArgsWords;                                  // mbarriers
+constexpr int kNumBars = 2 * kPStages + 2 * kVecSlots + 8 + 8;
+constexpr int kOffVec = (kOffBar + 2 * kNumBars + 31) & ~31;            // kVecSlots x kVecCount x kVStride
 constexpr int kOffW = kOffVec + kVecSlots * kVecCount * kVStride;       // 2 x kWStride  (xi part | psi part)
 constexpr int kOffRed = kOffW + 2 * kWStride;                           // 2 x kGemvWarps x kDimMax
-constexpr int kStreamEnd = kOffRed + 2 * kGemvWarps * kDimMax;
-constexpr int kOffSweep = kOffRing;                                     // the sweep region starts where the ring starts
+constexpr int kOffRing = kOffRed + 2 * kGemvWarps * kDimMax;            // 128-byte aligned: TMA destination; runtime size
+constexpr int kOffSweep = kOffVec;                                      // the sweep region starts where the stream region starts
+static_assert(kOffRing % 32 == 0, "ring must be 128-byte aligned");
 static_assert(kOffDsh % 2 == 0 && kOffBar % 2 == 0, "8-byte alignment of the double / mbarrier areas");
 
 __device__ __forceinline__ float *smem_f(int off) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     return reinterpret_cast<float *>(smem_raw) + off;
 }
+__device__ __forceinline__ unsigned long long *clk_smem() { return reinterpret_cast<unsigned long long *>(smem_f(kOffClk)); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // sweeps.  A "tile" is up to kTP columns that go through the same shared matrices: the stages of one chain
-// (column s = stage cs + s of scenario j) or up to kTP crown nodes.  Column arrays in shared memory are
-// [element][kTP] (row = 96 bytes, read and written as float4).  Every step is a small non-inlined function so
-// that none of them is register-critical for the whole kernel.
+// (column s = stage cs + s of scenario j) or a few crown nodes.  Column arrays in shared memory are [element][kTP]
+// (row = 96 bytes, read and written as float4).  The per-node operands of a chain (c, beta, the four partial products,
+// uhat, L v, e) live in "chain-major" private arrays -- row pos(node), rows of one chain contiguous, row length padded to
+// 16 bytes -- so that ONE bulk TMA copy per array brings a chain's block into the staging area, issued a chain ahead.
+// Every step is a small non-inlined function so that none of them is register-critical for the whole kernel; each one
+// reads what it needs from P into locals first (P sits behind a generic pointer there: a global store would otherwise
+// force a re-read).
 // ---------------------------------------------------------------------------------------------------------------
 struct SweepSmem {
-    float *G, *OT, *L, *B;      // shared matrices (bulk TMA copies of the pack)
-    float *X1, *Y, *V, *scr2;   // column arrays: X1 [(nv+nx) or nu rows], Y [max(nv,nu) rows], V [nv rows], scr2 [128 rows]
-    int *colnode;               // [kTP] node id of each column
-    float *colp;                // [kTP] probability that scales the column's Omega / Theta (Engine.cu:210-221)
+    float *G, *Om, *L, *B;      // shared matrices (bulk TMA copies of the pack); B overlays G (backward / forward)
+    float *X1, *Y, *V, *scr2;   // column arrays: X1 [q_bar rows | sigma rows] or [nu rows], Y [max(nv,nu) rows], V [nv rows]
+    float *stg;                 // staging area of the chain blocks
+    int *colnode;               // [kTP] chain-major row of each column
+    int *colid;                 // [kTP] node id of each column
+    float *colp;                // [kTP] probability that scales the column's Omega (Engine.cu:210-221)
     int *anc;                   // [kMaxCs] crown path of the current chain, root first
-    uint64_t *mfull;            // [4] mbarriers of the four matrix copies
+    uint64_t *mfull;            // [4] mbarriers of the matrix copies: G, OmegaBar, L, B
+    uint64_t *sfull;            // [4] mbarriers of the staging copies: c | beta, D xi, F psi | Phi xi, Psi psi | uhat, L v, e
 };
 __device__ __forceinline__ SweepSmem sweep_smem(const PArgs &P) {
     SweepSmem S;
-    S.G = smem_f(P.oG); S.OT = smem_f(P.oOT); S.L = smem_f(P.oL); S.B = smem_f(P.oB);
-    S.X1 = smem_f(P.oX1); S.Y = smem_f(P.oY); S.V = smem_f(P.oV); S.scr2 = smem_f(P.oScr2);
+    S.G = smem_f(P.oG); S.Om = smem_f(P.oOm); S.L = smem_f(P.oL); S.B = smem_f(P.oG);
+    S.X1 = smem_f(P.oX1); S.Y = smem_f(P.oY); S.V = smem_f(P.oV); S.scr2 = smem_f(P.oScr2); S.stg = smem_f(P.oStg);
     S.colnode = reinterpret_cast<int *>(smem_f(kOffMisc));
-    S.colp = smem_f(kOffMisc + kTP);
-    S.anc = reinterpret_cast<int *>(smem_f(kOffMisc + 2 * kTP));
-    S.mfull = reinterpret_cast<uint64_t *>(smem_f(kOffBar)) + (kNumBars - 4);
+    S.colid = reinterpret_cast<int *>(smem_f(kOffMisc + kTP));
+    S.colp = smem_f(kOffMisc + 2 * kTP);
+    S.anc = reinterpret_cast<int *>(smem_f(kOffMisc + 3 * kTP));
+    S.mfull = reinterpret_cast<uint64_t *>(smem_f(kOffBar)) + (kNumBars - 8);
+    S.sfull = S.mfull + 4;
     return S;
 }
+struct StagePhase { uint32_t c, r, v, f; };   // parities of the staging mbarriers (every thread tracks them)
 
-// one thread: pull G, [OmegaBar | ThetaBar], L, B into the sweep region (it overlays the idle stream ring)
+// one thread: pull G, OmegaBar, L into the sweep region (it overlays the idle stream ring)
 __device__ __forceinline__ void issue_matrix_loads(const PArgs &P) {
     const SweepSmem S = sweep_smem(P);
-    fence_proxy_async();   // the region was last written through the generic proxy (vector ring, w, partial sums)
+    fence_proxy_async_all();   // the region was last written through the generic proxy (vector ring, w, partial sums)
     mbar_expect_tx(&S.mfull[0], P.bG); bulk_g2s(S.G, P.pack + P.pG, P.bG, &S.mfull[0]);
-    mbar_expect_tx(&S.mfull[1], P.bOT); bulk_g2s(S.OT, P.pack + P.pOT, P.bOT, &S.mfull[1]);
+    mbar_expect_tx(&S.mfull[1], P.bOm); bulk_g2s(S.Om, P.pack + P.pOm, P.bOm, &S.mfull[1]);
     mbar_expect_tx(&S.mfull[2], P.bL); bulk_g2s(S.L, P.pack + P.pL, P.bL, &S.mfull[2]);
+}
+// one thread, after the last use of G in this iteration: B takes G's place
+__device__ __forceinline__ void issue_b_load(const PArgs &P) {
+    const SweepSmem S = sweep_smem(P);
+    fence_proxy_async_all();
     mbar_expect_tx(&S.mfull[3], P.bB); bulk_g2s(S.B, P.pack + P.pB, P.bB, &S.mfull[3]);
+}
+// one thread: the backward operand blocks of chain j -> staging.  Staging layout (floats): c | beta | p0 | p1 | p2 | p3
+__device__ __forceinline__ void issue_chain_backward_loads(const PArgs &P, int j) {
+    const SweepSmem S = sweep_smem(P);
+    const int T = P.N - P.cs;
+    const size_t row0 = (size_t)P.n_crown + (size_t)j * T;
+    const uint32_t bx = (uint32_t)(T * P.nxp * 4), bv = (uint32_t)(T * P.nvp * 4);
+    float *d = S.stg;
+    fence_proxy_async_all();   // the blocks were written with ordinary stores (phase S of other CTAs, before the barrier)
+    mbar_expect_tx(&S.sfull[0], bx);
+    bulk_g2s(d, P.cm_c + row0 * P.nxp, bx, &S.sfull[0]); d += T * P.nxp;
+    mbar_expect_tx(&S.sfull[1], 3 * bv);
+    bulk_g2s(d, P.cm_beta + row0 * P.nvp, bv, &S.sfull[1]); d += T * P.nvp;
+    bulk_g2s(d, P.part[0] + row0 * P.nvp, bv, &S.sfull[1]); d += T * P.nvp;
+    bulk_g2s(d, P.part[1] + row0 * P.nvp, bv, &S.sfull[1]); d += T * P.nvp;
+    if (!P.df_mode) {
+        mbar_expect_tx(&S.sfull[2], 2 * bv);
+        bulk_g2s(d, P.part[2] + row0 * P.nvp, bv, &S.sfull[2]); d += T * P.nvp;
+        bulk_g2s(d, P.part[3] + row0 * P.nvp, bv, &S.sfull[2]);
+    }
+}
+// one thread: the forward operand blocks of chain j -> staging.  Layout: uhat | L v | e
+__device__ __forceinline__ void issue_chain_forward_loads(const PArgs &P, int j) {
+    const SweepSmem S = sweep_smem(P);
+    const int T = P.N - P.cs;
+    const size_t row0 = (size_t)P.n_crown + (size_t)j * T;
+    const uint32_t bx = (uint32_t)(T * P.nxp * 4), bu = (uint32_t)(T * P.nup * 4);
+    float *d = S.stg;
+    fence_proxy_async_all();
+    mbar_expect_tx(&S.sfull[3], 2 * bu + bx);
+    bulk_g2s(d, P.cm_uhat + row0 * P.nup, bu, &S.sfull[3]); d += T * P.nup;
+    bulk_g2s(d, P.cm_lv + row0 * P.nup, bu, &S.sfull[3]); d += T * P.nup;
+    bulk_g2s(d, P.cm_e + row0 * P.nxp, bx, &S.sfull[3]);
 }
 
 __device__ __forceinline__ void row_load(const float *row, float (&v)[kTP]) {
@@ -244,83 +305,72 @@ __device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float
     cbar();
 }
 
+// all threads: dst[row(col)*ld + e] = src[e][col] for col < ncols, e < dim (rows from `rows`: node ids or chain-major rows)
+__device__ __forceinline__ void cols_to_global(const float *src, const int *rows, int ncols, int dim, int ld, float *__restrict__ dst) {
+    const int e = threadIdx.x & 127, s0 = threadIdx.x >> 7;
+    if (e >= dim) return;
+#pragma unroll
+    for (int k = 0; k < kTP / 4; k++) {
+        const int s = s0 + 4 * k;
+        if (s < ncols) dst[(size_t)rows[s] * ld + e] = src[e * kTP + s];
+    }
+}
+
 __device__ __forceinline__ bool stage_branches(const int *__restrict__ cum, int s) {   // more nodes than the stage above (:699-719)
     return s > 0 && (__ldg(cum + s + 1) - __ldg(cum + s)) > (__ldg(cum + s) - __ldg(cum + s - 1));
 }
 
-// the read-only inputs of the forward recursion, read out of P once per step
-struct FwdIn { const float *uprev, *uhat_prev, *uhat, *LV; const int *cum; int nu; };
-__device__ __forceinline__ FwdIn fwd_in(const PArgs &P) { return FwdIn{P.uprev, P.uhat_prev, P.uhat, P.LV, P.cum, P.nu}; }
-
-// v = ((-1/2 Omega sigma + Theta q_bar) + Psi psi) + Phi xi (:604-627) [df: v = -1/2 Omega r] for every column:
-// Y = [OmegaBar | ThetaBar] X1 on entry; Omega_i = OmegaBar / p_i.  V (shared, next GEMM's input) and devVecV.
-__device__ __noinline__ void sweep_vcombine(const PArgs &P, int ncols) {
+// v = ((-1/2 Omega sigma + Theta q_bar) + Psi psi) + Phi xi (:604-627), with Theta q_bar = -1/2 Omega (G q_bar) (Theta is
+// -1/2 Omega Bbar', Engine.cu:729-734) [df: v = -1/2 Omega r]: Y = OmegaBar X1s on entry, Omega_i = OmegaBar / p_i.
+// p2 / p3: Phi xi, Psi psi of the tile's columns, [col][nvp] in staging (chains) or read from the chain-major arrays
+__device__ __noinline__ void sweep_vcombine(const PArgs &P, int ncols, bool staged) {
     const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, nv = P.nv;
+    const int e = threadIdx.x, nv = P.nv, nvp = P.nvp;
     if (e >= nv) return;
-    // every field of P is read into a local first: P lives behind a generic pointer here, so a global store in the
-    // loop would otherwise force it to be re-read (same in all the sweep steps below)
     const bool df = P.df_mode != 0;
-    const float *__restrict__ p3 = P.part[3], *__restrict__ p2 = P.part[2];
-    float *__restrict__ Vg = P.V;
-    float y[kTP], b2[kTP], b3[kTP], cp[kTP];
-    int cn[kTP];
+    const int T = P.N - P.cs;
+    const float *__restrict__ g2 = P.part[2], *__restrict__ g3 = P.part[3];
+    const float *s2 = S.stg + T * P.nxp + 3 * T * nvp, *s3 = s2 + T * nvp;
+    float y[kTP];
     row_load(S.Y + e * kTP, y);
-    row_load(S.colp, cp);
-#pragma unroll
-    for (int s = 0; s < kTP; s++) cn[s] = S.colnode[s];
-    if (!df) {
-#pragma unroll
-        for (int s = 0; s < kTP; s++)
-            if (s < ncols) {
-                const size_t idx = (size_t)cn[s] * nv + e;
-                b3[s] = __ldcg(p3 + idx); b2[s] = __ldcg(p2 + idx);
-            }
-    }
 #pragma unroll
     for (int s = 0; s < kTP; s++) {
         float v = 0.f;
         if (s < ncols) {
-            v = y[s] / cp[s];
-            if (!df) v = (v + b3[s]) + b2[s];
-            Vg[(size_t)cn[s] * nv + e] = v;
+            v = y[s] / S.colp[s];
+            if (!df) {
+                const float b3 = staged ? s3[s * nvp + e] : __ldcg(g3 + (size_t)S.colnode[s] * nvp + e);
+                const float b2 = staged ? s2[s * nvp + e] : __ldcg(g2 + (size_t)S.colnode[s] * nvp + e);
+                v = (v + b3) + b2;
+            }
         }
         y[s] = v;
     }
     row_store(S.V + e * kTP, y);
 }
 
-// rows of Y -> dst[node(col)*dim + e]
-__device__ __noinline__ void sweep_cols_out(const PArgs &P, int ncols, float *__restrict__ dst, int dim) {
+// common end of the backward sweep of a tile: X1s = -1/2 (sigma + G q_bar) (df: -1/2 r) on entry
+__device__ __noinline__ void sweep_backward_finish(const PArgs &P, int ncols, bool staged, uint32_t mpar, StagePhase &ph, int next_chain) {
     const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x;
-    if (e >= dim) return;
-    float y[kTP];
-    int cn[kTP];
-    row_load(S.Y + e * kTP, y);
-#pragma unroll
-    for (int s = 0; s < kTP; s++) cn[s] = S.colnode[s];
-#pragma unroll
-    for (int s = 0; s < kTP; s++)
-        if (s < ncols) dst[(size_t)cn[s] * dim + e] = y[s];
-}
-
-// common end of the backward sweep of a tile: X1 = [-1/2 sigma ; q_bar] (df: -1/2 r) on entry; mpar = parity of the
-// matrix mbarriers in this iteration
-__device__ __noinline__ void sweep_backward_finish(const PArgs &P, int ncols, uint32_t mpar, int stamp0) {
-    const SweepSmem S = sweep_smem(P);
+    const int nv = P.nv, nu = P.nu;
+    float *Vg = P.V, *LVg = P.cm_lv;
+    const int nup = P.nup;
     mbar_wait(&S.mfull[1], mpar);
-    tile_gemm(S.OT, P.nv, P.df_mode ? P.nv : P.nv + P.nx, S.X1, S.Y, S.scr2);   // -1/2 OmegaBar sigma + ThetaBar q_bar
-    dstamp(P, stamp0);
-    sweep_vcombine(P, ncols);
+    tile_gemm(S.Om, nv, nv, S.X1 + P.nx * kTP, S.Y, S.scr2);                      // OmegaBar (sigma + G q_bar) (-1/2 folded in)
+    dstamp(P, 6);
+    if (staged && !P.df_mode) { mbar_wait(&S.sfull[2], ph.v); ph.v ^= 1; }
+    sweep_vcombine(P, ncols, staged);
     cbar();
-    dstamp(P, stamp0 + 1);
+    // the staging area is free: request the next chain's blocks, they land while L v is formed and written
+    if (next_chain >= 0 && threadIdx.x == 0) issue_chain_backward_loads(P, next_chain);
+    cols_to_global(S.V, S.colid, ncols, nv, nv, Vg);                             // devVecV
+    dstamp(P, 7);
     mbar_wait(&S.mfull[2], mpar);
-    tile_gemm(S.L, P.nu, P.nv, S.V, S.Y, S.scr2);                                // L v   (:701, :727)
-    dstamp(P, stamp0 + 2);
-    sweep_cols_out(P, ncols, P.LV, P.nu);
+    tile_gemm(S.L, nu, nv, S.V, S.Y, S.scr2);                                    // L v   (:701, :727)
+    dstamp(P, 8);
+    cols_to_global(S.Y, S.colnode, ncols, nu, nup, LVg);
     cbar();
-    dstamp(P, stamp0 + 3);
+    dstamp(P, 9);
 }
 
 // ---- chains ------------------------------------------------------------------------------------------------------
@@ -330,7 +380,8 @@ __device__ __forceinline__ void chain_columns(const PArgs &P, int j) {
     const int t = threadIdx.x, T = P.N - P.cs;
     if (t < kTP) {
         const int node = t < T ? __ldg(P.cum + P.cs + t) + j : 0;
-        S.colnode[t] = node;
+        S.colid[t] = node;
+        S.colnode[t] = t < T ? P.n_crown + j * T + t : 0;
         S.colp[t] = t < T ? __ldg(P.prob + __ldg(P.omega_idx + node)) : 1.f;
     }
     if (t == 32) {
@@ -340,17 +391,16 @@ __device__ __forceinline__ void chain_columns(const PArgs &P, int j) {
     cbar();
 }
 
-// q-scan: q = c + q_child (:651-658).  X1 rows nv.. get q_bar (q of the child, 0 at the leaf); head q -> qh[j]
+// q-scan: q = c + q_child (:651-658).  X1 rows 0..nx-1 get q_bar (q of the child, 0 at the leaf); head q -> qh[j]
 __device__ __noinline__ void chain_qscan(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, T = P.N - P.cs, nx = P.nx;
+    const int e = threadIdx.x, T = P.N - P.cs, nx = P.nx, nxp = P.nxp;
     if (e >= nx) return;
-    const float *__restrict__ cg = P.c;
     float *__restrict__ qh = P.qh;
-    float *xrow = S.X1 + (P.nv + e) * kTP;
+    const float *cs_ = S.stg;
     float cv[kTP];
 #pragma unroll
-    for (int s = 0; s < kTP; s++) cv[s] = s < T ? __ldcg(cg + (size_t)S.colnode[s] * nx + e) : 0.f;
+    for (int s = 0; s < kTP; s++) cv[s] = s < T ? cs_[s * nxp + e] : 0.f;
     float qrun = 0.f;
 #pragma unroll
     for (int s = kTP - 1; s >= 0; s--) {
@@ -358,79 +408,73 @@ __device__ __noinline__ void chain_qscan(const PArgs &P, int j) {
         cv[s] = s < T ? qrun : 0.f;
         if (s < T) qrun = c + qrun;
     }
-    row_store(xrow, cv);
+    row_store(S.X1 + e * kTP, cv);
     qh[(size_t)j * nx + e] = qrun;
 }
 
 // r-scan: sigma = beta + r_child (:599); r = ((sigma + D xi) + F psi) + G q_bar (:631-646).  Y = G q_bar on entry.
-// X1 rows 0..nv-1 get -1/2 sigma (df: -1/2 r); sigma -> devMatSigma; head r -> rh[j]
+// X1 rows nx.. get -1/2 (sigma + G q_bar) (df: -1/2 r); head r -> rh[j]
 __device__ __noinline__ void chain_rscan(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, T = P.N - P.cs, nv = P.nv;
+    const int e = threadIdx.x, T = P.N - P.cs, nv = P.nv, nvp = P.nvp;
     if (e >= nv) return;
     const bool df = P.df_mode != 0;
-    const float *__restrict__ bg = P.beta, *__restrict__ p0 = P.part[0], *__restrict__ p1 = P.part[1];
-    float *__restrict__ sig = P.sigma, *__restrict__ rh = P.rh;
+    float *__restrict__ rh = P.rh;
+    const float *sb = S.stg + T * P.nxp, *s0 = sb + T * nvp, *s1 = s0 + T * nvp;
     float y[kTP];
-    int cn[kTP];
     row_load(S.Y + e * kTP, y);
-#pragma unroll
-    for (int s = 0; s < kTP; s++) cn[s] = S.colnode[s];
     float rrun = 0.f;
 #pragma unroll
-    for (int hb = 1; hb >= 0; hb--) {       // two halves of 12 stages: bounds the registers held by the loads
-        float be[12], a0[12], a1[12];
-#pragma unroll
-        for (int k = 0; k < 12; k++) {
-            const int s = hb * 12 + k;
-            if (s < T) {
-                const size_t idx = (size_t)cn[s] * nv + e;
-                be[k] = __ldg(bg + idx); a0[k] = __ldcg(p0 + idx); a1[k] = __ldcg(p1 + idx);
-            }
+    for (int s = kTP - 1; s >= 0; s--) {
+        float out = 0.f;
+        if (s < T) {
+            const float sg = sb[s * nvp + e] + rrun;
+            rrun = ((sg + s0[s * nvp + e]) + s1[s * nvp + e]) + y[s];
+            out = -0.5f * (df ? rrun : sg + y[s]);
         }
-#pragma unroll
-        for (int k = 11; k >= 0; k--) {
-            const int s = hb * 12 + k;
-            float out = 0.f;
-            if (s < T) {
-                const float sg = be[k] + rrun;
-                rrun = ((sg + a0[k]) + a1[k]) + y[s];
-                sig[(size_t)cn[s] * nv + e] = sg;
-                out = -0.5f * (df ? rrun : sg);
-            }
-            y[s] = out;
-        }
+        y[s] = out;
     }
-    row_store(S.X1 + e * kTP, y);
+    row_store(S.X1 + (P.nx + e) * kTP, y);
     rh[(size_t)j * nv + e] = rrun;
 }
 
-__device__ __noinline__ void chain_backward(const PArgs &P, int j, uint32_t mpar) {
+__device__ __noinline__ void chain_backward(const PArgs &P, int j, int next_chain, uint32_t mpar, StagePhase &ph) {
     const SweepSmem S = sweep_smem(P);
     chain_columns(P, j);
+    mbar_wait(&S.sfull[0], ph.c); ph.c ^= 1;
     chain_qscan(P, j);
     cbar();
     dstamp(P, 3);
     mbar_wait(&S.mfull[0], mpar);
-    tile_gemm(S.G, P.nv, P.nx, S.X1 + P.nv * kTP, S.Y, S.scr2);                  // G q_bar   (:644-646)
+    tile_gemm(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2);                               // G q_bar   (:644-646)
     dstamp(P, 4);
+    mbar_wait(&S.sfull[1], ph.r); ph.r ^= 1;
     chain_rscan(P, j);
     cbar();
     dstamp(P, 5);
-    sweep_backward_finish(P, P.N - P.cs, mpar, 6);
+    sweep_backward_finish(P, P.N - P.cs, true, mpar, ph, next_chain);
 }
 
-// u along the crown path root -> node `last` (reference recursion :683-728, element e): returns u of the last node,
-// adds every u on the path to usum
-__device__ __forceinline__ float path_u(const FwdIn &I, const int *path, int len, int e, float &usum) {
+// the read-only inputs of the forward recursion along a crown path, read out of P once per step
+struct FwdIn { const float *uprev, *uhat_prev, *uhat, *LV; const int *cum; int nup; };
+__device__ __forceinline__ FwdIn fwd_in(const PArgs &P) { return FwdIn{P.uprev, P.uhat_prev, P.cm_uhat, P.cm_lv, P.cum, P.nup}; }
+
+// u along the crown path root -> path[len-1] (reference recursion :683-728, element e): returns u of the last node,
+// adds every u on the path to usum.  Crown nodes sit at row = node id of the chain-major arrays.
+__device__ __forceinline__ float path_u(const FwdIn &I, const int *path, int len, int e, float &usum, float &uh_last) {
+    float uh[kMaxCs], lv[kMaxCs];
+#pragma unroll
+    for (int k = 0; k < kMaxCs; k++)
+        if (k < len) { uh[k] = __ldg(I.uhat + (size_t)path[k] * I.nup + e); lv[k] = __ldcg(I.LV + (size_t)path[k] * I.nup + e); }
     float up = __ldg(I.uprev + e), uhp = __ldg(I.uhat_prev + e);
-    for (int k = 0; k < len; k++) {
-        const int a = path[k];
-        const float uh = __ldg(I.uhat + (size_t)a * I.nu + e), lv = __ldcg(I.LV + (size_t)a * I.nu + e);
-        const float u = stage_branches(I.cum, k) ? (up + -1.f * uhp) + (uh + lv) : ((uh + up) + -1.f * uhp) + lv;
-        usum += u;
-        up = u; uhp = uh;
-    }
+#pragma unroll
+    for (int k = 0; k < kMaxCs; k++)
+        if (k < len) {
+            const float u = stage_branches(I.cum, k) ? (up + -1.f * uhp) + (uh[k] + lv[k]) : ((uh[k] + up) + -1.f * uhp) + lv[k];
+            usum += u;
+            up = u; uhp = uh[k];
+        }
+    uh_last = uhp;
     return up;
 }
 
@@ -439,56 +483,45 @@ __device__ __forceinline__ float path_u(const FwdIn &I, const int *path, int len
 // sum of u over the crown path (for x of the chain's parent)
 __device__ __noinline__ void chain_uscan(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, T = P.N - P.cs, nu = P.nu;
+    const int e = threadIdx.x, T = P.N - P.cs, nu = P.nu, nup = P.nup;
     if (e >= nu) return;
     const FwdIn I = fwd_in(P);
     const int cs = P.cs;
-    float *__restrict__ Ug = P.U;
-    int cn[kTP];
-#pragma unroll
-    for (int s = 0; s < kTP; s++) cn[s] = S.colnode[s];
-    float uh[kTP], lv[kTP];
-#pragma unroll
-    for (int s = 0; s < kTP; s++)
-        if (s < T) {
-            const size_t idx = (size_t)cn[s] * nu + e;
-            uh[s] = __ldg(I.uhat + idx); lv[s] = __ldcg(I.LV + idx);
-        }
-    float usum = 0.f;
-    float up = path_u(I, S.anc, cs, e, usum);
-    float uhp = cs > 0 ? __ldg(I.uhat + (size_t)S.anc[cs - 1] * nu + e) : __ldg(I.uhat_prev + e);
+    const float *su = S.stg, *sl = su + T * nup;
+    float usum = 0.f, uhp;
+    float up = path_u(I, S.anc, cs, e, usum, uhp);
     const bool head_br = stage_branches(I.cum, cs);
+    float out[kTP];
 #pragma unroll
     for (int s = 0; s < kTP; s++) {
         float u = 0.f;
         if (s < T) {
-            u = (s == 0 && head_br) ? (up + -1.f * uhp) + (uh[s] + lv[s]) : ((uh[s] + up) + -1.f * uhp) + lv[s];
-            Ug[(size_t)cn[s] * nu + e] = u;
-            up = u; uhp = uh[s];
+            const float uh = su[s * nup + e], lv = sl[s * nup + e];
+            u = (s == 0 && head_br) ? (up + -1.f * uhp) + (uh + lv) : ((uh + up) + -1.f * uhp) + lv;
+            up = u; uhp = uh;
         } else if (s == T) u = usum;
-        lv[s] = u;
+        out[s] = u;
     }
-    row_store(S.X1 + e * kTP, lv);
+    row_store(S.X1 + e * kTP, out);
 }
 
 // x-scan: x = (x_par + e) + B u (:730-737).  Y = B [u | usum] on entry, Y rows = x on exit
 __device__ __noinline__ void chain_xscan(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, T = P.N - P.cs, nx = P.nx;
+    const int e = threadIdx.x, T = P.N - P.cs, nx = P.nx, nxp = P.nxp;
     if (e >= nx) return;
-    const float *__restrict__ eg = P.e;
-    float *__restrict__ Xg = P.X;
+    const float *__restrict__ eg = P.cm_e;
     const int cs = P.cs;
     const bool head_br = stage_branches(P.cum, cs);
-    float y[kTP], ev[kTP];
-    int cn[kTP];
+    const float *se = S.stg + 2 * T * P.nup;
+    float y[kTP];
     row_load(S.Y + e * kTP, y);
+    float pe[kMaxCs];
 #pragma unroll
-    for (int s = 0; s < kTP; s++) cn[s] = S.colnode[s];
-#pragma unroll
-    for (int s = 0; s < kTP; s++) if (s < T) ev[s] = __ldg(eg + (size_t)cn[s] * nx + e);
+    for (int k = 0; k < kMaxCs; k++) if (k < cs) pe[k] = __ldg(eg + (size_t)S.anc[k] * nxp + e);
     float xrun = __ldg(P.xcur + e);
-    for (int k = 0; k < cs; k++) xrun += __ldg(eg + (size_t)S.anc[k] * nx + e);
+#pragma unroll
+    for (int k = 0; k < kMaxCs; k++) if (k < cs) xrun += pe[k];
     if (cs > 0) {
         float bus = 0.f;   // (B usum)[e] sits in column T
 #pragma unroll
@@ -498,66 +531,84 @@ __device__ __noinline__ void chain_xscan(const PArgs &P, int j) {
 #pragma unroll
     for (int s = 0; s < kTP; s++)
         if (s < T) {
-            const float x = (s == 0 && head_br) ? xrun + (ev[s] + y[s]) : (xrun + ev[s]) + y[s];
-            Xg[(size_t)cn[s] * nx + e] = x;
+            const float ev = se[s * nxp + e];
+            const float x = (s == 0 && head_br) ? xrun + (ev + y[s]) : (xrun + ev) + y[s];
             y[s] = x; xrun = x;
         }
     row_store(S.Y + e * kTP, y);
 }
 
 // Hx = sysF x, Hu = sysG u (:744-747), t = Hx + w/step, box projections (Utilities.cu:237-254) and the partial sums of
-// the two global distances (:792, :810) for every column.  x in Y rows; u in X1 rows (chains) or devVecU (crown).
-__device__ __noinline__ void sweep_epilogue(const PArgs &P, int ncols, bool u_in_smem, const float *wxi, const float *wpsi,
+// the two global distances (:792, :810) for every column.  x in Y rows, u in `urows` rows.  Two uniform passes (xi part,
+// psi part); item = (column, element), all threads, every load of a batch issued before its first use
+__device__ __noinline__ void sweep_epilogue(const PArgs &P, int ncols, const float *urows, const float *wxi, const float *wpsi,
                                             double &s1, double &s2) {
     const SweepSmem S = sweep_smem(P);
     const int nx = P.nx, nu = P.nu, ny = 2 * nx + nu;
     const float inv_step = P.inv_step;
     const float *__restrict__ diag = P.diag, *__restrict__ sxmin = P.sxmin, *__restrict__ sxmax = P.sxmax,
                 *__restrict__ sxs = P.sxs, *__restrict__ sumin = P.sumin, *__restrict__ sumax = P.sumax;
-    const float *Ug = P.U;
     float *__restrict__ pri_xi = P.pri_xi, *__restrict__ pri_psi = P.pri_psi, *__restrict__ dual_xi = P.dual_xi,
           *__restrict__ dual_psi = P.dual_psi;
+    const float *xrows = S.Y;
+    constexpr int kB = 6;
     double l1 = 0, l2 = 0;
-    for (int el = threadIdx.x; el < ny; el += kPC) {
-        const bool isx = el < 2 * nx;
-        const int jx = el < nx ? el : el - nx, ju = el - 2 * nx;
-        const float *src = isx ? S.Y + jx * kTP : S.X1 + ju * kTP;
-        for (int sb = 0; sb < ncols; sb += 4) {
-            float dgv[4], wv[4], lo[4], hi[4], val[4];
+    {   // xi part: element e < 2 nx of column c; e < nx: state box, else safety level
+        const int dim = 2 * nx, items = ncols * dim;
+        for (int base = threadIdx.x; base < items; base += kB * kPC) {
+            float dgv[kB], wv[kB], lo[kB], hi[kB], val[kB];
+            size_t off[kB];
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int s = sb + b;
-                if (s < ncols) {
-                    const size_t i = (size_t)S.colnode[s];
-                    dgv[b] = __ldg(diag + i * ny + el);
-                    if (isx) {
-                        const size_t kb = i * nx + jx;
-                        wv[b] = __ldcg(wxi + i * 2 * nx + el);
-                        lo[b] = el < nx ? __ldg(sxmin + kb) : __ldg(sxs + kb);
-                        hi[b] = el < nx ? __ldg(sxmax + kb) : __int_as_float(0x7F7F7F7F);
-                        val[b] = src[s];
-                    } else {
-                        const size_t kk = i * nu + ju;
-                        wv[b] = __ldcg(wpsi + kk);
-                        lo[b] = __ldg(sumin + kk);
-                        hi[b] = __ldg(sumax + kk);
-                        val[b] = u_in_smem ? src[s] : __ldcg(Ug + kk);
-                    }
-                }
+            for (int b = 0; b < kB; b++) {
+                const int it = min(base + b * kPC, items - 1);
+                const int c = it / dim, e = it - c * dim, jx = e < nx ? e : e - nx;
+                const size_t i = (size_t)S.colid[c];
+                off[b] = i * dim + e;
+                dgv[b] = __ldg(diag + i * ny + e);
+                wv[b] = __ldcg(wxi + off[b]);
+                lo[b] = __ldg((e < nx ? sxmin : sxs) + i * nx + jx);
+                hi[b] = e < nx ? __ldg(sxmax + i * nx + jx) : __int_as_float(0x7F7F7F7F);
+                val[b] = xrows[jx * kTP + c];
             }
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int s = sb + b;
-                if (s < ncols) {
-                    const size_t i = (size_t)S.colnode[s];
+            for (int b = 0; b < kB; b++) {
+                const int it = base + b * kPC;
+                if (it < items) {
                     const float h = dgv[b] * val[b];
                     const float tt = h + inv_step * wv[b];
                     const float z = clampf(tt, lo[b], hi[b]);
-                    if (isx) {
-                        pri_xi[i * 2 * nx + el] = h; dual_xi[i * 2 * nx + el] = z;
-                        const float df = tt + -1.f * z;
-                        if (el < nx) l1 += (double)df * df; else l2 += (double)df * df;
-                    } else { pri_psi[i * nu + ju] = h; dual_psi[i * nu + ju] = z; }
+                    pri_xi[off[b]] = h; dual_xi[off[b]] = z;
+                    const float df = tt + -1.f * z;
+                    const int e = it % dim;
+                    if (e < nx) l1 += (double)df * df; else l2 += (double)df * df;
+                }
+            }
+        }
+    }
+    {   // psi part
+        const int items = ncols * nu;
+        for (int base = threadIdx.x; base < items; base += kB * kPC) {
+            float dgv[kB], wv[kB], lo[kB], hi[kB], val[kB];
+            size_t off[kB];
+#pragma unroll
+            for (int b = 0; b < kB; b++) {
+                const int it = min(base + b * kPC, items - 1);
+                const int c = it / nu, e = it - c * nu;
+                const size_t i = (size_t)S.colid[c];
+                off[b] = i * nu + e;
+                dgv[b] = __ldg(diag + i * ny + 2 * nx + e);
+                wv[b] = __ldcg(wpsi + off[b]);
+                lo[b] = __ldg(sumin + off[b]);
+                hi[b] = __ldg(sumax + off[b]);
+                val[b] = urows[e * kTP + c];
+            }
+#pragma unroll
+            for (int b = 0; b < kB; b++) {
+                const int it = base + b * kPC;
+                if (it < items) {
+                    const float h = dgv[b] * val[b];
+                    pri_psi[off[b]] = h;
+                    dual_psi[off[b]] = clampf(h + inv_step * wv[b], lo[b], hi[b]);
                 }
             }
         }
@@ -565,38 +616,47 @@ __device__ __noinline__ void sweep_epilogue(const PArgs &P, int ncols, bool u_in
     s1 += l1; s2 += l2;
 }
 
-__device__ __noinline__ void chain_forward(const PArgs &P, int j, uint32_t mpar, const float *wxi, const float *wpsi,
-                                           double &s1, double &s2) {
+__device__ __noinline__ void chain_forward(const PArgs &P, int j, int next_chain, uint32_t mpar, StagePhase &ph, const float *wxi,
+                                           const float *wpsi, double &s1, double &s2) {
     const SweepSmem S = sweep_smem(P);
+    const int T = P.N - P.cs;
+    float *Ug = P.U, *Xg = P.X;
+    const int nu = P.nu, nx = P.nx;
     chain_columns(P, j);
     dstamp(P, 15);
+    mbar_wait(&S.sfull[3], ph.f); ph.f ^= 1;
     chain_uscan(P, j);
     cbar();
+    cols_to_global(S.X1, S.colid, T, nu, nu, Ug);                                 // devVecU
     dstamp(P, 16);
     mbar_wait(&S.mfull[3], mpar);
-    tile_gemm(S.B, P.nx, P.nu, S.X1, S.Y, S.scr2);                               // B u   (:715, :736)
+    tile_gemm(S.B, nx, nu, S.X1, S.Y, S.scr2);                                   // B u   (:715, :736)
     dstamp(P, 17);
     chain_xscan(P, j);
     cbar();
+    if (next_chain >= 0 && threadIdx.x == 0) issue_chain_forward_loads(P, next_chain);
+    cols_to_global(S.Y, S.colid, T, nx, nx, Xg);                                  // devVecX
     dstamp(P, 18);
-    sweep_epilogue(P, P.N - P.cs, true, wxi, wpsi, s1, s2);
+    sweep_epilogue(P, T, S.X1, wxi, wpsi, s1, s2);
     cbar();
     dstamp(P, 19);
 }
 
 // ---- crown (stages above the chains) ------------------------------------------------------------------------------
-// A tile = up to kTP consecutive crown nodes.  solveSumChildren (Utilities.cu:168-201) unrolled over the whole subtree:
+// A tile = up to kTP/2 consecutive crown nodes.  solveSumChildren (Utilities.cu:168-201) unrolled over the whole subtree:
 //   q_bar_i = sum_{crown j below i} c_j + sum_{heads h below i} q_h
 //   sigma_i = beta_i + [ sum_{heads} r_h + sum_{crown j below i} (beta_j + D xi_j + F psi_j) ] + G QS_i
 //   QS_i    = sum_{crown j below i} q_bar_j = sum_{crown j below i} (s_j - s_i - 1) c_j + (cs - 1 - s_i) sum_{heads} q_h
-// (the descendants of a node are one contiguous id range per stage: children are contiguous, Utilities.cu:184-199)
+// (the descendants of a node are one contiguous id range per stage: children are contiguous, Utilities.cu:184-199).
+// X1 q-rows: columns 0..n-1 = QS_i, columns 12..12+n-1 = q_bar_i (one G GEMM gives both products); V rows = base_i
 __device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols) {
     const SweepSmem S = sweep_smem(P);
-    const int t = threadIdx.x, g = t >> 7, e = t & 127, nx = P.nx, nv = P.nv, cs = P.cs;
+    const int t = threadIdx.x, g = t >> 7, e = t & 127, nx = P.nx, nv = P.nv, cs = P.cs, nxp = P.nxp, nvp = P.nvp;
     const int head0 = __ldg(P.cum + cs);
     const int *__restrict__ stages = P.stages, *__restrict__ crown_rng = P.crown_rng;
-    const float *__restrict__ cg = P.c, *__restrict__ bg = P.beta, *__restrict__ p0 = P.part[0], *__restrict__ p1 = P.part[1],
+    const float *__restrict__ cg = P.cm_c, *__restrict__ bg = P.cm_beta, *__restrict__ p0 = P.part[0], *__restrict__ p1 = P.part[1],
                 *__restrict__ qhg = P.qh, *__restrict__ rhg = P.rh;
+    const bool ex = e < nx, ev = e < nv;
     for (int col = 0; col < ncols; col++) {
         const int i = i0 + col, si = __ldg(stages + i);
         const int *rng = crown_rng + (size_t)i * (kMaxCs + 1) * 2;
@@ -604,21 +664,41 @@ __device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols) {
         for (int s = si + 1; s < cs; s++) {
             const int lo = __ldg(rng + 2 * s), hi = __ldg(rng + 2 * s + 1);
             float cpart = 0.f, bpart = 0.f;
-            for (int jn = lo + g; jn < hi; jn += 4) {
-                if (e < nx) cpart += __ldcg(cg + (size_t)jn * nx + e);
-                if (e < nv) {
-                    const size_t idx = (size_t)jn * nv + e;
-                    bpart += (__ldg(bg + idx) + __ldcg(p0 + idx)) + __ldcg(p1 + idx);
+            int jn = lo + g;
+            for (; jn + 12 < hi; jn += 16) {   // four rows in flight
+                float c4[4], b4[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const size_t r = (size_t)(jn + 4 * k);
+                    c4[k] = ex ? __ldcg(cg + r * nxp + e) : 0.f;
+                    b4[k] = ev ? (__ldg(bg + r * nvp + e) + __ldcg(p0 + r * nvp + e)) + __ldcg(p1 + r * nvp + e) : 0.f;
                 }
+#pragma unroll
+                for (int k = 0; k < 4; k++) { cpart += c4[k]; bpart += b4[k]; }
+            }
+            for (; jn < hi; jn += 4) {
+                if (ex) cpart += __ldcg(cg + (size_t)jn * nxp + e);
+                if (ev) bpart += (__ldg(bg + (size_t)jn * nvp + e) + __ldcg(p0 + (size_t)jn * nvp + e)) + __ldcg(p1 + (size_t)jn * nvp + e);
             }
             qb += cpart; qs += (float)(s - si - 1) * cpart; bs += bpart;
         }
         {
             const int lo = __ldg(rng + 2 * cs) - head0, hi = __ldg(rng + 2 * cs + 1) - head0;
             float hq = 0.f, hr = 0.f;
-            for (int h = lo + g; h < hi; h += 4) {
-                if (e < nx) hq += __ldcg(qhg + (size_t)h * nx + e);
-                if (e < nv) hr += __ldcg(rhg + (size_t)h * nv + e);
+            int h = lo + g;
+            for (; h + 12 < hi; h += 16) {
+                float q4[4], r4[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    q4[k] = ex ? __ldcg(qhg + (size_t)(h + 4 * k) * nx + e) : 0.f;
+                    r4[k] = ev ? __ldcg(rhg + (size_t)(h + 4 * k) * nv + e) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) { hq += q4[k]; hr += r4[k]; }
+            }
+            for (; h < hi; h += 4) {
+                if (ex) hq += __ldcg(qhg + (size_t)h * nx + e);
+                if (ev) hr += __ldcg(rhg + (size_t)h * nv + e);
             }
             qb += hq; qs += (float)(cs - 1 - si) * hq; bs += hr;
         }
@@ -627,108 +707,79 @@ __device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols) {
         cbar();
         if (g == 0) {
             const float *s0 = S.scr2;
-            if (e < nx) {
-                S.X1[(nv + e) * kTP + col] = ((s0[e] + s0[384 + e]) + s0[768 + e]) + s0[1152 + e];                    // q_bar
-                S.V[e * kTP + col] = ((s0[128 + e] + s0[512 + e]) + s0[896 + e]) + s0[1280 + e];                       // QS
+            if (ex) {
+                S.X1[e * kTP + 12 + col] = ((s0[e] + s0[384 + e]) + s0[768 + e]) + s0[1152 + e];                      // q_bar
+                S.X1[e * kTP + col] = ((s0[128 + e] + s0[512 + e]) + s0[896 + e]) + s0[1280 + e];                     // QS
             }
-            if (e < nv)
-                S.X1[e * kTP + col] = __ldg(bg + (size_t)i * nv + e) +
-                                      (((s0[256 + e] + s0[640 + e]) + s0[1024 + e]) + s0[1408 + e]);                  // sigma - G QS
+            if (ev)
+                S.V[e * kTP + col] = __ldg(bg + (size_t)i * nvp + e) +
+                                     (((s0[256 + e] + s0[640 + e]) + s0[1024 + e]) + s0[1408 + e]);                   // sigma - G QS
         }
         cbar();
     }
-    // unused columns: zeros
-    if (g == 0)
-        for (int col = ncols; col < kTP; col++) {
-            if (e < nx) { S.X1[(nv + e) * kTP + col] = 0.f; S.V[e * kTP + col] = 0.f; }
-            if (e < nv) S.X1[e * kTP + col] = 0.f;
-        }
+    if (g == 0 && ex)   // unused columns: zeros
+        for (int col = 0; col < kTP; col++)
+            if ((col >= ncols && col < 12) || col >= 12 + ncols) S.X1[e * kTP + col] = 0.f;
     cbar();
 }
 
-// sigma = (beta + sums) + G QS; X1 rows 0..nv-1: sigma on exit (df: kept unscaled for the second pass)
+// sigma = (beta + sums) + G QS;  X1 sigma-rows = -1/2 (sigma + G q_bar)  (df: -1/2 r, r = ((sigma + D xi) + F psi) + G q_bar)
 __device__ __noinline__ void crown_sigma(const PArgs &P, int ncols) {
     const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, nv = P.nv;
+    const int e = threadIdx.x, nv = P.nv, nvp = P.nvp;
     if (e >= nv) return;
     const bool df = P.df_mode != 0;
-    float *__restrict__ sig = P.sigma;
-    float y[kTP], b[kTP];
-    int cn[kTP];
-    row_load(S.Y + e * kTP, y);
-    row_load(S.X1 + e * kTP, b);
-#pragma unroll
-    for (int s = 0; s < kTP; s++) cn[s] = S.colnode[s];
-#pragma unroll
-    for (int s = 0; s < kTP; s++) {
-        float sg = 0.f;
-        if (s < ncols) {
-            sg = b[s] + y[s];
-            sig[(size_t)cn[s] * nv + e] = sg;
-        }
-        b[s] = df ? sg : -0.5f * sg;
-    }
-    row_store(S.X1 + e * kTP, b);
-}
-
-// df mode: r = ((sigma + D xi) + F psi) + G q_bar; X1 rows 0..nv-1 = -1/2 r.  Y = G q_bar on entry
-__device__ __noinline__ void crown_r_df(const PArgs &P, int ncols) {
-    const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, nv = P.nv;
-    if (e >= nv) return;
     const float *__restrict__ p0 = P.part[0], *__restrict__ p1 = P.part[1];
     float y[kTP], b[kTP];
     row_load(S.Y + e * kTP, y);
-    row_load(S.X1 + e * kTP, b);
+    row_load(S.V + e * kTP, b);
 #pragma unroll
-    for (int s = 0; s < kTP; s++) {
-        float r = 0.f;
+    for (int s = 0; s < 12; s++) {
+        float out = 0.f;
         if (s < ncols) {
-            const size_t idx = (size_t)S.colnode[s] * nv + e;
-            r = ((b[s] + __ldcg(p0 + idx)) + __ldcg(p1 + idx)) + y[s];
+            const float sg = b[s] + y[s];
+            if (df) {
+                const size_t idx = (size_t)S.colnode[s] * nvp + e;
+                out = -0.5f * (((sg + __ldcg(p0 + idx)) + __ldcg(p1 + idx)) + y[12 + s]);
+            } else out = -0.5f * (sg + y[12 + s]);
         }
-        b[s] = -0.5f * r;
+        b[s] = out; b[12 + s] = 0.f;
     }
-    row_store(S.X1 + e * kTP, b);
+    row_store(S.X1 + (P.nx + e) * kTP, b);
 }
 
-__device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, uint32_t mpar) {
+__device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, uint32_t mpar, StagePhase &ph) {
     const SweepSmem S = sweep_smem(P);
     const int t = threadIdx.x;
     if (t < kTP) {
         const int node = t < ncols ? i0 + t : 0;
-        S.colnode[t] = node;
+        S.colnode[t] = node; S.colid[t] = node;
         S.colp[t] = t < ncols ? __ldg(P.prob + __ldg(P.omega_idx + node)) : 1.f;
     }
     cbar();
     crown_sums(P, i0, ncols);
     dstamp(P, 11);
     mbar_wait(&S.mfull[0], mpar);
-    tile_gemm(S.G, P.nv, P.nx, S.V, S.Y, S.scr2);                                // G QS
+    tile_gemm(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2);                               // G [QS | q_bar]
     crown_sigma(P, ncols);
     cbar();
-    if (P.df_mode) {
-        tile_gemm(S.G, P.nv, P.nx, S.X1 + P.nv * kTP, S.Y, S.scr2);              // G q_bar
-        crown_r_df(P, ncols);
-        cbar();
-    }
     dstamp(P, 12);
-    sweep_backward_finish(P, ncols, mpar, 6);
+    sweep_backward_finish(P, ncols, false, mpar, ph, -1);
 }
 
 // forward sweep of a crown tile: u along each node's path (reference recursion), x = x_cur + sum_path e + B sum_path u
 __device__ __noinline__ void crown_forward(const PArgs &P, int i0, int ncols, uint32_t mpar, const float *wxi, const float *wpsi,
                                            double &s1, double &s2) {
     const SweepSmem S = sweep_smem(P);
-    const int t = threadIdx.x, g = t >> 7, e = t & 127, nx = P.nx, nu = P.nu;
+    const int t = threadIdx.x, g = t >> 7, e = t & 127, nx = P.nx, nu = P.nu, nxp = P.nxp;
     const FwdIn I = fwd_in(P);
     const int *__restrict__ stages = P.stages, *__restrict__ parent = P.parent;
-    const float *__restrict__ eg = P.e, *__restrict__ xcur = P.xcur;
-    float *__restrict__ Ug = P.U, *__restrict__ Xg = P.X;
-    if (t < kTP) S.colnode[t] = t < ncols ? i0 + t : 0;
+    const float *__restrict__ eg = P.cm_e, *__restrict__ xcur = P.xcur;
+    float *Ug = P.U, *Xg = P.X;
+    if (t < kTP) { S.colnode[t] = t < ncols ? i0 + t : 0; S.colid[t] = S.colnode[t]; }
     cbar();
     for (int col = g; col < kTP; col += 4) {
-        float usum = 0.f, xb = 0.f;
+        float usum = 0.f, xb = 0.f, u = 0.f;
         if (col < ncols) {
             const int i = i0 + col, si = __ldg(stages + i);
             int path[kMaxCs];
@@ -736,38 +787,38 @@ __device__ __noinline__ void crown_forward(const PArgs &P, int i0, int ncols, ui
 #pragma unroll
             for (int k = kMaxCs - 1; k >= 0; k--)
                 if (k <= si) { path[k] = a; a = __ldg(parent + a); }
-            if (e < nu) {
-                const float u = path_u(I, path, si + 1, e, usum);
-                Ug[(size_t)i * nu + e] = u;
-            }
+            if (e < nu) { float uhl; u = path_u(I, path, si + 1, e, usum, uhl); }
             if (e < nx) {
+                float pe[kMaxCs];
+#pragma unroll
+                for (int k = 0; k < kMaxCs; k++) if (k <= si) pe[k] = __ldg(eg + (size_t)path[k] * nxp + e);
                 xb = __ldg(xcur + e);
 #pragma unroll
-                for (int k = 0; k < kMaxCs; k++) if (k <= si) xb += __ldg(eg + (size_t)path[k] * nx + e);
+                for (int k = 0; k < kMaxCs; k++) if (k <= si) xb += pe[k];
             }
         }
-        if (e < nu) S.X1[e * kTP + col] = usum;
-        if (e < nx) S.V[e * kTP + col] = xb;
+        if (e < nu) { S.X1[e * kTP + col] = usum; S.V[e * kTP + col] = u; }
+        if (e < nx) S.scr2[e * kTP + col] = xb;
     }
     cbar();
+    cols_to_global(S.V, S.colid, ncols, nu, nu, Ug);                              // devVecU
     dstamp(P, 13);
+    // x base sits in scr2, which the GEMM uses as scratch: move it to registers first
+    float xb[kTP];
+    if (t < nx) row_load(S.scr2 + t * kTP, xb);
+    cbar();
     mbar_wait(&S.mfull[3], mpar);
     tile_gemm(S.B, nx, nu, S.X1, S.Y, S.scr2);                                   // B sum_path u
     if (t < nx) {
-        float y[kTP], xb[kTP];
+        float y[kTP];
         row_load(S.Y + t * kTP, y);
-        row_load(S.V + t * kTP, xb);
 #pragma unroll
-        for (int s = 0; s < kTP; s++)
-            if (s < ncols) {
-                const float x = xb[s] + y[s];
-                Xg[(size_t)(i0 + s) * nx + t] = x;
-                y[s] = x;
-            }
+        for (int s = 0; s < kTP; s++) y[s] = s < ncols ? xb[s] + y[s] : 0.f;
         row_store(S.Y + t * kTP, y);
     }
     cbar();
-    sweep_epilogue(P, ncols, false, wxi, wpsi, s1, s2);
+    cols_to_global(S.Y, S.colid, ncols, nx, nx, Xg);                              // devVecX
+    sweep_epilogue(P, ncols, S.V, wxi, wpsi, s1, s2);
     cbar();
     dstamp(P, 14);
 }
@@ -813,7 +864,7 @@ __device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderS
     const float *g0 = P.pri_xi, *g1 = P.Wxi[prev_], *g2 = P.dual_xi, *g3 = P.Yxi[prev_], *g8 = P.diag;
     const float *g4 = P.pri_psi, *g5 = P.Wpsi[prev_], *g6 = P.dual_psi, *g7 = P.Ypsi[prev_];
     const float *m0 = P.mat[0], *m1 = P.mat[1], *m2 = P.mat[2], *m3 = P.mat[3];
-    const int n_mats = P.n_mats, cols_per_chunk = P.cols_per_chunk;
+    const int n_mats = P.n_mats, cols_per_chunk = P.cols_per_chunk, n_stages = P.n_stages, stage_stride = P.stage_stride;
     const int u_begin = R.u_begin, u_end = R.u_end, node_first = R.node_first, node_last = R.node_last;
     auto load_vec = [&](int node, int) {
         const size_t ox = (size_t)node * 2 * nx, op = (size_t)node * nu;
@@ -866,10 +917,10 @@ __device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderS
                 { const long long c_ = clock64(); mbar_wait(&M.empty[st], ph ^ 1); cyc_empty += clock64() - c_; }
                 if (lane == 0) {
                     mbar_expect_tx(&M.full[st], bytes);
-                    bulk_g2s(M.ring + st * kPStageStride, reinterpret_cast<const void *>(b0), bytes, &M.full[st]);
+                    bulk_g2s(M.ring + st * stage_stride, reinterpret_cast<const void *>(b0), bytes, &M.full[st]);
                 }
                 __syncwarp();
-                if (++st == kPStages) { st = 0; ph ^= 1; }
+                if (++st == n_stages) { st = 0; ph ^= 1; }
                 issued++;
             }
         }
@@ -892,6 +943,7 @@ template <int NR>
 __device__ __forceinline__ void gemv_role(const PArgs &P, const Slice &R, GemvState &G) {
     const Pipe M = pipe_smem();
     const int nx = P.nx, nu = P.nu, nv = P.nv, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_stages = P.n_stages, stage_stride = P.stage_stride;
     int st = G.st, wb = G.wb, rb = G.rb; uint32_t ph = G.ph, wph = G.wph, rph = G.rph;
     int node_prev = -1;
     const bool dbg = blockIdx.x == P.clock_cta && threadIdx.x == 0;
@@ -921,19 +973,22 @@ __device__ __forceinline__ void gemv_role(const PArgs &P, const Slice &R, GemvSt
             mbar_wait(&M.full[st], ph);
             const long long c2_ = clock64();
             cyc_full += c2_ - c1_;
-            const float *sb = M.ring + st * kPStageStride + off + lane;
+            const float *sb = M.ring + st * stage_stride + off + lane;
             const float *wc = wseg + c0;
             int j = warp;
-            for (; j + kGemvWarps < cc; j += 2 * kGemvWarps) {   // two columns per trip: all loads first
-                const float w0 = wc[j], w1 = wc[j + kGemvWarps];
-                const float *col0 = sb + j * nv, *col1 = col0 + kGemvWarps * nv;
-                float a[NR], b[NR];
+            for (; j + 3 * kGemvWarps < cc; j += 4 * kGemvWarps) {   // four columns per trip: all loads first
+                const float w0 = wc[j], w1 = wc[j + kGemvWarps], w2 = wc[j + 2 * kGemvWarps], w3 = wc[j + 3 * kGemvWarps];
+                const float *col0 = sb + j * nv, *col1 = col0 + kGemvWarps * nv, *col2 = col1 + kGemvWarps * nv, *col3 = col2 + kGemvWarps * nv;
+                float a[NR], b[NR], c[NR], d[NR];
 #pragma unroll
-                for (int k = 0; k < NR; k++) { a[k] = col0[32 * k]; b[k] = col1[32 * k]; }
+                for (int k = 0; k < NR; k++) { a[k] = col0[32 * k]; b[k] = col1[32 * k]; c[k] = col2[32 * k]; d[k] = col3[32 * k]; }
 #pragma unroll
-                for (int k = 0; k < NR; k++) { acc[k] = fmaf(a[k], w0, acc[k]); acc[k] = fmaf(b[k], w1, acc[k]); }
+                for (int k = 0; k < NR; k++) {
+                    acc[k] = fmaf(a[k], w0, acc[k]); acc[k] = fmaf(b[k], w1, acc[k]);
+                    acc[k] = fmaf(c[k], w2, acc[k]); acc[k] = fmaf(d[k], w3, acc[k]);
+                }
             }
-            if (j < cc) {
+            for (; j < cc; j += kGemvWarps) {
                 const float w0 = wc[j];
                 const float *col0 = sb + j * nv;
                 float a[NR];
@@ -944,7 +999,7 @@ __device__ __forceinline__ void gemv_role(const PArgs &P, const Slice &R, GemvSt
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&M.empty[st]);
-            if (++st == kPStages) { st = 0; ph ^= 1; }
+            if (++st == n_stages) { st = 0; ph ^= 1; }
             cyc_cmp += clock64() - c2_;
         }
         // hand the per-warp partial sums to the element-wise warps
@@ -962,7 +1017,7 @@ __device__ __forceinline__ void gemv_role(const PArgs &P, const Slice &R, GemvSt
         if (++wb == 2) { wb = 0; wph ^= 1; }
     }
     G.st = st; G.ph = ph; G.wb = wb; G.wph = wph; G.rb = rb; G.rph = rph;
-    if (dbg) { P.phase_ns[24] += cyc_full; P.phase_ns[25] += cyc_w; P.phase_ns[26] += cyc_red; P.phase_ns[27] += cyc_cmp; }
+    if (dbg) { unsigned long long *c = clk_smem(); c[24] += cyc_full; c[25] += cyc_w; c[26] += cyc_red; c[27] += cyc_cmp; }
 }
 
 // ---- element-wise warps: fused finalisation (previous iteration) + extrapolation (this one), one node ahead of the
@@ -979,7 +1034,9 @@ __device__ __noinline__ void ew_role(const PArgs &P, const Slice &R, EwState &E,
     const float inv_step = P.inv_step, step = P.step, a1 = I.a1, a2 = I.a2, sc1 = I.sc1, sc2 = I.sc2;
     const bool br1 = I.br1 != 0, br2 = I.br2 != 0;
     float *__restrict__ Yxi = P.Yxi[I.cur], *__restrict__ Wxi = P.Wxi[I.cur], *__restrict__ Ypsi = P.Ypsi[I.cur],
-          *__restrict__ Wpsi = P.Wpsi[I.cur], *__restrict__ cg = P.c;
+          *__restrict__ Wpsi = P.Wpsi[I.cur], *__restrict__ cg = P.cm_c;
+    const int *__restrict__ pos = P.pos;
+    const int nxp = P.nxp, nvp = P.nvp;
     float *__restrict__ part0 = P.part[0], *__restrict__ part1 = P.part[1], *__restrict__ part2 = P.part[2],
           *__restrict__ part3 = P.part[3];
     Cand lbx = bx, lbp = bp;
@@ -1019,7 +1076,8 @@ __device__ __noinline__ void ew_role(const PArgs &P, const Slice &R, EwState &E,
         ewbar();
         if (wr_xi) {   // c = sysF' xi_w  (:651-658)
             const float *dg = vsl + 8 * kVStride;
-            for (int t = et; t < nx; t += kEwWarps * 32) cg[(size_t)node * nx + t] = dg[t] * wdst[t] + dg[nx + t] * wdst[nx + t];
+            const size_t row = (size_t)__ldg(pos + node) * nxp;
+            for (int t = et; t < nx; t += kEwWarps * 32) cg[row + t] = dg[t] * wdst[t] + dg[nx + t] * wdst[nx + t];
         }
         __syncwarp();
         if (lane == 0) { mbar_arrive(&M.vempty[vs]); mbar_arrive(&M.wfull[wb]); }
@@ -1038,7 +1096,7 @@ __device__ __noinline__ void ew_role(const PArgs &P, const Slice &R, EwState &E,
 #pragma unroll
             for (int w = 1; w < kGemvWarps; w++) sum += rd[w * kDimMax];
             float *__restrict__ pm = m == 0 ? part0 : (m == 1 ? part1 : (m == 2 ? part2 : part3));
-            pm[(size_t)node * nv + et] = sum;
+            pm[(size_t)__ldg(pos + node) * nvp + et] = sum;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&M.rempty[rb]);
@@ -1046,13 +1104,23 @@ __device__ __noinline__ void ew_role(const PArgs &P, const Slice &R, EwState &E,
     }
     E.vs = vs; E.vph = vph; E.wb = wb; E.wph = wph; E.rb = rb; E.rph = rph;
     bx = lbx; bp = lbp;
-    if (blockIdx.x == P.clock_cta && et == 0) { P.phase_ns[30] += cyc_rf; P.phase_ns[31] += cyc_pro; }
+    if (blockIdx.x == P.clock_cta && et == 0) { unsigned long long *c = clk_smem(); c[30] += cyc_rf; c[31] += cyc_pro; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant__ PArgs P) {
+    // The non-inlined role / sweep functions get the arguments through a reference; reads of the kernel-parameter
+    // space behind a generic pointer cost about a microsecond each (ncu: 12 % of all stall samples sat on them), so
+    // those functions are handed a shared-memory copy instead.
+    static_assert(sizeof(PArgs) <= kPArgsWords * 4 && sizeof(PArgs) % 4 == 0, "PArgs copy");
+    {
+        const int *src = reinterpret_cast<const int *>(&P);
+        int *dst = reinterpret_cast<int *>(smem_f(kOffPArgs));
+        for (int k = threadIdx.x; k < (int)(sizeof(PArgs) / 4); k += kPC) dst[k] = src[k];
+    }
+    const PArgs &PS = *reinterpret_cast<const PArgs *>(smem_f(kOffPArgs));
     const int nv = P.nv;
     const Pipe M = pipe_smem();
     double *dsh = reinterpret_cast<double *>(smem_f(kOffDsh));      // 2 * 16 doubles
@@ -1067,7 +1135,7 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
             mbar_init(&M.wfull[s], kEwWarps); mbar_init(&M.wempty[s], kGemvWarps);
             mbar_init(&M.rfull[s], kGemvWarps); mbar_init(&M.rempty[s], kEwWarps);
         }
-        for (int s = 0; s < 4; s++) mbar_init(&M.rempty[2 + s], 1);   // = SweepSmem::mfull
+        for (int s = 0; s < 8; s++) mbar_init(&M.rempty[2 + s], 1);   // = SweepSmem::mfull, sfull
         mbar_fence_init();
     }
     __syncthreads();
@@ -1081,11 +1149,17 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
     R.node_last = R.u_begin < R.u_end ? (R.u_end - 1) / P.n_mats : -1;
 
     unsigned int bar_target = 0;
+    StagePhase SP{0u, 0u, 0u, 0u};
     GemvState GS{0, 0u, 0, 0u, 0, 0u};
     EwState ES{0, 0u, 0, 0u, 0, 0u};
     LoaderState LS{0, 0u, 0, 0u, 0};
     double s1 = 0, s2 = 0;
-    if (blockIdx.x == P.clock_cta && tid == 0) g_t_prev = globaltimer();
+    if (tid == 0) {
+        unsigned long long *c = clk_smem();
+        for (int k = 0; k < 32; k++) c[k] = 0;
+        c[32] = globaltimer(); c[33] = blockIdx.x == P.clock_cta ? 1 : 0;
+    }
+    __syncthreads();
     auto stamp = [&](int idx) { dstamp(P, idx); };
     const bool is_gemv = warp < kGemvWarps;
     const int nr = (nv + 31) >> 5;
@@ -1114,7 +1188,7 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
             if (nr == 4) gemv_role<4>(P, R, GS); else if (nr == 3) gemv_role<3>(P, R, GS);
             else if (nr == 2) gemv_role<2>(P, R, GS); else gemv_role<1>(P, R, GS);
         } else if (warp == kLoaderWarp) {
-            loader_role(P, R, LS, it);
+            loader_role(PS, R, LS, it);
         } else {
             const float d1 = sd[0], d2 = sd[1];
             const float thr1 = P.inv_step * P.pen_x, thr2 = P.inv_step * P.pen_xs;
@@ -1122,7 +1196,7 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
             I.a1 = 1.f + lam; I.a2 = -lam; I.cur = cur;
             I.br1 = d1 > thr1; I.br2 = d2 > thr2;
             I.sc1 = I.br1 ? 1.f - thr1 / d1 : 0.f; I.sc2 = I.br2 ? 1.f - thr2 / d2 : 0.f;
-            ew_role(P, R, ES, I, bx, bp);
+            ew_role(PS, R, ES, I, bx, bp);
         }
         // infeasibility candidates of iteration it-1 (updatePrimalInfeasibity, :1480-1496)
         if (it > 0) {
@@ -1138,7 +1212,7 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
         }
         // the stream ring is idle now: pull the shared sweep matrices over it while the grid barrier is pending
         cbar();
-        if (tid == 0) issue_matrix_loads(P);
+        if (tid == 0) issue_matrix_loads(PS);
         stamp(0);
         grid_sync(P.bar, bar_target);
         stamp(1);
@@ -1154,28 +1228,35 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
         }
         const uint32_t mpar = (uint32_t)(it & 1);
         // crown tiles: as narrow as the grid allows (every CTA is free during phase C)
-        const int tile_w = min(kTP, max(1, (P.n_crown + (int)gridDim.x - 1) / (int)gridDim.x));
+        const int tile_w = min(kTP / 2, max(1, (P.n_crown + (int)gridDim.x - 1) / (int)gridDim.x));
         const int n_tiles = (P.n_crown + tile_w - 1) / tile_w;
+        const int grid = (int)gridDim.x, j0 = (int)blockIdx.x;
 
-        // ---- phase B: backward sweep of the chains
+        // ---- phase B: backward sweep of the chains (operand blocks by bulk TMA, one chain ahead)
         stamp(2);
-        for (int j = blockIdx.x; j < P.K; j += gridDim.x) chain_backward(P, j, mpar);
+        if (tid == 0 && j0 < P.K) issue_chain_backward_loads(PS, j0);
+        for (int j = j0; j < P.K; j += grid) chain_backward(PS, j, j + grid < P.K ? j + grid : -1, mpar, SP);
         stamp(10);
         // ---- phase C: backward sweep of the crown (tiles are dealt from the last CTA down: those have the fewest chains)
         if (P.n_crown > 0) {
             grid_sync(P.bar, bar_target);
             stamp(20);
-            for (int tl = (int)gridDim.x - 1 - (int)blockIdx.x; tl < n_tiles; tl += gridDim.x)
-                crown_backward(P, tl * tile_w, min(tile_w, P.n_crown - tl * tile_w), mpar);
+            for (int tl = grid - 1 - j0; tl < n_tiles; tl += grid)
+                crown_backward(PS, tl * tile_w, min(tile_w, P.n_crown - tl * tile_w), mpar, SP);
             stamp(21);
+        }
+        // G has done its work for this iteration: B takes its place (every step above ended with a CTA barrier)
+        if (tid == 0) issue_b_load(PS);
+        if (P.n_crown > 0) {
             grid_sync(P.bar, bar_target);
             stamp(22);
         }
         // ---- phase F: forward sweep + prox boxes
         const float *wxi = P.Wxi[cur], *wpsi = P.Wpsi[cur];
-        for (int tl = (int)gridDim.x - 1 - (int)blockIdx.x; tl < n_tiles; tl += gridDim.x)
-            crown_forward(P, tl * tile_w, min(tile_w, P.n_crown - tl * tile_w), mpar, wxi, wpsi, s1, s2);
-        for (int j = blockIdx.x; j < P.K; j += gridDim.x) chain_forward(P, j, mpar, wxi, wpsi, s1, s2);
+        if (tid == 0 && j0 < P.K) issue_chain_forward_loads(PS, j0);
+        for (int tl = grid - 1 - j0; tl < n_tiles; tl += grid)
+            crown_forward(PS, tl * tile_w, min(tile_w, P.n_crown - tl * tile_w), mpar, wxi, wpsi, s1, s2);
+        for (int j = j0; j < P.K; j += grid) chain_forward(PS, j, j + grid < P.K ? j + grid : -1, mpar, SP, wxi, wpsi, s1, s2);
         stamp(23);
         {   // this CTA's share of the two squared distances
             for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
@@ -1192,6 +1273,10 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
         grid_sync(P.bar, bar_target);
         stamp(29);
     }
+    if (blockIdx.x == P.clock_cta && tid == 0) {
+        const unsigned long long *c = clk_smem();
+        for (int k = 0; k < 32; k++) P.phase_ns[k] += c[k];
+    }
     if (blockIdx.x == 0 && tid == 0) *P.iter_dev = P.iters - 1;   // k_finalize finishes iteration iters-1
 }
 
@@ -1199,24 +1284,48 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 struct SweepLayout {
-    int oG, oOT, oL, oB, oX1, oY, oV, oScr2, end;   // shared-memory float offsets
-    int pG, pOT, pL, pB, pack_floats;               // float offsets inside the pack
+    int oG, oOm, oL, oX1, oY, oV, oScr2, oStg, end;   // shared-memory float offsets
+    int pG, pOm, pL, pB, pack_floats;                 // float offsets inside the pack
+    int nxp, nup, nvp;
 };
 static int pad4(long long n) { return (int)((n + 3) & ~3LL); }
 static SweepLayout sweep_layout(const Handle *h) {
-    const int nx = h->d.nx, nu = h->d.nu, nv = h->d.nv;
+    const int nx = h->d.nx, nu = h->d.nu, nv = h->d.nv, T = h->d.N - h->chain_stage;
     SweepLayout Y{};
-    const int sG = pad4((long long)nv * nx), sOT = pad4((long long)nv * (nv + nx)), sL = pad4((long long)nu * nv), sB = pad4((long long)nx * nu);
-    Y.pG = 0; Y.pOT = sG; Y.pL = sG + sOT; Y.pB = sG + sOT + sL; Y.pack_floats = sG + sOT + sL + sB;
-    Y.oG = kOffSweep; Y.oOT = Y.oG + sG; Y.oL = Y.oOT + sOT; Y.oB = Y.oL + sL;
-    Y.oX1 = Y.oB + sB;
+    Y.nxp = pad4(nx); Y.nup = pad4(nu); Y.nvp = pad4(nv);
+    const int sG = pad4((long long)nv * nx), sOm = pad4((long long)nv * nv), sL = pad4((long long)nu * nv), sB = pad4((long long)nx * nu);
+    Y.pG = 0; Y.pOm = sG; Y.pL = sG + sOm; Y.pB = sG + sOm + sL; Y.pack_floats = sG + sOm + sL + sB;
+    Y.oG = kOffSweep; Y.oOm = Y.oG + std::max(sG, sB); Y.oL = Y.oOm + sOm;     // B overlays G
+    Y.oX1 = Y.oL + sL;
     Y.oY = Y.oX1 + std::max(nv + nx, nu) * kTP;
     Y.oV = Y.oY + std::max(std::max(nv, nu), nx) * kTP;
-    Y.oScr2 = Y.oV + nv * kTP;
-    Y.end = Y.oScr2 + 128 * kTP;
+    Y.oScr2 = Y.oV + std::max(nv, nu) * kTP;
+    Y.oStg = Y.oScr2 + 128 * kTP;
+    Y.end = Y.oStg + std::max(T * Y.nxp + 5 * T * Y.nvp, 2 * T * Y.nup + T * Y.nxp);
     return Y;
 }
-static size_t persist_smem_bytes(const Handle *h) { return (size_t)std::max(kStreamEnd, sweep_layout(h).end) * 4 + 128; }
+// matrix ring of phase S: whole factor matrices per stage when three of them fit next to the sweep region's size,
+// otherwise as many columns as a stage holds (stage payload >= 16 KB, at least 3 stages)
+struct RingLayout { int n_stages, stage_stride, cols_per_chunk, end; };
+static RingLayout ring_layout(const Handle *h) {
+    const int nx = h->d.nx, nu = h->d.nu, nv = h->d.nv;
+    const int budget = std::max(sweep_layout(h).end, kOffRing + 6 * (kPStageMinFloats + 32)) - kOffRing;   // floats for the ring
+    const int whole = ((nv * std::max(2 * nx, nu) + 31) & ~31) + 32;
+    RingLayout R{};
+    if (3 * whole <= budget) {
+        R.stage_stride = whole;
+        R.n_stages = std::min(kPStages, budget / whole);
+        R.cols_per_chunk = std::max(2 * nx, nu);
+    } else {
+        const int payload = std::max(kPStageMinFloats, ((budget / 6 - 32) / 32) * 32);
+        R.stage_stride = payload + 32;
+        R.n_stages = std::min(kPStages, std::max(3, budget / R.stage_stride));
+        R.cols_per_chunk = payload / nv;
+    }
+    R.end = kOffRing + R.n_stages * R.stage_stride;
+    return R;
+}
+static size_t persist_smem_bytes(const Handle *h) { return (size_t)std::max(ring_layout(h).end, sweep_layout(h).end) * 4 + 128; }
 
 bool persistent_supported(const Handle *h) {
     const rn_dims &d = h->d;
@@ -1225,30 +1334,46 @@ bool persistent_supported(const Handle *h) {
     if (cs >= d.N || cs > kMaxCs) return false;                       // needs a non-branching tail; bounded crown depth
     if (h->h_nps[cs] != d.K) return false;                             // the tail's chains are the scenarios
     if (d.N - cs + (cs > 0 ? 1 : 0) > kTP) return false;               // a chain (+ its parent's column) is one tile
-    if (kPStageFloats / d.nv < 1) return false;
+    if (ring_layout(h).cols_per_chunk < 1) return false;
     return persist_smem_bytes(h) <= 227 * 1024;
+}
+
+// dst[pos(node)][dimp] = src[node][dim]: chain-major copies of the per-solve vectors (beta, uhat, e)
+__global__ void k_to_chain_major(int nodes, int dim, int dimp, const int *__restrict__ pos, const float *__restrict__ src,
+                                 float *__restrict__ dst) {
+    const int i = blockIdx.x;
+    if (i >= nodes) return;
+    const size_t row = (size_t)pos[i] * dimp;
+    for (int t = threadIdx.x; t < dim; t += blockDim.x) dst[row + t] = src[(size_t)i * dim + t];
 }
 
 rn_status persistent_prepare(Handle *h) {
     if (h->persist_ready) return RN_OK;
     const rn_dims &d = h->d;
     const size_t n = d.nodes;
-    const int cs = h->chain_stage, n_crown = h->h_cum[cs];
-    RN_CHECK(dev_alloc(h, &h->part[0], n * d.nv)); RN_CHECK(dev_alloc(h, &h->part[1], n * d.nv));
-    RN_CHECK(dev_alloc(h, &h->part[2], n * d.nv)); RN_CHECK(dev_alloc(h, &h->part[3], n * d.nv));
-    RN_CHECK(dev_alloc(h, &h->LV, n * d.nu));
+    const int cs = h->chain_stage, n_crown = h->h_cum[cs], T = d.N - cs;
+    const SweepLayout Y = sweep_layout(h);
+    for (int k = 0; k < 4; k++) RN_CHECK(dev_alloc(h, &h->part[k], n * Y.nvp));
+    RN_CHECK(dev_alloc(h, &h->cm_c, n * Y.nxp)); RN_CHECK(dev_alloc(h, &h->cm_lv, n * Y.nup));
+    RN_CHECK(dev_alloc(h, &h->cm_beta, n * Y.nvp)); RN_CHECK(dev_alloc(h, &h->cm_uhat, n * Y.nup)); RN_CHECK(dev_alloc(h, &h->cm_e, n * Y.nxp));
     RN_CHECK(dev_alloc(h, &h->qh, (size_t)d.K * d.nx)); RN_CHECK(dev_alloc(h, &h->rh, (size_t)d.K * d.nv));
     RN_CHECK(dev_alloc(h, &h->grid_bar, 8));
     RN_CHECK(dev_alloc(h, &h->phase_ns, 32));
-    // G | OmegaBar ThetaBar | L | B, each padded to 16 bytes: the four bulk copies of the sweeps
-    const SweepLayout Y = sweep_layout(h);
+    // G | OmegaBar | L | B, each padded to 16 bytes: the four bulk copies of the sweeps
     RN_CHECK(dev_alloc(h, &h->sweep_pack, (size_t)Y.pack_floats));
     const size_t f = sizeof(float);
     RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pG, h->G, (size_t)d.nv * d.nx * f, cudaMemcpyDeviceToDevice, h->stream));
-    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pOT, h->OmegaBar, (size_t)d.nv * d.nv * f, cudaMemcpyDeviceToDevice, h->stream));
-    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pOT + (size_t)d.nv * d.nv, h->ThetaBar, (size_t)d.nv * d.nx * f, cudaMemcpyDeviceToDevice, h->stream));
+    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pOm, h->OmegaBar, (size_t)d.nv * d.nv * f, cudaMemcpyDeviceToDevice, h->stream));
     RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pL, h->L, (size_t)d.nu * d.nv * f, cudaMemcpyDeviceToDevice, h->stream));
     RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pB, h->B, (size_t)d.nx * d.nu * f, cudaMemcpyDeviceToDevice, h->stream));
+    // chain-major row of every node: crown nodes keep their id, chain j / stage cs+s sits at n_crown + j T + s
+    std::vector<int> pos(n);
+    for (int i = 0; i < d.nodes; i++) {
+        const int s = h->h_stages[i];
+        pos[i] = s < cs ? i : n_crown + (i - h->h_cum[s]) * T + (s - cs);
+    }
+    RN_CHECK(dev_alloc(h, &h->pos_dev, n));
+    RN_CUDA(h, cudaMemcpyAsync(h->pos_dev, pos.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     // descendant id range of every crown node at every later stage up to the chain heads (children are contiguous)
     std::vector<int> rng((size_t)std::max(n_crown, 1) * (kMaxCs + 1) * 2, 0);
     for (int i = 0; i < n_crown; i++) {
@@ -1280,12 +1405,13 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     const rn_dims &d = h->d;
     PArgs P{};
     P.parent = h->t.parent; P.child_first = h->t.child_first; P.child_count = h->t.child_count; P.omega_idx = h->t.omega_idx;
-    P.cum = h->cum_dev; P.stages = h->t.stages; P.crown_rng = h->crown_rng;
+    P.cum = h->cum_dev; P.stages = h->t.stages; P.crown_rng = h->crown_rng; P.pos = h->pos_dev;
     P.N = d.N; P.cs = h->chain_stage; P.K = d.K; P.nodes = d.nodes; P.n_crown = h->h_cum[h->chain_stage];
     P.n_mats = h->factor_mode == RN_FACTORS_FULL ? 4 : 2;
     P.df_mode = h->factor_mode == RN_FACTORS_DF ? 1 : 0;
     P.iters = iters; P.nx = d.nx; P.nu = d.nu; P.nv = d.nv;
-    P.cols_per_chunk = kPStageFloats / d.nv;
+    const RingLayout RL = ring_layout(h);
+    P.cols_per_chunk = RL.cols_per_chunk; P.n_stages = RL.n_stages; P.stage_stride = RL.stage_stride;
     static const char *clock_env = getenv("RN_CLOCK_CTA");
     P.clock_cta = clock_env ? std::min(atoi(clock_env), h->persist_grid - 1) : 0;
     P.mat[0] = h->D; P.mat[1] = h->F; P.mat[2] = h->Phi; P.mat[3] = h->Psi;
@@ -1296,15 +1422,22 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     P.Wxi[0] = h->wA_xi; P.Wxi[1] = h->wB_xi; P.Wpsi[0] = h->wA_psi; P.Wpsi[1] = h->wB_psi;
     P.pri_xi = h->pri_xi; P.pri_psi = h->pri_psi; P.dual_xi = h->dual_xi; P.dual_psi = h->dual_psi;
     for (int k = 0; k < 4; k++) P.part[k] = h->part[k];
-    P.c = h->c; P.qh = h->qh; P.rh = h->rh; P.sigma = h->sigma; P.V = h->V; P.U = h->U; P.X = h->X; P.LV = h->LV;
+    P.qh = h->qh; P.rh = h->rh; P.V = h->V; P.U = h->U; P.X = h->X;
+    P.cm_c = h->cm_c; P.cm_lv = h->cm_lv; P.cm_beta = h->cm_beta; P.cm_uhat = h->cm_uhat; P.cm_e = h->cm_e;
     P.dist_part = h->dist_part; P.pinf = h->pinf; P.pinf_part = h->pinf_part;
     P.lambda_tab = h->lambda_tab; P.bar = h->grid_bar; P.iter_dev = h->iter_dev; P.phase_ns = h->phase_ns;
     P.step = h->step; P.inv_step = 1 / h->step; P.pen_x = h->pen_x; P.pen_xs = h->pen_xs;
     const SweepLayout Y = sweep_layout(h);
-    P.oG = Y.oG; P.oOT = Y.oOT; P.oL = Y.oL; P.oB = Y.oB; P.oX1 = Y.oX1; P.oY = Y.oY; P.oV = Y.oV; P.oScr2 = Y.oScr2;
-    P.pG = Y.pG; P.pOT = Y.pOT; P.pL = Y.pL; P.pB = Y.pB;
-    P.bG = (unsigned)(Y.pOT - Y.pG) * 4u; P.bOT = (unsigned)(Y.pL - Y.pOT) * 4u; P.bL = (unsigned)(Y.pB - Y.pL) * 4u;
+    P.oG = Y.oG; P.oOm = Y.oOm; P.oL = Y.oL; P.oX1 = Y.oX1; P.oY = Y.oY; P.oV = Y.oV; P.oScr2 = Y.oScr2; P.oStg = Y.oStg;
+    P.pG = Y.pG; P.pOm = Y.pOm; P.pL = Y.pL; P.pB = Y.pB;
+    P.bG = (unsigned)(Y.pOm - Y.pG) * 4u; P.bOm = (unsigned)(Y.pL - Y.pOm) * 4u; P.bL = (unsigned)(Y.pB - Y.pL) * 4u;
     P.bB = (unsigned)(Y.pack_floats - Y.pB) * 4u;
+    P.nxp = Y.nxp; P.nup = Y.nup; P.nvp = Y.nvp;
+    // chain-major copies of the per-solve vectors the sweeps stage with bulk copies
+    k_to_chain_major<<<d.nodes, 128, 0, st>>>(d.nodes, d.nv, Y.nvp, h->pos_dev, h->beta, h->cm_beta);
+    k_to_chain_major<<<d.nodes, 128, 0, st>>>(d.nodes, d.nu, Y.nup, h->pos_dev, h->uhat, h->cm_uhat);
+    k_to_chain_major<<<d.nodes, 128, 0, st>>>(d.nodes, d.nx, Y.nxp, h->pos_dev, h->e, h->cm_e);
+    h->launches += 3;
     RN_CUDA(h, cudaMemsetAsync(h->grid_bar, 0, sizeof(unsigned int), st));
     RN_CUDA(h, cudaMemsetAsync(h->dist_part, 0, 2 * sizeof(double) * h->persist_grid, st));
     void *args[] = {&P};

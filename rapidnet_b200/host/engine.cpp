@@ -71,14 +71,18 @@ real_t *Engine::buf(rn_buffer_id id) {
     return static_cast<real_t *>(p);
 }
 
-void Engine::factorStep() { check(rn_factor_step(h), "Engine::factorStep"); }
+// The reference runs on the legacy default stream, so a cudaMemcpy issued by the caller right after any of these
+// methods sees their results; the library's stream is non-blocking, hence the explicit rn_sync.
+void Engine::factorStep() { check(rn_factor_step(h), "Engine::factorStep"); check(rn_sync(h), "rn_sync"); }
 
 void Engine::updateStateControl(real_t *currentX, real_t *prevU, real_t *prevDemand) {
     check(rn_update_state(h, currentX, prevU, prevDemand), "Engine::updateStateControl");
+    check(rn_sync(h), "rn_sync");
 }
 
 void Engine::eliminateInputDistubanceCoupling(real_t *nominalDemand, real_t *nominalPrices) {
     check(rn_eliminate_coupling(h, nominalDemand, nominalPrices), "Engine::eliminateInputDistubanceCoupling");
+    check(rn_sync(h), "rn_sync");
 }
 
 void Engine::setPriceUncertaintyFlag(bool inputFlag) {
@@ -161,18 +165,20 @@ void SmpcController::initialiseSmpcController() {
 
 void SmpcController::initialiseAlgorithm() {
     check(rn_apg_init(ptrMyEngine->handle()), "SmpcController::initialiseAlgorithm");
+    check(rn_sync(ptrMyEngine->handle()), "rn_sync");
     refreshDevicePointers();
 }
 
-void SmpcController::dualExtrapolationStep(real_t lambda) {
-    check(rn_step(ptrMyEngine->handle(), RN_STEP_EXTRAPOLATE, lambda), "SmpcController::dualExtrapolationStep");
+// one protected step, synchronous like the reference's (see Engine::factorStep)
+void SmpcController::step(rn_step_kind kind, real_t lambda, const char *what) {
+    check(rn_step(ptrMyEngine->handle(), kind, lambda), what);
+    check(rn_sync(ptrMyEngine->handle()), "rn_sync");
 }
-void SmpcController::solveStep() { check(rn_step(ptrMyEngine->handle(), RN_STEP_SOLVE, 0.f), "SmpcController::solveStep"); }
-void SmpcController::proximalFunG() { check(rn_step(ptrMyEngine->handle(), RN_STEP_PROX, 0.f), "SmpcController::proximalFunG"); }
-void SmpcController::computeFixedPointResidual() {
-    check(rn_step(ptrMyEngine->handle(), RN_STEP_RESIDUAL, 0.f), "SmpcController::computeFixedPointResidual");
-}
-void SmpcController::dualUpdate() { check(rn_step(ptrMyEngine->handle(), RN_STEP_DUAL_UPDATE, 0.f), "SmpcController::dualUpdate"); }
+void SmpcController::dualExtrapolationStep(real_t lambda) { step(RN_STEP_EXTRAPOLATE, lambda, "SmpcController::dualExtrapolationStep"); }
+void SmpcController::solveStep() { step(RN_STEP_SOLVE, 0.f, "SmpcController::solveStep"); }
+void SmpcController::proximalFunG() { step(RN_STEP_PROX, 0.f, "SmpcController::proximalFunG"); }
+void SmpcController::computeFixedPointResidual() { step(RN_STEP_RESIDUAL, 0.f, "SmpcController::computeFixedPointResidual"); }
+void SmpcController::dualUpdate() { step(RN_STEP_DUAL_UPDATE, 0.f, "SmpcController::dualUpdate"); }
 
 uint_t SmpcController::algorithmApg() {
     const uint_t iters = ptrMySmpcConfig->getMaxIterations();

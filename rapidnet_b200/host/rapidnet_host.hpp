@@ -249,6 +249,7 @@ protected:
 private:
     void construct();
     void check(rn_status rc, const char *what);
+    void step(rn_step_kind kind, real_t lambda, const char *what);
     bool ownsObjects = false;
 };
 
