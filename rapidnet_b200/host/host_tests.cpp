@@ -67,6 +67,7 @@ static std::vector<real_t> from_device(const real_t *dev, size_t n) {
 }
 static void to_device(real_t *dev, const std::vector<real_t> &h) {
     T_ASSERT(cudaMemcpy(dev, h.data(), h.size() * sizeof(real_t), cudaMemcpyHostToDevice) == cudaSuccess);
+    T_ASSERT(cudaDeviceSynchronize() == cudaSuccess);   // pageable H2D may return before the DMA lands; the library's stream is non-blocking
 }
 static bool dev_close(const real_t *dev, const std::vector<real_t> &want, size_t off, size_t n, double tol = 1e-2) {
     std::vector<real_t> h = from_device(dev, n);
