@@ -253,10 +253,25 @@ __device__ __forceinline__ void row_store(float *row, const float (&v)[kTP]) {
         *reinterpret_cast<float4 *>(row + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
 
+// what tile_gemm does with its result
+enum GemmEpi { kEpiStore = 0, kEpiV = 1, kEpiLv = 2 };
+struct EpiArgs {
+    const int *colnode, *colid;   // per column: chain-major row / node id
+    const float *colp;            // per column: probability
+    const float *p2, *p3;         // kEpiV: Phi xi, Psi psi of the columns -- staged [col][ld23] or (staged == 0) chain-major global
+    float *out_g;                 // kEpiV: devVecV [node][ld_g];  kEpiLv: chain-major L v [row][ld_g]
+    int ncols, ld23, ld_g, staged, df;
+};
+
 // Y[r][c] = sum_k M[r + k*m] X[k][c],  r < m, c < kTP.  M (m x K, column-major), X, Y and scr2 in shared memory.
 // 256 threads compute: thread = (rows {rp, rp + 64}, 12 columns, one half of k); the upper half of k is handed over
-// through scr2.  All kPC threads call; ends with a CTA barrier.
-__device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float *X, float *Y, float *scr2) {
+// through scr2.  Epilogue (fused into the hand-over so that no extra pass / barrier is needed):
+//   kEpiStore  Y = result
+//   kEpiV      v = ((result / p_col) + Psi psi) + Phi xi  [df: result / p_col]  -> Y (next GEMM's input) and devVecV
+//   kEpiLv     result -> the chain-major L v array only
+// All kPC threads call; ends with a CTA barrier.
+template <int EPI>
+__device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float *X, float *Y, float *scr2, const EpiArgs *E) {
     const int t = threadIdx.x, ks = t >> 7, u = t & 127, rp = u & 63, cg = u >> 6;
     const bool work = ks < 2 && rp < m;
     const bool two = rp + 64 < m;
@@ -291,15 +306,61 @@ __device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float
     if (work && ks == 0) {
         const float4 *sp = reinterpret_cast<const float4 *>(scr2 + u * kTP);
         const float4 p0 = sp[0], p1 = sp[1], p2 = sp[2], p3 = sp[3], p4 = sp[4], p5 = sp[5];
-        float4 *y0 = reinterpret_cast<float4 *>(Y + rp * kTP + cg * 12);
-        y0[0] = make_float4(a0[0] + p0.x, a0[1] + p0.y, a0[2] + p0.z, a0[3] + p0.w);
-        y0[1] = make_float4(a0[4] + p1.x, a0[5] + p1.y, a0[6] + p1.z, a0[7] + p1.w);
-        y0[2] = make_float4(a0[8] + p2.x, a0[9] + p2.y, a0[10] + p2.z, a0[11] + p2.w);
-        if (two) {
-            float4 *y1 = reinterpret_cast<float4 *>(Y + (rp + 64) * kTP + cg * 12);
-            y1[0] = make_float4(a1[0] + p3.x, a1[1] + p3.y, a1[2] + p3.z, a1[3] + p3.w);
-            y1[1] = make_float4(a1[4] + p4.x, a1[5] + p4.y, a1[6] + p4.z, a1[7] + p4.w);
-            y1[2] = make_float4(a1[8] + p5.x, a1[9] + p5.y, a1[10] + p5.z, a1[11] + p5.w);
+        a0[0] += p0.x; a0[1] += p0.y; a0[2] += p0.z; a0[3] += p0.w; a0[4] += p1.x; a0[5] += p1.y; a0[6] += p1.z; a0[7] += p1.w;
+        a0[8] += p2.x; a0[9] += p2.y; a0[10] += p2.z; a0[11] += p2.w;
+        a1[0] += p3.x; a1[1] += p3.y; a1[2] += p3.z; a1[3] += p3.w; a1[4] += p4.x; a1[5] += p4.y; a1[6] += p4.z; a1[7] += p4.w;
+        a1[8] += p5.x; a1[9] += p5.y; a1[10] += p5.z; a1[11] += p5.w;
+        if (EPI != kEpiStore) {
+            // everything out of *E first (it sits behind a generic pointer: the global stores below would force re-reads)
+            const int c0 = cg * 12, ncols = E->ncols, ldg = E->ld_g, ld23 = E->ld23;
+            const bool staged = E->staged != 0, df = E->df != 0;
+            float *__restrict__ og = E->out_g;
+            const float *__restrict__ p2g = E->p2, *__restrict__ p3g = E->p3;
+            const int *rows = EPI == kEpiV ? E->colid : E->colnode, *cn = E->colnode;
+            const float *colp = E->colp;
+            int rg[12], r23[12];
+            float pinv[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const int c = c0 + i;
+                rg[i] = c < ncols ? rows[c] : 0;
+                r23[i] = staged ? c : (c < ncols ? cn[c] : 0);
+                pinv[i] = EPI == kEpiV ? colp[c] : 1.f;
+            }
+            if (EPI == kEpiV) {
+                float b30[12], b20[12], b31[12], b21[12];
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    b30[i] = b20[i] = b31[i] = b21[i] = 0.f;
+                    if (!df && c0 + i < ncols) {
+                        const float *q3 = p3g + (size_t)r23[i] * ld23 + rp, *q2 = p2g + (size_t)r23[i] * ld23 + rp;
+                        if (staged) { b30[i] = q3[0]; b20[i] = q2[0]; if (two) { b31[i] = q3[64]; b21[i] = q2[64]; } }
+                        else { b30[i] = __ldcg(q3); b20[i] = __ldcg(q2); if (two) { b31[i] = __ldcg(q3 + 64); b21[i] = __ldcg(q2 + 64); } }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    a0[i] = (a0[i] * pinv[i] + b30[i]) + b20[i];
+                    a1[i] = (a1[i] * pinv[i] + b31[i]) + b21[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                if (c0 + i < ncols) {
+                    og[(size_t)rg[i] * ldg + rp] = a0[i];
+                    if (two) og[(size_t)rg[i] * ldg + rp + 64] = a1[i];
+                } else { a0[i] = 0.f; a1[i] = 0.f; }
+            }
+        }
+        if (EPI != kEpiLv) {
+            float4 *y0 = reinterpret_cast<float4 *>(Y + rp * kTP + cg * 12);
+            y0[0] = make_float4(a0[0], a0[1], a0[2], a0[3]); y0[1] = make_float4(a0[4], a0[5], a0[6], a0[7]);
+            y0[2] = make_float4(a0[8], a0[9], a0[10], a0[11]);
+            if (two) {
+                float4 *y1 = reinterpret_cast<float4 *>(Y + (rp + 64) * kTP + cg * 12);
+                y1[0] = make_float4(a1[0], a1[1], a1[2], a1[3]); y1[1] = make_float4(a1[4], a1[5], a1[6], a1[7]);
+                y1[2] = make_float4(a1[8], a1[9], a1[10], a1[11]);
+            }
         }
     }
     cbar();
@@ -321,52 +382,54 @@ __device__ __forceinline__ bool stage_branches(const int *__restrict__ cum, int 
 }
 
 // v = ((-1/2 Omega sigma + Theta q_bar) + Psi psi) + Phi xi (:604-627), with Theta q_bar = -1/2 Omega (G q_bar) (Theta is
-// -1/2 Omega Bbar', Engine.cu:729-734) [df: v = -1/2 Omega r]: Y = OmegaBar X1s on entry, Omega_i = OmegaBar / p_i.
-// p2 / p3: Phi xi, Psi psi of the tile's columns, [col][nvp] in staging (chains) or read from the chain-major arrays
-__device__ __noinline__ void sweep_vcombine(const PArgs &P, int ncols, bool staged) {
-    const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, nv = P.nv, nvp = P.nvp;
+// -1/2 Omega Bbar', Engine.cu:729-734) [df: v = -1/2 Omega r]: Y = OmegaBar X1s on entry, Omega_i = OmegaBar / p_i
+// (colp holds 1 / p_i).  All threads: thread = (row, every 4th column).  V rows (next GEMM's input) and devVecV.
+__device__ __forceinline__ void sweep_vcombine(const PArgs &P, const SweepSmem &S, int ncols, bool staged) {
+    const int e = threadIdx.x & 127, s0 = threadIdx.x >> 7, nv = P.nv, nvp = P.nvp, T = P.N - P.cs;
     if (e >= nv) return;
     const bool df = P.df_mode != 0;
-    const int T = P.N - P.cs;
     const float *__restrict__ g2 = P.part[2], *__restrict__ g3 = P.part[3];
+    float *__restrict__ Vg = P.V;
     const float *s2 = S.stg + T * P.nxp + 3 * T * nvp, *s3 = s2 + T * nvp;
-    float y[kTP];
-    row_load(S.Y + e * kTP, y);
+    float y[kTP / 4], b2[kTP / 4], b3[kTP / 4];
 #pragma unroll
-    for (int s = 0; s < kTP; s++) {
+    for (int k = 0; k < kTP / 4; k++) {
+        const int s = s0 + 4 * k;
+        y[k] = S.Y[e * kTP + s];
+        b2[k] = b3[k] = 0.f;
+        if (!df && s < ncols) {
+            b3[k] = staged ? s3[s * nvp + e] : __ldcg(g3 + (size_t)S.colnode[s] * nvp + e);
+            b2[k] = staged ? s2[s * nvp + e] : __ldcg(g2 + (size_t)S.colnode[s] * nvp + e);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kTP / 4; k++) {
+        const int s = s0 + 4 * k;
         float v = 0.f;
         if (s < ncols) {
-            v = y[s] / S.colp[s];
-            if (!df) {
-                const float b3 = staged ? s3[s * nvp + e] : __ldcg(g3 + (size_t)S.colnode[s] * nvp + e);
-                const float b2 = staged ? s2[s * nvp + e] : __ldcg(g2 + (size_t)S.colnode[s] * nvp + e);
-                v = (v + b3) + b2;
-            }
+            v = (y[k] * S.colp[s] + b3[k]) + b2[k];
+            Vg[(size_t)S.colid[s] * nv + e] = v;
         }
-        y[s] = v;
+        S.V[e * kTP + s] = v;
     }
-    row_store(S.V + e * kTP, y);
 }
 
 // common end of the backward sweep of a tile: X1s = -1/2 (sigma + G q_bar) (df: -1/2 r) on entry
 __device__ __noinline__ void sweep_backward_finish(const PArgs &P, int ncols, bool staged, uint32_t mpar, StagePhase &ph, int next_chain) {
     const SweepSmem S = sweep_smem(P);
-    const int nv = P.nv, nu = P.nu;
-    float *Vg = P.V, *LVg = P.cm_lv;
-    const int nup = P.nup;
+    const int nv = P.nv, nu = P.nu, nup = P.nup;
+    float *LVg = P.cm_lv;
     mbar_wait(&S.mfull[1], mpar);
-    tile_gemm(S.Om, nv, nv, S.X1 + P.nx * kTP, S.Y, S.scr2);                      // OmegaBar (sigma + G q_bar) (-1/2 folded in)
+    tile_gemm<kEpiStore>(S.Om, nv, nv, S.X1 + P.nx * kTP, S.Y, S.scr2, nullptr);   // OmegaBar (sigma + G q_bar) (-1/2 folded in)
     dstamp(P, 6);
     if (staged && !P.df_mode) { mbar_wait(&S.sfull[2], ph.v); ph.v ^= 1; }
-    sweep_vcombine(P, ncols, staged);
+    sweep_vcombine(P, S, ncols, staged);
     cbar();
     // the staging area is free: request the next chain's blocks, they land while L v is formed and written
     if (next_chain >= 0 && threadIdx.x == 0) issue_chain_backward_loads(P, next_chain);
-    cols_to_global(S.V, S.colid, ncols, nv, nv, Vg);                             // devVecV
     dstamp(P, 7);
     mbar_wait(&S.mfull[2], mpar);
-    tile_gemm(S.L, nu, nv, S.V, S.Y, S.scr2);                                    // L v   (:701, :727)
+    tile_gemm<kEpiStore>(S.L, nu, nv, S.V, S.Y, S.scr2, nullptr);                  // L v   (:701, :727)
     dstamp(P, 8);
     cols_to_global(S.Y, S.colnode, ncols, nu, nup, LVg);
     cbar();
@@ -382,7 +445,7 @@ __device__ __forceinline__ void chain_columns(const PArgs &P, int j) {
         const int node = t < T ? __ldg(P.cum + P.cs + t) + j : 0;
         S.colid[t] = node;
         S.colnode[t] = t < T ? P.n_crown + j * T + t : 0;
-        S.colp[t] = t < T ? __ldg(P.prob + __ldg(P.omega_idx + node)) : 1.f;
+        S.colp[t] = t < T ? 1.f / __ldg(P.prob + __ldg(P.omega_idx + node)) : 1.f;   // Omega_i = OmegaBar / p_i
     }
     if (t == 32) {
         int a = __ldg(P.parent + __ldg(P.cum + P.cs) + j);
@@ -446,7 +509,7 @@ __device__ __noinline__ void chain_backward(const PArgs &P, int j, int next_chai
     cbar();
     dstamp(P, 3);
     mbar_wait(&S.mfull[0], mpar);
-    tile_gemm(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2);                               // G q_bar   (:644-646)
+    tile_gemm<kEpiStore>(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2, nullptr);                               // G q_bar   (:644-646)
     dstamp(P, 4);
     mbar_wait(&S.sfull[1], ph.r); ph.r ^= 1;
     chain_rscan(P, j);
@@ -630,7 +693,7 @@ __device__ __noinline__ void chain_forward(const PArgs &P, int j, int next_chain
     cols_to_global(S.X1, S.colid, T, nu, nu, Ug);                                 // devVecU
     dstamp(P, 16);
     mbar_wait(&S.mfull[3], mpar);
-    tile_gemm(S.B, nx, nu, S.X1, S.Y, S.scr2);                                   // B u   (:715, :736)
+    tile_gemm<kEpiStore>(S.B, nx, nu, S.X1, S.Y, S.scr2, nullptr);                                   // B u   (:715, :736)
     dstamp(P, 17);
     chain_xscan(P, j);
     cbar();
@@ -665,16 +728,16 @@ __device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols) {
             const int lo = __ldg(rng + 2 * s), hi = __ldg(rng + 2 * s + 1);
             float cpart = 0.f, bpart = 0.f;
             int jn = lo + g;
-            for (; jn + 12 < hi; jn += 16) {   // four rows in flight
-                float c4[4], b4[4];
+            for (; jn + 28 < hi; jn += 32) {   // eight rows in flight
+                float c4[8], b4[8];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
+                for (int k = 0; k < 8; k++) {
                     const size_t r = (size_t)(jn + 4 * k);
                     c4[k] = ex ? __ldcg(cg + r * nxp + e) : 0.f;
                     b4[k] = ev ? (__ldg(bg + r * nvp + e) + __ldcg(p0 + r * nvp + e)) + __ldcg(p1 + r * nvp + e) : 0.f;
                 }
 #pragma unroll
-                for (int k = 0; k < 4; k++) { cpart += c4[k]; bpart += b4[k]; }
+                for (int k = 0; k < 8; k++) { cpart += c4[k]; bpart += b4[k]; }
             }
             for (; jn < hi; jn += 4) {
                 if (ex) cpart += __ldcg(cg + (size_t)jn * nxp + e);
@@ -686,15 +749,15 @@ __device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols) {
             const int lo = __ldg(rng + 2 * cs) - head0, hi = __ldg(rng + 2 * cs + 1) - head0;
             float hq = 0.f, hr = 0.f;
             int h = lo + g;
-            for (; h + 12 < hi; h += 16) {
-                float q4[4], r4[4];
+            for (; h + 28 < hi; h += 32) {
+                float q4[8], r4[8];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
+                for (int k = 0; k < 8; k++) {
                     q4[k] = ex ? __ldcg(qhg + (size_t)(h + 4 * k) * nx + e) : 0.f;
                     r4[k] = ev ? __ldcg(rhg + (size_t)(h + 4 * k) * nv + e) : 0.f;
                 }
 #pragma unroll
-                for (int k = 0; k < 4; k++) { hq += q4[k]; hr += r4[k]; }
+                for (int k = 0; k < 8; k++) { hq += q4[k]; hr += r4[k]; }
             }
             for (; h < hi; h += 4) {
                 if (ex) hq += __ldcg(qhg + (size_t)h * nx + e);
@@ -754,13 +817,13 @@ __device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, u
     if (t < kTP) {
         const int node = t < ncols ? i0 + t : 0;
         S.colnode[t] = node; S.colid[t] = node;
-        S.colp[t] = t < ncols ? __ldg(P.prob + __ldg(P.omega_idx + node)) : 1.f;
+        S.colp[t] = t < ncols ? 1.f / __ldg(P.prob + __ldg(P.omega_idx + node)) : 1.f;
     }
     cbar();
     crown_sums(P, i0, ncols);
     dstamp(P, 11);
     mbar_wait(&S.mfull[0], mpar);
-    tile_gemm(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2);                               // G [QS | q_bar]
+    tile_gemm<kEpiStore>(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2, nullptr);                               // G [QS | q_bar]
     crown_sigma(P, ncols);
     cbar();
     dstamp(P, 12);
@@ -808,7 +871,7 @@ __device__ __noinline__ void crown_forward(const PArgs &P, int i0, int ncols, ui
     if (t < nx) row_load(S.scr2 + t * kTP, xb);
     cbar();
     mbar_wait(&S.mfull[3], mpar);
-    tile_gemm(S.B, nx, nu, S.X1, S.Y, S.scr2);                                   // B sum_path u
+    tile_gemm<kEpiStore>(S.B, nx, nu, S.X1, S.Y, S.scr2, nullptr);                                   // B sum_path u
     if (t < nx) {
         float y[kTP];
         row_load(S.Y + t * kTP, y);
