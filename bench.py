@@ -14,6 +14,9 @@ missing from the reference).
           to the host -- H2D and D2H inside the timed region.
   N > 1 : one process per GPU, each rank solves its own independent SMPC instance (same network and tree, its
           own initial tank levels): closed-loop Monte-Carlo instances shard with no data-path collective ("weak").
+          The same line also carries "tree_partition": ONE larger tree (C3, K=480, 10 171 nodes) cut below its last
+          branching stage across the N GPUs -- the crown replicated, the chains split, q/r of the chain heads and the
+          prox distances exchanged inside the persistent kernel over NVLink peer memory (rapidnet_b200/partition.py).
   --impl reference : the reference's own CUDA/cuBLAS build (oracle/_ref/ref_driver, compiled from
           /root/reference/src in place) on the same workload through its controlAction(real_t*); if that binary is
           missing, the CPU oracle port on the host cores.  Rank 0 only.
@@ -171,6 +174,42 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def bench_partition(args, rank, world, local, stream):
+    """ONE tree cut across the `world` GPUs (strong scaling): iterations/s of the partitioned solve, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from rapidnet_b200 import cabi
+    from rapidnet_b200.datagen import named_problem
+    from rapidnet_b200.partition import DistributedSolver
+    prob = named_problem(args.partition_workload, max_iter=args.iters)
+    ds = DistributedSolver(prob, rank, world, device=local)
+    ds.solver.set_stream(stream.cuda_stream)
+    ds.solver.set_modes(cabi.SWEEP_PERSISTENT, cabi.FACTORS_FULL if args.factors == "full" else cabi.FACTORS_DF)
+    ds.setup(slot=0)
+    iters, steps = args.iters, max(1, min(args.steps, 3))
+    with torch.cuda.stream(stream):
+        ds.apg_solve(iters, want_u0=False)
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            ds.apg_solve(iters, want_u0=False)
+        e1.record(stream)
+        dist.barrier(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    d = prob.dims
+    out = {"workload": describe(args.partition_workload, prob), "n_gpus": world, "scaling": "strong", "steps": steps,
+           "value": steps * iters / (ms * 1e-3), "unit": UNIT, "ms_per_solve": ms / steps,
+           "nodes_per_rank": int(ds.local.tree.nodes), "crown_nodes_replicated": int(ds.meta.n_crown),
+           "exchange_bytes_per_iteration_per_rank": int((ds.local.tree.K * (d["nx"] + d["nv"]) * 4 + 16) * (world - 1)),
+           "exchange": "in-kernel stores to peer memory (CUDA IPC over NVLink) + flag barriers; no NCCL on the data path"}
+    ds.close()
+    return out
+
+
 def describe(workload, prob):
     d = prob.dims
     return (f"{workload}: Barcelona-shaped DWN nx={d['nx']} nu={d['nu']} nd={d['nd']} nv={d['nv']} N={d['N']}, "
@@ -190,6 +229,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", default="persistent", choices=["persistent", "chain", "per_stage"])
     ap.add_argument("--factors", default="full", choices=["full", "df"])
+    ap.add_argument("--partition-workload", default="C3", help="N > 1: the tree that is cut across the GPUs ('' = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -262,6 +302,10 @@ def main():
         ms_e2e = max(f0.elapsed_time(f1), wall_ms)
         clocks = sampler.stop() if rank == 0 else None
 
+    part = None
+    if world > 1 and args.partition_workload:
+        part = bench_partition(args, rank, world, local, stream)
+
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -276,6 +320,14 @@ def main():
         stream_bytes = info.stream_bytes_per_iteration
         achieved = stream_bytes / (prof["stream"] * 1e-3) / 1e9 if prof["stream"] > 0 else 0.0
         total_prof = sum(prof.values())
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and args.workload == "C2" and args.sweep == "persistent" and args.factors == "full":
+            tj = json.load(open(tpath))
+            traffic = tj["dram_bytes_per_iteration"]
+            traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of {tj['kernel']} "
+                            f"({tj['iterations_in_capture']} iterations, ALL phases) / iterations; compare with the whole-iteration "
+                            f"algorithmic bytes {info.apg_bytes_per_iteration:.0f}")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -291,8 +343,11 @@ def main():
             "gpu_launches": int(launches),
             "launches_per_iteration": int(info.launches_per_iteration),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_stream", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+            "roofline": {"bound": "hbm",
+                         "kernel": ("k_apg_persistent, phase S (factor-matrix stream + fused element-wise pass) of one iteration"
+                                    if args.sweep == "persistent" else "k_stream"),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
                          "algorithmic_bytes_per_launch": stream_bytes, "launch_ms": prof["stream"],
                          "share_of_iteration": prof["stream"] / total_prof if total_prof > 0 else None,
                          "iteration_ms_by_kernel": prof,
@@ -300,6 +355,8 @@ def main():
                                              "achieved": info.apg_bytes_per_iteration / (ms_dev / args.steps / iters * 1e-3) / 1e9,
                                              "frac": info.apg_bytes_per_iteration / (ms_dev / args.steps / iters * 1e-3) / 1e9 / peak}},
         }
+        if part is not None:
+            line["tree_partition"] = part
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = max(4, min(iters, args.cpu_sample_iters))

@@ -43,6 +43,9 @@ typedef struct rn_dims {
     int N, K, nodes;          /* horizon, scenarios, tree nodes */
     int n_nonleaf;            /* nNonLeafNodes */
     int n_children_tot;       /* nChildrenTot */
+    int chain_stage_hint;     /* 0: whole tree (the reference's case).  > 0: this tree is one rank's part of a larger
+                                 tree (crown + some of its scenario chains, rn_dist_*) whose non-branching tail starts at
+                                 this stage; the Omega/Theta aliasing (Engine.cu:210-221) then follows the larger tree */
 } rn_dims;
 
 /* ScenarioTree getters (ScenarioTree.cuh:100-154); arrays as they appear in the JSON. */
@@ -161,6 +164,7 @@ typedef enum rn_buffer_id {
     RN_BUF_VEC_RESIDUAL_PSI,
     RN_BUF_CONTROL_ACTION,     /* devControlAction       nu                */
     RN_BUF_STATE_UPDATE,       /* devStateUpdate         nx                */
+    RN_BUF_VEC_ZETA,           /* devVecZeta             nodes*nu   (calculateZeta, Utilities.cu:100-131) */
     RN_BUF_COUNT_
 } rn_buffer_id;
 
@@ -233,6 +237,32 @@ rn_status rn_control_action(rn_handle *h, const float *x, const float *u_prev, c
 /* plant update of SmpcController::moveForewardInTime (:1679-1717): x_next = x + B*u0_clamped
  * (reference drops the disturbance term).  Outputs nx and nu host floats. */
 rn_status rn_move_forward(rn_handle *h, float *x_next_host, float *u_applied_host);
+
+/* ---- one tree across several GPUs (no counterpart in the reference, which is single-GPU) ------------------------
+ * Subtree partition: every rank (one process per GPU) holds the stages above the last branching stage (the "crown",
+ * replicated) and a contiguous range of the scenario chains below it; its handle is created on that LOCAL tree.  Per
+ * APG iteration the ranks exchange, inside the persistent kernel and over NVLink peer memory, q and r of their
+ * chain heads (the near-root contributions of SmpcController::solveStep's backward sweep, :661-672) and the two
+ * squared prox distances (:792, :810).  Call order: rn_create (local tree) -> rn_dist_prepare -> exchange the 64-byte
+ * handles between the processes (e.g. torch.distributed.all_gather_object) -> rn_dist_connect -> factor step, solves. */
+#define RN_IPC_HANDLE_BYTES 64
+/* world <= 8 ranks; this rank owns global chains [chain_offset, chain_offset + K_local) of K_global; head_lo/head_hi
+ * [number of crown nodes]: global chain-index range of the chain heads below each crown node.  Writes the CUDA IPC
+ * handle of this rank's exchange buffer to ipc_handle_out. */
+rn_status rn_dist_prepare(rn_handle *h, int world, int rank, int K_global, int chain_offset, const int *head_lo,
+                          const int *head_hi, unsigned char *ipc_handle_out /*[RN_IPC_HANDLE_BYTES]*/);
+/* handles: world x RN_IPC_HANDLE_BYTES, rank-major (the entry of this rank is ignored) */
+rn_status rn_dist_connect(rn_handle *h, const unsigned char *handles);
+/* The only per-SOLVE quantity that couples the ranks: zeta of a node just above the chain heads sums over ALL of
+ * its children (calculateZeta, Utilities.cu:100-131), some of which live on other ranks.  After rn_eliminate_coupling
+ * the host sums the ranks' contributions and hands the corrected zeta rows of nodes [first, first + count) back;
+ * beta = 2 (W L)' zeta + p L' alpha (Engine.cu:1253-1261) is recomputed for them. */
+rn_status rn_dist_fix_crown_beta(rn_handle *h, int first, int count, const float *zeta_rows /*[count*nu]*/);
+/* per iteration (|res|, res) at the arg-max of the xi block and of the psi block of THIS rank's nodes, 4 floats each:
+ * the host merges them across ranks into vecPrimalInfs (updatePrimalInfeasibity, :1480-1496) */
+rn_status rn_read_pinf_parts(rn_handle *h, int iterations, float *host /*[iterations*4]*/);
+/* nonzero when a cross-GPU wait of the last solve timed out (a peer died): results are invalid */
+rn_status rn_dist_error(rn_handle *h, int *timed_out);
 
 /* ---- buffers ---------------------------------------------------------------------------------- */
 

@@ -30,7 +30,7 @@ BUFFER_IDS = [
     "MAT_G", "MAT_SIGMA", "MAT_WV", "DIAG", "VEC_E", "VEC_UHAT", "VEC_ALPHA", "VEC_BETA", "VEC_CURRENT_STATE",
     "VEC_PREV_CONTROL", "VEC_PREV_UHAT", "VEC_PREV_DEMAND", "VEC_X", "VEC_U", "VEC_V", "VEC_XI", "VEC_PSI",
     "VEC_ACCEL_XI", "VEC_ACCEL_PSI", "VEC_PRIMAL_XI", "VEC_PRIMAL_PSI", "VEC_DUAL_XI", "VEC_DUAL_PSI",
-    "VEC_UPDATE_XI", "VEC_UPDATE_PSI", "VEC_RESIDUAL_XI", "VEC_RESIDUAL_PSI", "CONTROL_ACTION", "STATE_UPDATE",
+    "VEC_UPDATE_XI", "VEC_UPDATE_PSI", "VEC_RESIDUAL_XI", "VEC_RESIDUAL_PSI", "CONTROL_ACTION", "STATE_UPDATE", "VEC_ZETA",
 ]
 BUF = {name: i for i, name in enumerate(BUFFER_IDS)}
 
@@ -40,11 +40,13 @@ EXPORTS = [
     "rn_get_info", "rn_set_null_space", "rn_factor_step", "rn_update_state", "rn_eliminate_coupling",
     "rn_set_uncertainty", "rn_apg_init", "rn_step", "rn_apg_solve", "rn_control_action", "rn_move_forward",
     "rn_buffer", "rn_read_buffer", "rn_write_buffer", "rn_profile_stream", "rn_profile_kernels", "rn_phase_times",
+    "rn_dist_prepare", "rn_dist_connect", "rn_dist_fix_crown_beta", "rn_read_pinf_parts", "rn_dist_error",
 ]
 
 
 class RnDims(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("nx", "nu", "nd", "ne", "nv", "N", "K", "nodes", "n_nonleaf", "n_children_tot")]
+    _fields_ = [(n, C.c_int) for n in ("nx", "nu", "nd", "ne", "nv", "N", "K", "nodes", "n_nonleaf", "n_children_tot",
+                                       "chain_stage_hint")]
 
 
 class RnTree(C.Structure):
@@ -111,6 +113,11 @@ def load():
     lib.rn_profile_stream.argtypes = [H, C.c_int, FP]
     lib.rn_profile_kernels.argtypes = [H, C.c_int, FP]
     lib.rn_phase_times.argtypes = [H, C.POINTER(C.c_double)]
+    lib.rn_dist_prepare.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, IP, IP, C.c_char_p]
+    lib.rn_dist_connect.argtypes = [H, C.c_char_p]
+    lib.rn_dist_fix_crown_beta.argtypes = [H, C.c_int, C.c_int, FP]
+    lib.rn_read_pinf_parts.argtypes = [H, C.c_int, FP]
+    lib.rn_dist_error.argtypes = [H, IP]
     for name in EXPORTS:
         if name != "rn_last_error":
             getattr(lib, name).restype = C.c_int
@@ -136,7 +143,7 @@ class Solver:
     Method names follow the reference (Engine::factorStep, ::updateStateControl,
     ::eliminateInputDistubanceCoupling; SmpcController::algorithmApg, ::controlAction)."""
 
-    def __init__(self, problem, device: int = 0):
+    def __init__(self, problem, device: int = 0, chain_stage_hint: int = 0):
         lib = load()
         n, t, c = problem.network, problem.tree, problem.config
         f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
@@ -149,7 +156,7 @@ class Solver:
             Ed=f32(n.Ed), xmin=f32(n.xmin), xmax=f32(n.xmax), xsafe=f32(n.xsafe), umin=f32(n.umin), umax=f32(n.umax),
             a1=f32(n.alpha1), W=f32(c.costW), pc=f32(c.precond))
         k = self._keep
-        dims = RnDims(n.nx, n.nu, n.nd, n.ne, c.nv, t.N, t.K, t.nodes, t.n_nonleaf, t.n_children_tot)
+        dims = RnDims(n.nx, n.nu, n.nd, n.ne, c.nv, t.N, t.K, t.nodes, t.n_nonleaf, t.n_children_tot, int(chain_stage_hint))
         tree = RnTree(_ip(k["stages"]), _ip(k["nps"]), _ip(k["cum"]), _ip(k["leaves"]), _ip(k["children"]),
                       _ip(k["ancestor"]), _ip(k["nch"]), _ip(k["ncc"]), _fp(k["prob"]), _fp(k["ed"]), _fp(k["ep"]))
         net = RnNetwork(_fp(k["B"]), _fp(k["Gd"]), _fp(k["E"]), _fp(k["Ed"]), _fp(k["xmin"]), _fp(k["xmax"]),
@@ -239,6 +246,33 @@ class Solver:
         self._check(load().rn_control_action(self.h, *[_fp(a) for a in args], int(iterations), int(bool(clamp)),
                                              _fp(u0)), "rn_control_action")
         return u0
+
+    # -- one tree across several GPUs (rapidnet_b200/partition.py drives these) --
+    def dist_prepare(self, world: int, rank: int, k_global: int, chain_offset: int, head_lo, head_hi) -> bytes:
+        lo = np.ascontiguousarray(head_lo, dtype=np.int32)
+        hi = np.ascontiguousarray(head_hi, dtype=np.int32)
+        out = C.create_string_buffer(64)
+        self._check(load().rn_dist_prepare(self.h, int(world), int(rank), int(k_global), int(chain_offset), _ip(lo), _ip(hi),
+                                           out), "rn_dist_prepare")
+        return out.raw
+
+    def dist_connect(self, handles):
+        blob = b"".join(handles)
+        self._check(load().rn_dist_connect(self.h, blob), "rn_dist_connect")
+
+    def dist_fix_crown_beta(self, first: int, zeta_rows):
+        z = np.ascontiguousarray(zeta_rows, dtype=np.float32)
+        self._check(load().rn_dist_fix_crown_beta(self.h, int(first), int(z.shape[0]), _fp(z)), "rn_dist_fix_crown_beta")
+
+    def pinf_parts(self, iterations: int) -> np.ndarray:
+        out = np.zeros((max(iterations, 1), 4), dtype=np.float32)
+        self._check(load().rn_read_pinf_parts(self.h, int(iterations), _fp(out)), "rn_read_pinf_parts")
+        return out[:iterations]
+
+    def dist_error(self) -> bool:
+        flag = np.zeros(1, dtype=np.int32)
+        self._check(load().rn_dist_error(self.h, _ip(flag)), "rn_dist_error")
+        return bool(flag[0])
 
     def move_forward(self):
         x = np.zeros(self.dims.nx, dtype=np.float32)

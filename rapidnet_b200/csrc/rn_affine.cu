@@ -84,6 +84,42 @@ k_elim_beta(int nodes, int nu, int nv, const int *__restrict__ parent, const int
     }
 }
 
+// beta = 2 (W L)' zeta + p L' alpha for nodes [first, first + count) from the zeta rows already in place
+__global__ void __launch_bounds__(256)
+k_beta_from_zeta(int first, int nu, int nv, const float *__restrict__ prob, const float *__restrict__ zeta,
+                 const float *__restrict__ alpha, const float *__restrict__ Wv, const float *__restrict__ L,
+                 float *__restrict__ beta) {
+    extern __shared__ float sm[];   // zeta[nu] | alpha[nu]
+    float *sz = sm, *sa = sm + nu;
+    const int i = first + blockIdx.x;
+    const float p = prob[i];
+    for (int t = threadIdx.x; t < nu; t += blockDim.x) { sz[t] = zeta[(size_t)i * nu + t]; sa[t] = alpha[(size_t)i * nu + t]; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < nv; r += nwarps) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int t = lane; t < nu; t += 32) {
+            s1 += Wv[t + (size_t)r * nu] * sz[t];
+            s2 += L[t + (size_t)r * nu] * sa[t];
+        }
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        if (lane == 0) beta[(size_t)i * nv + r] = 2.f * s1 + p * s2;
+    }
+}
+
+rn_status fix_beta(Handle *h, int first, int count, const float *zeta_rows) {
+    if (count == 0) return RN_OK;
+    const rn_dims &d = h->d;
+    RN_CUDA(h, cudaMemcpyAsync(h->zeta + (size_t)first * d.nu, zeta_rows, (size_t)count * d.nu * sizeof(float),
+                               cudaMemcpyHostToDevice, h->stream));
+    k_beta_from_zeta<<<count, 256, 2 * d.nu * sizeof(float), h->stream>>>(first, d.nu, d.nv, h->t.prob, h->zeta, h->alpha, h->Wv,
+                                                                           h->L, h->beta);
+    h->launches += 1;
+    RN_CUDA(h, cudaGetLastError());
+    RN_CUDA(h, cudaStreamSynchronize(h->stream));   // zeta_rows is the caller's buffer
+    return RN_OK;
+}
+
 rn_status update_state(Handle *h, const float *x, const float *u_prev, const float *d_prev) {
     const rn_dims &d = h->d;
     // staged through pinned memory: one async H2D per vector, no driver-side pageable staging

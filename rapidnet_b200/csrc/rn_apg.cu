@@ -890,7 +890,7 @@ static rn_status enqueue_persistent(Handle *h, int iterations) {
         h->acc_xi = last ? h->wB_xi : h->wA_xi; h->acc_psi = last ? h->wB_psi : h->wA_psi;
         FinalArgs F = make_final_args(h);
         F.yA_xi = h->yA_xi; F.yA_psi = h->yA_psi; F.yB_xi = h->yB_xi; F.yB_psi = h->yB_psi;
-        F.n_slots = h->persist_grid;
+        F.n_slots = h->dist_world > 1 ? 1 : h->persist_grid;   // several GPUs: the kernel left the global sums in slot 0
         F.do_branch = 1; F.do_residual = 1; F.do_update = 1; F.parity_swap = 1; F.log_inf = 1;
         k_finalize<<<finalize_grid(h), kEwThreads, 0, h->stream>>>(F);
         RN_CUDA(h, cudaGetLastError());

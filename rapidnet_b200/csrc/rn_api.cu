@@ -34,6 +34,11 @@ static bool build_tree_host(Handle *h, const rn_tree *t) {
     h->fb_node = 0; h->fb_stage = 0;
     for (int s = 0; s < d.N - 1; s++)
         if (h->h_nps[s] == h->h_nps[s + 1]) { h->fb_node = h->h_cum[s + 1]; h->fb_stage = s; break; }
+    const int hint = d.chain_stage_hint;
+    if (hint > 0) {   // one rank's part of a larger tree: the larger tree's first repeated stage is its chain stage
+        if (hint >= d.N) return false;
+        if (hint < d.N - 1) { h->fb_node = h->h_cum[hint + 1]; h->fb_stage = hint; } else { h->fb_node = 0; h->fb_stage = 0; }
+    }
     h->n_omega = h->fb_node > 0 ? h->fb_node : d.nodes;
     h->h_omega_idx.resize(d.nodes);
     for (int s = 0; s < d.N; s++)
@@ -51,6 +56,10 @@ static bool build_tree_host(Handle *h, const rn_tree *t) {
         for (int j = 0; j < h->h_nps[s] && ok; j++) ok = (h->h_parent[h->h_cum[s] + j] == h->h_cum[s - 1] + j);
         if (!ok) break;
         cs--;
+    }
+    if (hint > 0) {
+        if (cs > hint) return false;   // the tail must be non-branching from the hinted stage on
+        cs = hint;
     }
     // a chain CTA keeps one Omega/Theta in shared memory: the alias must be constant along each chain
     for (int s = cs + 1; s < d.N && cs < d.N; s++)
@@ -200,6 +209,7 @@ rn_status rn_destroy(rn_handle *hh) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     rn::apg_release_graph(h);
+    for (int r = 0; r < 8; r++) if (h->xchg_opened[r] && h->xchg_peer[r]) cudaIpcCloseMemHandle(h->xchg_peer[r]);
     for (void *p : h->allocs) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -371,6 +381,78 @@ rn_status rn_move_forward(rn_handle *hh, float *x_next_host, float *u_applied_ho
     return RN_OK;
 }
 
+rn_status rn_dist_prepare(rn_handle *hh, int world, int rank, int K_global, int chain_offset, const int *head_lo,
+                          const int *head_hi, unsigned char *ipc_handle_out) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return RN_ERR_INVALID;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || !ipc_handle_out)
+        return rn::fail(h, RN_ERR_INVALID, "rn_dist_prepare: world %d / rank %d out of range (1..8 ranks)", world, rank);
+    if (h->persist_ready || h->xchg) return rn::fail(h, RN_ERR_STATE, "rn_dist_prepare must precede the first solve");
+    if (!rn::persistent_supported(h)) return rn::fail(h, RN_ERR_INVALID, "the tree partition needs the persistent kernel, which does not fit this problem");
+    const int n_crown = h->h_cum[h->chain_stage];
+    if (chain_offset < 0 || chain_offset + h->d.K > K_global) return rn::fail(h, RN_ERR_INVALID, "rn_dist_prepare: chain range outside K_global");
+    if (world > 1 && (!head_lo || !head_hi)) return rn::fail(h, RN_ERR_INVALID, "rn_dist_prepare: head ranges missing");
+    h->dist_world = world; h->dist_rank = rank; h->dist_K_glob = K_global; h->dist_chain_off = chain_offset;
+    if (world > 1) { h->dist_head_lo.assign(head_lo, head_lo + n_crown); h->dist_head_hi.assign(head_hi, head_hi + n_crown); }
+    RN_CUDA(h, cudaSetDevice(h->device));
+    RN_CHECK(rn::ensure_xchg(h));
+    cudaIpcMemHandle_t mh;
+    static_assert(sizeof(mh) == RN_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    RN_CUDA(h, cudaIpcGetMemHandle(&mh, h->xchg));
+    memcpy(ipc_handle_out, &mh, sizeof(mh));
+    return RN_OK;
+}
+
+rn_status rn_dist_connect(rn_handle *hh, const unsigned char *handles) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !handles) return RN_ERR_INVALID;
+    if (!h->xchg) return rn::fail(h, RN_ERR_STATE, "rn_dist_connect before rn_dist_prepare");
+    RN_CUDA(h, cudaSetDevice(h->device));
+    for (int r = 0; r < h->dist_world; r++) {
+        if (r == h->dist_rank || h->xchg_peer[r]) continue;
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, handles + (size_t)r * RN_IPC_HANDLE_BYTES, sizeof(mh));
+        void *p = nullptr;
+        RN_CUDA(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->xchg_peer[r] = p; h->xchg_opened[r] = true;
+    }
+    return RN_OK;
+}
+
+rn_status rn_dist_fix_crown_beta(rn_handle *hh, int first, int count, const float *zeta_rows) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !zeta_rows || first < 0 || count < 0 || first + count > h->d.nodes) return RN_ERR_INVALID;
+    if (!h->eliminated) return rn::fail(h, RN_ERR_STATE, "rn_dist_fix_crown_beta before rn_eliminate_coupling");
+    return rn::fix_beta(h, first, count, zeta_rows);
+}
+
+rn_status rn_read_pinf_parts(rn_handle *hh, int iterations, float *host) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !host || iterations < 0) return RN_ERR_INVALID;
+    if (iterations > h->pinf4_cap) return rn::fail(h, RN_ERR_STATE, "rn_read_pinf_parts: only %d iterations were logged", h->pinf4_cap);
+    // iterations 0 .. n-2 come from the persistent kernel; the last one is finished by k_finalize (scalar log only)
+    RN_CUDA(h, cudaMemcpyAsync(host, h->pinf4, (size_t)iterations * 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RN_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RN_OK;
+}
+
+rn_status rn_dist_error(rn_handle *hh, int *timed_out) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !timed_out) return RN_ERR_INVALID;
+    *timed_out = 0;
+    if (!h->xchg) return RN_OK;
+    // the flag is the last word of the exchange buffer (rn_persist.cu: xchg_layout)
+    RN_CUDA(h, cudaStreamSynchronize(h->stream));
+    size_t off = 0;
+    {
+        const size_t Kg = (size_t)(h->dist_world > 1 ? h->dist_K_glob : h->d.K);
+        auto take = [&](size_t bytes) { size_t at = off; off = (off + bytes + 255) & ~size_t(255); return at; };
+        take(Kg * h->d.nx * 4); take(Kg * h->d.nv * 4); take(8 * 4 * 8); take(8 * 4); take(4);
+    }
+    RN_CUDA(h, cudaMemcpy(timed_out, static_cast<char *>(h->xchg) + off, sizeof(int), cudaMemcpyDeviceToHost));
+    return RN_OK;
+}
+
 rn_status rn_buffer(rn_handle *hh, rn_buffer_id id, void **dev_ptr, size_t *bytes) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (!h || !dev_ptr || !bytes) return RN_ERR_INVALID;
@@ -430,6 +512,7 @@ rn_status rn_buffer(rn_handle *hh, rn_buffer_id id, void **dev_ptr, size_t *byte
         case RN_BUF_VEC_RESIDUAL_PSI: p = h->res_psi; cnt = n * nu; break;
         case RN_BUF_CONTROL_ACTION: p = h->control_action; cnt = nu; break;
         case RN_BUF_STATE_UPDATE: p = h->state_update; cnt = nx; break;
+        case RN_BUF_VEC_ZETA: p = h->zeta; cnt = n * nu; break;
         default: return rn::fail(h, RN_ERR_INVALID, "rn_buffer: unknown id %d", (int)id);
     }
     *dev_ptr = p;

@@ -97,7 +97,16 @@ struct Handle {
 
     // persistent cooperative kernel
     float *part[4] = {nullptr, nullptr, nullptr, nullptr};   // D xi_w, F psi_w, Phi xi_w, Psi psi_w
-    float *qh = nullptr, *rh = nullptr, *sweep_pack = nullptr;
+    float *sweep_pack = nullptr;
+    // subtree partition across GPUs (rn_dist_prepare / rn_dist_connect)
+    int dist_world = 1, dist_rank = 0, dist_K_glob = 0, dist_chain_off = 0;
+    std::vector<int> dist_head_lo, dist_head_hi;   // per crown node: global chain-index range of the heads below it
+    void *xchg = nullptr;                          // this rank's exchange buffer (one cudaMalloc -> one IPC handle)
+    void *xchg_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool xchg_opened[8] = {false, false, false, false, false, false, false, false};
+    unsigned int xepoch = 0;
+    float *pinf4 = nullptr;
+    int pinf4_cap = 0;
     float *cm_c = nullptr, *cm_lv = nullptr, *cm_beta = nullptr, *cm_uhat = nullptr, *cm_e = nullptr;   // chain-major arrays
     int *crown_rng = nullptr, *pos_dev = nullptr;
     unsigned int *grid_bar = nullptr;
@@ -172,6 +181,7 @@ rn_status factor_step(Handle *h);
 rn_status materialise_dense_sys(Handle *h);
 rn_status update_state(Handle *h, const float *x, const float *u_prev, const float *d_prev);
 rn_status eliminate_coupling(Handle *h, const float *d_hat, const float *alpha_hat);
+rn_status fix_beta(Handle *h, int first, int count, const float *zeta_rows);
 rn_status apg_init(Handle *h);
 rn_status apg_step(Handle *h, rn_step_kind kind, float lambda);
 rn_status apg_enqueue(Handle *h, int iterations);
@@ -180,6 +190,7 @@ rn_status profile_stream(Handle *h, int reps, float *mean_ms);
 rn_status profile_kernels(Handle *h, int iterations, float *ms_out);
 bool persistent_supported(const Handle *h);
 rn_status persistent_prepare(Handle *h);
+rn_status ensure_xchg(Handle *h);
 rn_status persistent_launch(Handle *h, cudaStream_t st, int iters);
 rn_status clamp_control(Handle *h);
 rn_status move_forward(Handle *h);

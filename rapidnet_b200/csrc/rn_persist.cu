@@ -49,6 +49,7 @@ constexpr int kWStride = 2 * kVStride;          // w of one node: xi part | psi 
 constexpr int kTP = 24;                         // columns of a sweep tile (a chain's stages, or 24 crown nodes)
 constexpr int kMaxCs = 8;                       // deepest crown supported (stages above the chains)
 constexpr int kDimMax = 128;                    // max(2nx, nu, nv) supported by this kernel
+constexpr int kMaxRanks = 8;                    // GPUs of one node
 
 struct PArgs {
     const int *parent, *child_first, *child_count, *omega_idx, *cum, *stages;
@@ -66,8 +67,18 @@ struct PArgs {
     float *Yxi[2], *Ypsi[2], *Wxi[2], *Wpsi[2];
     float *pri_xi, *pri_psi, *dual_xi, *dual_psi;
     float *part[4];                             // D xi_w, F psi_w, Phi xi_w, Psi psi_w   chain-major [nodes][nvp] each
-    float *qh, *rh, *V, *U, *X;                 // qh, rh: q and r of the chain heads  [K*nx], [K*nv]
+    float *V, *U, *X;
     double *dist_part;                          // [2*grid]
+    // Subtree partition across GPUs (DESIGN.md "multi-GPU"): this rank owns chains [chain_off, chain_off + K) of K_glob;
+    // the crown is replicated.  Every rank's exchange buffer is mapped into every process (CUDA IPC); index = rank.
+    int n_ranks, rank, K_glob, chain_off;
+    unsigned int epoch0;                        // cross-GPU barrier epochs of this launch start after epoch0
+    float *qh_peer[kMaxRanks], *rh_peer[kMaxRanks];        // q / r of ALL chain heads [K_glob*nx], [K_glob*nv] on each rank
+    double *dslot_peer[kMaxRanks];              // [kMaxRanks][2] squared prox distances of each rank, on each rank
+    unsigned int *xflag_peer[kMaxRanks];        // [kMaxRanks] arrival epochs, on each rank
+    unsigned int *release;                      // local: epoch up to which the cross-GPU barriers are released
+    int *xerr;                                  // local: set when a cross-GPU wait timed out
+    float *pinf4;                               // [iters][4] |res|, res at the arg-max of the xi block and of the psi block
     float *pinf, *pinf_part;                    // [iters], [grid*6]
     const float *lambda_tab;
     unsigned int *bar;
@@ -124,6 +135,55 @@ __device__ __forceinline__ void grid_sync(unsigned int *ctr, unsigned int &targe
         __threadfence();
         atomicAdd(ctr, 1u);
         while (ld_acquire_u32(ctr) < target) {}
+        __threadfence();
+    }
+    cbar();
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin until *p >= want (system scope); gives up after about two seconds and raises *err instead of hanging the GPU
+__device__ __forceinline__ void wait_sys(const unsigned int *p, unsigned int want, int *err) {
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    while ((int)(ld_acquire_sys_u32(p) - want) < 0) {
+        if ((++spins & 1023u) == 0) {
+            const unsigned long long now = globaltimer();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) { *err = 1; break; }
+        }
+    }
+}
+
+// Grid barrier that is also a barrier across the GPUs of the partition: every CTA arrives on the local counter; CTA 0
+// waits for all of them, runs `mid()` (its thread 0: publish this rank's contribution to the peers), signals epoch
+// `ep` into every peer's flag array (NVLink stores), waits for every peer's signal, then releases the local CTAs.
+// Peer data written by any thread of this GPU before the barrier is ordered before the signal by the CTA barriers +
+// the system-scope fence (cumulativity), like cooperative_groups' grid sync does at device scope.
+template <typename Mid>
+__device__ __forceinline__ void grid_sync_cross(const PArgs &P, unsigned int &target, unsigned int ep, Mid mid) {
+    cbar();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence_system();
+        atomicAdd(P.bar, 1u);
+        if (blockIdx.x == 0) {
+            while (ld_acquire_u32(P.bar) < target) {}
+            mid();
+            __threadfence_system();
+            for (int r = 0; r < P.n_ranks; r++) st_release_sys_u32(P.xflag_peer[r] + P.rank, ep);
+            for (int r = 0; r < P.n_ranks; r++) wait_sys(P.xflag_peer[P.rank] + r, ep, P.xerr);
+            __threadfence_system();
+            st_release_sys_u32(P.release, ep);
+        } else {
+            wait_sys(P.release, ep, P.xerr);
+        }
         __threadfence();
     }
     cbar();
@@ -459,7 +519,6 @@ __device__ __noinline__ void chain_qscan(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
     const int e = threadIdx.x, T = P.N - P.cs, nx = P.nx, nxp = P.nxp;
     if (e >= nx) return;
-    float *__restrict__ qh = P.qh;
     const float *cs_ = S.stg;
     float cv[kTP];
 #pragma unroll
@@ -472,7 +531,8 @@ __device__ __noinline__ void chain_qscan(const PArgs &P, int j) {
         if (s < T) qrun = c + qrun;
     }
     row_store(S.X1 + e * kTP, cv);
-    qh[(size_t)j * nx + e] = qrun;
+    const size_t hrow = (size_t)(P.chain_off + j) * nx + e;   // every rank's copy of the table (own copy: plain store)
+    for (int r = 0; r < P.n_ranks; r++) P.qh_peer[r][hrow] = qrun;
 }
 
 // r-scan: sigma = beta + r_child (:599); r = ((sigma + D xi) + F psi) + G q_bar (:631-646).  Y = G q_bar on entry.
@@ -482,7 +542,6 @@ __device__ __noinline__ void chain_rscan(const PArgs &P, int j) {
     const int e = threadIdx.x, T = P.N - P.cs, nv = P.nv, nvp = P.nvp;
     if (e >= nv) return;
     const bool df = P.df_mode != 0;
-    float *__restrict__ rh = P.rh;
     const float *sb = S.stg + T * P.nxp, *s0 = sb + T * nvp, *s1 = s0 + T * nvp;
     float y[kTP];
     row_load(S.Y + e * kTP, y);
@@ -498,7 +557,8 @@ __device__ __noinline__ void chain_rscan(const PArgs &P, int j) {
         y[s] = out;
     }
     row_store(S.X1 + (P.nx + e) * kTP, y);
-    rh[(size_t)j * nv + e] = rrun;
+    const size_t hrow = (size_t)(P.chain_off + j) * nv + e;
+    for (int r = 0; r < P.n_ranks; r++) P.rh_peer[r][hrow] = rrun;
 }
 
 __device__ __noinline__ void chain_backward(const PArgs &P, int j, int next_chain, uint32_t mpar, StagePhase &ph) {
@@ -715,10 +775,9 @@ __device__ __noinline__ void chain_forward(const PArgs &P, int j, int next_chain
 __device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols) {
     const SweepSmem S = sweep_smem(P);
     const int t = threadIdx.x, g = t >> 7, e = t & 127, nx = P.nx, nv = P.nv, cs = P.cs, nxp = P.nxp, nvp = P.nvp;
-    const int head0 = __ldg(P.cum + cs);
     const int *__restrict__ stages = P.stages, *__restrict__ crown_rng = P.crown_rng;
     const float *__restrict__ cg = P.cm_c, *__restrict__ bg = P.cm_beta, *__restrict__ p0 = P.part[0], *__restrict__ p1 = P.part[1],
-                *__restrict__ qhg = P.qh, *__restrict__ rhg = P.rh;
+                *__restrict__ qhg = P.qh_peer[P.rank], *__restrict__ rhg = P.rh_peer[P.rank];
     const bool ex = e < nx, ev = e < nv;
     for (int col = 0; col < ncols; col++) {
         const int i = i0 + col, si = __ldg(stages + i);
@@ -746,7 +805,7 @@ __device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols) {
             qb += cpart; qs += (float)(s - si - 1) * cpart; bs += bpart;
         }
         {
-            const int lo = __ldg(rng + 2 * cs) - head0, hi = __ldg(rng + 2 * cs + 1) - head0;
+            const int lo = __ldg(rng + 2 * cs), hi = __ldg(rng + 2 * cs + 1);   // (global) chain indices of the heads below i
             float hq = 0.f, hr = 0.f;
             int h = lo + g;
             for (; h + 28 < hi; h += 32) {
@@ -1231,7 +1290,15 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
         const float lam = __ldg(P.lambda_tab + it);
         const int cur = it & 1;
         // ---- global distances of the previous iteration's prox (cublasSnrm2, :792, :810); zeros at it == 0
-        {
+        if (P.n_ranks > 1) {   // every rank published its share (crown counted by rank 0 only); same order everywhere
+            if (tid == 0) {
+                double t1 = 0, t2 = 0;
+                const double *ds = P.dslot_peer[P.rank] + 2 * ((it + 1) & 1);
+                if (it > 0) for (int r = 0; r < P.n_ranks; r++) { t1 += __ldcg(ds + 4 * r); t2 += __ldcg(ds + 4 * r + 1); }
+                sd[0] = (float)sqrt(t1); sd[1] = (float)sqrt(t2);
+            }
+            cbar();
+        } else {
             double p1 = 0, p2 = 0;
             for (int k = tid; k < (int)gridDim.x; k += kPC) { p1 += __ldcg(P.dist_part + 2 * k); p2 += __ldcg(P.dist_part + 2 * k + 1); }
             for (int o = 16; o > 0; o >>= 1) { p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o); }
@@ -1287,7 +1354,11 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
                 cand_merge(x, cx); cand_merge(p, cp);
             }
             x = cand_warp(x); p = cand_warp(p);
-            if (lane == 0) P.pinf[it - 1] = fmaxf(x.v, p.v);    // max(maxValueXi, maxValuePsi) (:1495)
+            if (lane == 0) {
+                P.pinf[it - 1] = fmaxf(x.v, p.v);    // max(maxValueXi, maxValuePsi) (:1495)
+                float *o4 = P.pinf4 + 4 * (size_t)(it - 1);
+                o4[0] = x.a; o4[1] = x.v; o4[2] = p.a; o4[3] = p.v;   // for the cross-rank merge on the host
+            }
         }
         const uint32_t mpar = (uint32_t)(it & 1);
         // crown tiles: as narrow as the grid allows (every CTA is free during phase C)
@@ -1302,7 +1373,10 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
         stamp(10);
         // ---- phase C: backward sweep of the crown (tiles are dealt from the last CTA down: those have the fewest chains)
         if (P.n_crown > 0) {
-            grid_sync(P.bar, bar_target);
+            // the crown needs the heads of every chain: with several GPUs their q, r were stored into every rank's
+            // table (chain_qscan / chain_rscan), and this barrier spans the GPUs
+            if (P.n_ranks > 1) grid_sync_cross(P, bar_target, P.epoch0 + 2u * (unsigned)it + 1u, [] {});
+            else grid_sync(P.bar, bar_target);
             stamp(20);
             for (int tl = grid - 1 - j0; tl < n_tiles; tl += grid)
                 crown_backward(PS, tl * tile_w, min(tile_w, P.n_crown - tl * tile_w), mpar, SP);
@@ -1317,8 +1391,12 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
         // ---- phase F: forward sweep + prox boxes
         const float *wxi = P.Wxi[cur], *wpsi = P.Wpsi[cur];
         if (tid == 0 && j0 < P.K) issue_chain_forward_loads(PS, j0);
-        for (int tl = grid - 1 - j0; tl < n_tiles; tl += grid)
-            crown_forward(PS, tl * tile_w, min(tile_w, P.n_crown - tl * tile_w), mpar, wxi, wpsi, s1, s2);
+        {
+            double c1 = 0, c2 = 0;
+            for (int tl = grid - 1 - j0; tl < n_tiles; tl += grid)
+                crown_forward(PS, tl * tile_w, min(tile_w, P.n_crown - tl * tile_w), mpar, wxi, wpsi, c1, c2);
+            if (P.rank == 0) { s1 += c1; s2 += c2; }   // the crown is replicated: it counts once in the global distances
+        }
         for (int j = j0; j < P.K; j += grid) chain_forward(PS, j, j + grid < P.K ? j + grid : -1, mpar, SP, wxi, wpsi, s1, s2);
         stamp(23);
         {   // this CTA's share of the two squared distances
@@ -1333,8 +1411,23 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
             s1 = 0; s2 = 0;
         }
         stamp(28);
-        grid_sync(P.bar, bar_target);
+        if (P.n_ranks > 1) {
+            grid_sync_cross(P, bar_target, P.epoch0 + 2u * (unsigned)it + 2u, [&] {
+                double t1 = 0, t2 = 0;   // this rank's share, CTA order
+                for (int k = 0; k < (int)gridDim.x; k++) { t1 += __ldcg(P.dist_part + 2 * k); t2 += __ldcg(P.dist_part + 2 * k + 1); }
+                for (int r = 0; r < P.n_ranks; r++) {
+                    double *ds = P.dslot_peer[r] + 2 * (it & 1) + 4 * P.rank;
+                    ds[0] = t1; ds[1] = t2;
+                }
+            });
+        } else grid_sync(P.bar, bar_target);
         stamp(29);
+    }
+    if (P.n_ranks > 1 && blockIdx.x == 0 && tid == 0) {   // k_finalize reads the global sums from slot 0
+        double t1 = 0, t2 = 0;
+        const double *ds = P.dslot_peer[P.rank] + 2 * ((P.iters + 1) & 1);
+        for (int r = 0; r < P.n_ranks; r++) { t1 += __ldcg(ds + 4 * r); t2 += __ldcg(ds + 4 * r + 1); }
+        P.dist_part[0] = t1; P.dist_part[1] = t2;
     }
     if (blockIdx.x == P.clock_cta && tid == 0) {
         const unsigned long long *c = clk_smem();
@@ -1410,6 +1503,30 @@ __global__ void k_to_chain_major(int nodes, int dim, int dimp, const int *__rest
     for (int t = threadIdx.x; t < dim; t += blockDim.x) dst[row + t] = src[(size_t)i * dim + t];
 }
 
+// Exchange buffer of this rank (one cudaMalloc, so that one CUDA IPC handle maps it into the peer processes):
+//   qh table [K_glob*nx] | rh table [K_glob*nv] | distance slots [kMaxRanks][2][2] doubles | flags [kMaxRanks] | release | err
+struct XchgLayout { size_t qh, rh, dslot, flags, release, err, bytes; };
+static XchgLayout xchg_layout(const Handle *h) {
+    XchgLayout X{};
+    const size_t Kg = (size_t)(h->dist_world > 1 ? h->dist_K_glob : h->d.K);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~size_t(255); return at; };
+    X.qh = take(Kg * h->d.nx * 4); X.rh = take(Kg * h->d.nv * 4); X.dslot = take(kMaxRanks * 4 * 8);
+    X.flags = take(kMaxRanks * 4); X.release = take(4); X.err = take(4); X.bytes = o;
+    return X;
+}
+rn_status ensure_xchg(Handle *h) {
+    if (h->xchg) return RN_OK;
+    const XchgLayout X = xchg_layout(h);
+    RN_CUDA(h, cudaMalloc(&h->xchg, X.bytes));
+    h->allocs.push_back(h->xchg);
+    h->device_bytes += X.bytes;
+    RN_CUDA(h, cudaMemset(h->xchg, 0, X.bytes));
+    for (int r = 0; r < kMaxRanks; r++) h->xchg_peer[r] = nullptr;
+    h->xchg_peer[h->dist_rank] = h->xchg;
+    return RN_OK;
+}
+
 rn_status persistent_prepare(Handle *h) {
     if (h->persist_ready) return RN_OK;
     const rn_dims &d = h->d;
@@ -1419,7 +1536,7 @@ rn_status persistent_prepare(Handle *h) {
     for (int k = 0; k < 4; k++) RN_CHECK(dev_alloc(h, &h->part[k], n * Y.nvp));
     RN_CHECK(dev_alloc(h, &h->cm_c, n * Y.nxp)); RN_CHECK(dev_alloc(h, &h->cm_lv, n * Y.nup));
     RN_CHECK(dev_alloc(h, &h->cm_beta, n * Y.nvp)); RN_CHECK(dev_alloc(h, &h->cm_uhat, n * Y.nup)); RN_CHECK(dev_alloc(h, &h->cm_e, n * Y.nxp));
-    RN_CHECK(dev_alloc(h, &h->qh, (size_t)d.K * d.nx)); RN_CHECK(dev_alloc(h, &h->rh, (size_t)d.K * d.nv));
+    RN_CHECK(ensure_xchg(h));
     RN_CHECK(dev_alloc(h, &h->grid_bar, 8));
     RN_CHECK(dev_alloc(h, &h->phase_ns, 32));
     // G | OmegaBar | L | B, each padded to 16 bytes: the four bulk copies of the sweeps
@@ -1438,13 +1555,19 @@ rn_status persistent_prepare(Handle *h) {
     RN_CHECK(dev_alloc(h, &h->pos_dev, n));
     RN_CUDA(h, cudaMemcpyAsync(h->pos_dev, pos.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     // descendant id range of every crown node at every later stage up to the chain heads (children are contiguous)
+    // At stage cs the range is in chain indices; with several GPUs the host supplies the GLOBAL chain ranges there.
     std::vector<int> rng((size_t)std::max(n_crown, 1) * (kMaxCs + 1) * 2, 0);
     for (int i = 0; i < n_crown; i++) {
         int lo = i, hi = i + 1;
         for (int s = h->h_stages[i] + 1; s <= cs; s++) {
             const int nlo = h->h_child_first[lo], nhi = h->h_child_first[hi - 1] + h->h_child_count[hi - 1];
             lo = nlo; hi = nhi;
-            rng[((size_t)i * (kMaxCs + 1) + s) * 2] = lo; rng[((size_t)i * (kMaxCs + 1) + s) * 2 + 1] = hi;
+            int a = lo, b = hi;
+            if (s == cs) {
+                if (h->dist_world > 1) { a = h->dist_head_lo[i]; b = h->dist_head_hi[i]; }
+                else { a = lo - h->h_cum[cs]; b = hi - h->h_cum[cs]; }
+            }
+            rng[((size_t)i * (kMaxCs + 1) + s) * 2] = a; rng[((size_t)i * (kMaxCs + 1) + s) * 2 + 1] = b;
         }
     }
     RN_CHECK(dev_alloc(h, &h->crown_rng, rng.size()));
@@ -1485,7 +1608,29 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     P.Wxi[0] = h->wA_xi; P.Wxi[1] = h->wB_xi; P.Wpsi[0] = h->wA_psi; P.Wpsi[1] = h->wB_psi;
     P.pri_xi = h->pri_xi; P.pri_psi = h->pri_psi; P.dual_xi = h->dual_xi; P.dual_psi = h->dual_psi;
     for (int k = 0; k < 4; k++) P.part[k] = h->part[k];
-    P.qh = h->qh; P.rh = h->rh; P.V = h->V; P.U = h->U; P.X = h->X;
+    P.V = h->V; P.U = h->U; P.X = h->X;
+    {
+        const XchgLayout X = xchg_layout(h);
+        P.n_ranks = std::max(h->dist_world, 1); P.rank = h->dist_world > 1 ? h->dist_rank : 0;
+        P.K_glob = h->dist_world > 1 ? h->dist_K_glob : d.K; P.chain_off = h->dist_world > 1 ? h->dist_chain_off : 0;
+        for (int r = 0; r < P.n_ranks; r++) {
+            char *base = static_cast<char *>(h->xchg_peer[r]);
+            if (!base) return fail(h, RN_ERR_STATE, "rank %d's exchange buffer is not connected (rn_dist_connect)", r);
+            P.qh_peer[r] = reinterpret_cast<float *>(base + X.qh); P.rh_peer[r] = reinterpret_cast<float *>(base + X.rh);
+            P.dslot_peer[r] = reinterpret_cast<double *>(base + X.dslot);
+            P.xflag_peer[r] = reinterpret_cast<unsigned int *>(base + X.flags);
+        }
+        char *own = static_cast<char *>(h->xchg);
+        P.release = reinterpret_cast<unsigned int *>(own + X.release);
+        P.xerr = reinterpret_cast<int *>(own + X.err);
+        P.epoch0 = h->xepoch;
+        h->xepoch += 2u * (unsigned)iters + 2u;   // every rank runs the same launches: the epochs stay aligned
+    }
+    if (h->pinf4_cap < iters) {
+        h->pinf4_cap = iters + 8;
+        RN_CHECK(dev_alloc(h, &h->pinf4, (size_t)h->pinf4_cap * 4));
+    }
+    P.pinf4 = h->pinf4;
     P.cm_c = h->cm_c; P.cm_lv = h->cm_lv; P.cm_beta = h->cm_beta; P.cm_uhat = h->cm_uhat; P.cm_e = h->cm_e;
     P.dist_part = h->dist_part; P.pinf = h->pinf; P.pinf_part = h->pinf_part;
     P.lambda_tab = h->lambda_tab; P.bar = h->grid_bar; P.iter_dev = h->iter_dev; P.phase_ns = h->phase_ns;

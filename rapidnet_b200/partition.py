@@ -1,0 +1,212 @@
+"""Subtree partition of ONE scenario tree across the GPUs of a node (BASELINE config[2]).
+
+The reference is single-GPU; this is the host side of the B200 extension the north-star asks for.  The tree is cut at the
+first stage of its non-branching tail ("chain stage" cs: below it every scenario is an independent chain):
+
+  * the crown (stages < cs) is REPLICATED on every rank -- a few dozen nodes;
+  * rank r owns a contiguous range of the K scenario chains (stages cs .. N-1), i.e. ~1/G of the nodes, of the Engine
+    factor matrices and of the duals.
+
+Each rank builds an ordinary, smaller problem (crown + its chains, nodes renumbered breadth-first) and creates its
+handle on it; per APG iteration the ranks exchange -- inside the persistent kernel, over NVLink peer memory mapped with
+CUDA IPC -- the q and r of their chain heads (so that every rank can finish the crown) and the two squared prox
+distances.  Nothing else crosses GPUs.  torch.distributed is used only to hand the 64-byte IPC handles around.
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass
+from typing import List, Tuple
+
+import numpy as np
+
+from .problem import Problem, Tree
+
+
+def chain_stage(tree: Tree) -> int:
+    """First stage of the non-branching tail: every node of a later stage is the only child of the node with the same
+    index one stage up (same rule as the library, rapidnet_b200/csrc/rn_api.cu).  tree.N if there is no tail."""
+    nps, cum = tree.nodes_per_stage, tree.nodes_per_stage_cumul
+    par = tree.ancestor.astype(np.int64) - 1
+    cs = tree.N - 1
+    while cs > 0:
+        if nps[cs] != nps[cs - 1]:
+            break
+        j = np.arange(nps[cs])
+        if not np.array_equal(par[cum[cs] + j], cum[cs - 1] + j):
+            break
+        cs -= 1
+    return int(cs)
+
+
+def split_chains(K: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced chain ranges [lo, hi) per rank."""
+    if world < 1 or K < world:
+        raise ValueError(f"cannot split {K} scenario chains over {world} ranks")
+    edges = [(K * r) // world for r in range(world + 1)]
+    return [(edges[r], edges[r + 1]) for r in range(world)]
+
+
+@dataclass
+class PartitionMeta:
+    world: int
+    rank: int
+    cs: int                      # chain stage
+    n_crown: int                 # nodes of the replicated crown (same ids on every rank)
+    K_global: int
+    chain_lo: int                # this rank owns global chains [chain_lo, chain_hi)
+    chain_hi: int
+    head_lo: np.ndarray          # [n_crown] global chain-index range of the chain heads below each crown node
+    head_hi: np.ndarray
+    local_to_global: np.ndarray  # [local nodes] global node id of each local node
+
+
+def head_ranges(tree: Tree, cs: int) -> Tuple[np.ndarray, np.ndarray]:
+    """For every crown node: the range of chain indices (0..K-1, position inside stage cs) of the heads below it.
+    Children are contiguous per parent (/root/reference/src/Utilities.cu:184-199), so it is one range."""
+    cum = tree.nodes_per_stage_cumul
+    n_crown = int(cum[cs])
+    par = tree.ancestor.astype(np.int64) - 1
+    lo = np.full(n_crown, np.iinfo(np.int32).max, dtype=np.int64)
+    hi = np.zeros(n_crown, dtype=np.int64)
+    for j in range(int(tree.nodes_per_stage[cs])):
+        a = par[cum[cs] + j]
+        while a >= 0:
+            lo[a] = min(lo[a], j)
+            hi[a] = max(hi[a], j + 1)
+            a = par[a]
+    lo[hi == 0] = 0
+    return lo.astype(np.int32), hi.astype(np.int32)
+
+
+def local_problem(problem: Problem, rank: int, world: int) -> Tuple[Problem, PartitionMeta]:
+    """The problem rank `rank` of `world` solves: crown + its chains, renumbered stage by stage."""
+    t = problem.tree
+    cs = chain_stage(t)
+    if cs >= t.N:
+        raise ValueError("the tree has no non-branching tail to partition")
+    cum, nps = t.nodes_per_stage_cumul.astype(np.int64), t.nodes_per_stage.astype(np.int64)
+    K = int(nps[cs])
+    if K != t.K:
+        raise ValueError("the chains of the tail are not the scenarios of the tree")
+    lo, hi = split_chains(K, world)[rank]
+    kl = hi - lo
+    n_crown = int(cum[cs])
+    # global ids of the local nodes, in local (breadth-first) order
+    l2g = [np.arange(n_crown, dtype=np.int64)]
+    for s in range(cs, t.N):
+        l2g.append(cum[s] + np.arange(lo, hi))
+    l2g = np.concatenate(l2g)
+    g2l = -np.ones(t.nodes, dtype=np.int64)
+    g2l[l2g] = np.arange(l2g.size)
+    nodes = int(l2g.size)
+    stages = t.stages[l2g].astype(np.int32)
+    lnps = np.concatenate([nps[:cs], np.full(t.N - cs, kl), [0]]).astype(np.int32)
+    lcum = np.concatenate([[0], np.cumsum(lnps)]).astype(np.int32)
+    par_g = t.ancestor.astype(np.int64) - 1
+    anc = np.where(par_g[l2g] >= 0, g2l[np.maximum(par_g[l2g], 0)] + 1, 0).astype(np.int32)   # 1-based, root = 0
+    n_nonleaf = nodes - kl
+    # children of node i (local): its global children that are local; contiguous and in order by construction
+    cnt = np.zeros(n_nonleaf, dtype=np.int32)
+    for i in range(1, nodes):
+        cnt[anc[i] - 1] += 1
+    ccum = np.zeros(nodes, dtype=np.int32)
+    ccum[:n_nonleaf] = np.cumsum(cnt)
+    ccum[n_nonleaf:] = ccum[n_nonleaf - 1] if n_nonleaf > 0 else 0
+    nd, nu = problem.network.nd, problem.network.nu
+    ed = np.asarray(t.err_demand, dtype=np.float32).reshape(t.nodes, nd)[l2g].reshape(-1)
+    ep = np.asarray(t.err_price, dtype=np.float32).reshape(t.nodes, nu)[l2g].reshape(-1)
+    lt = Tree(N=t.N, K=kl, nodes=nodes, n_nonleaf=int(n_nonleaf), n_children_tot=nodes - 1, stages=stages,
+              nodes_per_stage=lnps, nodes_per_stage_cumul=lcum,
+              leaves=(lcum[t.N - 1] + np.arange(kl) + 1).astype(np.int32),
+              children=np.arange(2, nodes + 1, dtype=np.int32), ancestor=anc, n_children=cnt, n_children_cumul=ccum,
+              prob=np.asarray(t.prob, dtype=np.float32)[l2g], dim_demand=t.dim_demand, dim_price=t.dim_price,
+              err_demand=ed, err_price=ep)
+    lp = Problem(network=problem.network, tree=lt, config=copy.copy(problem.config), forecast=problem.forecast)
+    hlo, hhi = head_ranges(t, cs)
+    meta = PartitionMeta(world=world, rank=rank, cs=cs, n_crown=n_crown, K_global=K, chain_lo=lo, chain_hi=hi,
+                         head_lo=hlo, head_hi=hhi, local_to_global=l2g)
+    return lp, meta
+
+
+def merge_pinf(parts: List[np.ndarray]) -> np.ndarray:
+    """vecPrimalInfs (SmpcController.cu:1487-1495) from every rank's per-iteration (|res|, res) at its arg-max of the xi
+    block and of the psi block: the global arg-max of each block, then the larger of the two signed values."""
+    p = np.stack(parts)                       # [ranks, iters, 4]
+    ix = np.argmax(p[:, :, 0], axis=0)
+    ip = np.argmax(p[:, :, 2], axis=0)
+    it = np.arange(p.shape[1])
+    return np.maximum(p[ix, it, 1], p[ip, it, 3])
+
+
+class DistributedSolver:
+    """One tree on `world` GPUs, one process per GPU.  `group` is a torch.distributed process group (nccl or gloo:
+    it only carries the IPC handles and the host-side gathers of results)."""
+
+    def __init__(self, problem: Problem, rank: int, world: int, device: int, group=None):
+        import torch.distributed as dist
+        from . import cabi
+        self.rank, self.world, self.group = rank, world, group
+        self.global_problem = problem
+        self.local, self.meta = local_problem(problem, rank, world)
+        self.solver = cabi.Solver(self.local, device=device, chain_stage_hint=self.meta.cs)
+        m = self.meta
+        handle = self.solver.dist_prepare(world, rank, m.K_global, m.chain_lo, m.head_lo, m.head_hi)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        self.solver.dist_connect(handles)
+        dist.barrier(group=group)
+
+    def setup(self, slot: int = 0):
+        c, fc = self.global_problem.config, self.global_problem.forecast
+        s = self.solver
+        s.factor_step()
+        s.update_state(c.current_x, c.prev_u, c.prev_demand)
+        self.eliminate_coupling(fc.demand[slot], fc.prices[slot])
+
+    def eliminate_coupling(self, d_hat, alpha_hat):
+        """Engine::eliminateInputDistubanceCoupling on the partition.  zeta_i = p_i dU_i - sum_children p_c dU_c
+        (calculateZeta, /root/reference/src/Utilities.cu:100-131) of a node just above the chain heads sums over children
+        on every rank: each rank's local value holds p_i dU_i minus its own children, so
+        zeta_i = sum_ranks zeta_i^r - (G - 1) p_i dU_i, summed in rank order on every rank; beta follows on the device."""
+        import torch.distributed as dist
+        s, m, t = self.solver, self.meta, self.local.tree
+        s.eliminate_coupling(d_hat, alpha_hat)
+        if self.world == 1 or m.cs == 0:
+            s.sync()
+            return
+        nu = self.local.network.nu
+        cum = t.nodes_per_stage_cumul
+        n0, n1 = int(cum[m.cs - 1]), int(cum[m.cs])
+        zeta = s.read("VEC_ZETA", count=n1 * nu).reshape(n1, nu)[n0:n1]
+        uhat = s.read("VEC_UHAT", count=n1 * nu).reshape(n1, nu)
+        par = t.ancestor[n0:n1].astype(np.int64) - 1
+        up = np.where(par[:, None] >= 0, uhat[np.maximum(par, 0)], s.read("VEC_PREV_UHAT")[None, :])
+        pdu = (t.prob[n0:n1, None].astype(np.float32) * (uhat[n0:n1] - up)).astype(np.float32)
+        parts = [None] * self.world
+        dist.all_gather_object(parts, zeta, group=self.group)
+        total = parts[0].astype(np.float32).copy()
+        for z in parts[1:]:
+            total += z
+        s.dist_fix_crown_beta(n0, total - np.float32(self.world - 1) * pdu)
+
+    def apg_solve(self, iterations: int, want_u0=True):
+        """Every rank must call this with the same iteration count (the in-kernel barriers span the GPUs)."""
+        u0, _ = self.solver.apg_solve(iterations, want_u0=want_u0)
+        if self.solver.dist_error():
+            raise RuntimeError("a cross-GPU wait timed out: a peer rank did not reach the exchange")
+        return u0
+
+    def gather(self, name: str, dim: int) -> np.ndarray:
+        """A per-node buffer ([nodes][dim]) assembled in GLOBAL node order on every rank."""
+        import torch.distributed as dist
+        loc = self.solver.read(name).reshape(-1, dim)
+        parts = [None] * self.world
+        dist.all_gather_object(parts, (self.meta.local_to_global, loc), group=self.group)
+        out = np.zeros((self.global_problem.tree.nodes, dim), dtype=np.float32)
+        for l2g, a in parts:
+            out[l2g] = a          # crown rows arrive from every rank with identical values
+        return out
+
+    def close(self):
+        self.solver.close()
