@@ -1,6 +1,6 @@
 """GPU (needs >= 2 devices): ONE scenario tree partitioned across GPUs (rapidnet_b200/partition.py, rn_dist_*) against the
 same tree on one GPU.  tools/dist_check.py runs under torchrun, one process per GPU; the ranks exchange the chain heads
-and the prox distances inside the persistent kernel over NVLink peer memory.  Tolerance: norm-wise 1e-6 up to 10
+and the prox distances inside the persistent kernel over NVLink peer memory.  Tolerance: norm-wise 1e-5 up to 10
 iterations, 1e-4 at 100 (the two runs differ only by fp32 rounding order in the zeta correction)."""
 import os
 import subprocess

@@ -61,7 +61,7 @@ def main():
             same = all(np.array_equal(got[k], ref.read(k).reshape(got[k].shape)) for k in got)
             print(f"{args.workload} x{world} it={iters}: worst rel diff vs 1 GPU {worst:.2e}, bit-identical {same}, "
                   f"u0 diff {float(np.abs(u0 - ru0).max()):.2e}, pinf diff {pe:.2e}", flush=True)
-            ok = ok and worst < (1e-6 if iters <= 10 else 1e-4)   # fp32 rounding grows with the iteration count (DESIGN.md tolerances)
+            ok = ok and worst < (1e-5 if iters <= 10 else 1e-4)   # fp32 rounding grows with the iteration count (DESIGN.md tolerances)
     if args.bench:
         dist.barrier()
         ds.apg_solve(100, want_u0=False); ds.solver.sync()
