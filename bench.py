@@ -316,6 +316,10 @@ def main():
     if rank == 0:
         info = s.info()
         prof = s.profile_kernels(min(iters, 100))
+        try:
+            phases = {k: round(v) for k, v in s.phase_times().items()} if args.sweep == "persistent" else None
+        except Exception:
+            phases = None
         peak, peak_src = measured_peaks()
         stream_bytes = info.stream_bytes_per_iteration
         achieved = stream_bytes / (prof["stream"] * 1e-3) / 1e9 if prof["stream"] > 0 else 0.0
@@ -351,6 +355,7 @@ def main():
                          "algorithmic_bytes_per_launch": stream_bytes, "launch_ms": prof["stream"],
                          "share_of_iteration": prof["stream"] / total_prof if total_prof > 0 else None,
                          "iteration_ms_by_kernel": prof,
+                         "phase_clock_ns_per_iteration": phases,
                          "whole_iteration": {"bytes": info.apg_bytes_per_iteration,
                                              "achieved": info.apg_bytes_per_iteration / (ms_dev / args.steps / iters * 1e-3) / 1e9,
                                              "frac": info.apg_bytes_per_iteration / (ms_dev / args.steps / iters * 1e-3) / 1e9 / peak}},

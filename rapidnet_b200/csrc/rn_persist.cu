@@ -86,7 +86,7 @@ struct PArgs {
     unsigned long long *phase_ns;               // [32] fine-grained phase clock of one CTA (see cabi.PHASE_NAMES)
     float step, inv_step, pen_x, pen_xs;
     // sweep shared-memory layout (float offsets from the dynamic shared-memory base) and the pack's pieces
-    int oG, oOm, oL, oX1, oY, oV, oScr2, oStg;
+    int oG, oOm, oL, oX1, oY, oV, oScr2, oStg, oXb;
     unsigned int bG, bOm, bL, bB;               // bytes of the four bulk copies
     int pG, pOm, pL, pB;                        // float offsets inside the pack
 };
@@ -118,6 +118,11 @@ __device__ __forceinline__ void dstamp(const PArgs &P, int idx) {
             c[32] = now;
         }
     }
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -231,6 +236,7 @@ struct SweepSmem {
     float *G, *Om, *L, *B;      // shared matrices (bulk TMA copies of the pack); B overlays G (backward / forward)
     float *X1, *Y, *V, *scr2;   // column arrays: X1 [q_bar rows | sigma rows] or [nu rows], Y [max(nv,nu) rows], V [nv rows]
     float *stg;                 // staging area of the chain blocks
+    float *xb;                  // [nx][kTP] crown forward: x_cur + sum_path e per column
     int *colnode;               // [kTP] chain-major row of each column
     int *colid;                 // [kTP] node id of each column
     float *colp;                // [kTP] probability that scales the column's Omega (Engine.cu:210-221)
@@ -241,7 +247,7 @@ struct SweepSmem {
 __device__ __forceinline__ SweepSmem sweep_smem(const PArgs &P) {
     SweepSmem S;
     S.G = smem_f(P.oG); S.Om = smem_f(P.oOm); S.L = smem_f(P.oL); S.B = smem_f(P.oG);
-    S.X1 = smem_f(P.oX1); S.Y = smem_f(P.oY); S.V = smem_f(P.oV); S.scr2 = smem_f(P.oScr2); S.stg = smem_f(P.oStg);
+    S.X1 = smem_f(P.oX1); S.Y = smem_f(P.oY); S.V = smem_f(P.oV); S.scr2 = smem_f(P.oScr2); S.stg = smem_f(P.oStg); S.xb = smem_f(P.oXb);
     S.colnode = reinterpret_cast<int *>(smem_f(kOffMisc));
     S.colid = reinterpret_cast<int *>(smem_f(kOffMisc + kTP));
     S.colp = smem_f(kOffMisc + 2 * kTP);
@@ -614,18 +620,25 @@ __device__ __noinline__ void chain_uscan(const PArgs &P, int j) {
     float usum = 0.f, uhp;
     float up = path_u(I, S.anc, cs, e, usum, uhp);
     const bool head_br = stage_branches(I.cum, cs);
-    float out[kTP];
+    // two halves of 12 columns: 12 live outputs instead of 24
 #pragma unroll
-    for (int s = 0; s < kTP; s++) {
-        float u = 0.f;
-        if (s < T) {
-            const float uh = su[s * nup + e], lv = sl[s * nup + e];
-            u = (s == 0 && head_br) ? (up + -1.f * uhp) + (uh + lv) : ((uh + up) + -1.f * uhp) + lv;
-            up = u; uhp = uh;
-        } else if (s == T) u = usum;
-        out[s] = u;
+    for (int h = 0; h < 2; h++) {
+        float out[kTP / 2];
+#pragma unroll
+        for (int s2 = 0; s2 < kTP / 2; s2++) {
+            const int s = h * (kTP / 2) + s2;
+            float u = 0.f;
+            if (s < T) {
+                const float uh = su[s * nup + e], lv = sl[s * nup + e];
+                u = (s == 0 && head_br) ? (up + -1.f * uhp) + (uh + lv) : ((uh + up) + -1.f * uhp) + lv;
+                up = u; uhp = uh;
+            } else if (s == T) u = usum;
+            out[s2] = u;
+        }
+        float4 *d = reinterpret_cast<float4 *>(S.X1 + e * kTP + h * (kTP / 2));
+        d[0] = make_float4(out[0], out[1], out[2], out[3]); d[1] = make_float4(out[4], out[5], out[6], out[7]);
+        d[2] = make_float4(out[8], out[9], out[10], out[11]);
     }
-    row_store(S.X1 + e * kTP, out);
 }
 
 // x-scan: x = (x_par + e) + B u (:730-737).  Y = B [u | usum] on entry, Y rows = x on exit
@@ -637,28 +650,31 @@ __device__ __noinline__ void chain_xscan(const PArgs &P, int j) {
     const int cs = P.cs;
     const bool head_br = stage_branches(P.cum, cs);
     const float *se = S.stg + 2 * T * P.nup;
-    float y[kTP];
-    row_load(S.Y + e * kTP, y);
     float pe[kMaxCs];
 #pragma unroll
     for (int k = 0; k < kMaxCs; k++) if (k < cs) pe[k] = __ldg(eg + (size_t)S.anc[k] * nxp + e);
     float xrun = __ldg(P.xcur + e);
 #pragma unroll
     for (int k = 0; k < kMaxCs; k++) if (k < cs) xrun += pe[k];
-    if (cs > 0) {
-        float bus = 0.f;   // (B usum)[e] sits in column T
+    if (cs > 0) xrun += S.Y[e * kTP + T];   // (B usum)[e] sits in column T
+    // two halves of 12 columns: 12 live values instead of 24
 #pragma unroll
-        for (int s = 0; s < kTP; s++) if (s == T) bus = y[s];
-        xrun += bus;
-    }
+    for (int h = 0; h < 2; h++) {
+        float4 *yp = reinterpret_cast<float4 *>(S.Y + e * kTP + h * (kTP / 2));
+        const float4 q0 = yp[0], q1 = yp[1], q2 = yp[2];
+        float y[kTP / 2] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
-    for (int s = 0; s < kTP; s++)
-        if (s < T) {
-            const float ev = se[s * nxp + e];
-            const float x = (s == 0 && head_br) ? xrun + (ev + y[s]) : (xrun + ev) + y[s];
-            y[s] = x; xrun = x;
+        for (int s2 = 0; s2 < kTP / 2; s2++) {
+            const int s = h * (kTP / 2) + s2;
+            if (s < T) {
+                const float ev = se[s * nxp + e];
+                const float x = (s == 0 && head_br) ? xrun + (ev + y[s2]) : (xrun + ev) + y[s2];
+                y[s2] = x; xrun = x;
+            }
         }
-    row_store(S.Y + e * kTP, y);
+        yp[0] = make_float4(y[0], y[1], y[2], y[3]); yp[1] = make_float4(y[4], y[5], y[6], y[7]);
+        yp[2] = make_float4(y[8], y[9], y[10], y[11]);
+    }
 }
 
 // Hx = sysF x, Hu = sysG u (:744-747), t = Hx + w/step, box projections (Utilities.cu:237-254) and the partial sums of
@@ -898,6 +914,7 @@ __device__ __noinline__ void crown_forward(const PArgs &P, int i0, int ncols, ui
     const int *__restrict__ stages = P.stages, *__restrict__ parent = P.parent;
     const float *__restrict__ eg = P.cm_e, *__restrict__ xcur = P.xcur;
     float *Ug = P.U, *Xg = P.X;
+    float *xbase = S.xb;   // x_cur + sum_path e per column (kept in shared memory: 24 registers live across the GEMM call otherwise)
     if (t < kTP) { S.colnode[t] = t < ncols ? i0 + t : 0; S.colid[t] = S.colnode[t]; }
     cbar();
     for (int col = g; col < kTP; col += 4) {
@@ -920,20 +937,17 @@ __device__ __noinline__ void crown_forward(const PArgs &P, int i0, int ncols, ui
             }
         }
         if (e < nu) { S.X1[e * kTP + col] = usum; S.V[e * kTP + col] = u; }
-        if (e < nx) S.scr2[e * kTP + col] = xb;
+        if (e < nx) xbase[e * kTP + col] = xb;
     }
     cbar();
     cols_to_global(S.V, S.colid, ncols, nu, nu, Ug);                              // devVecU
     dstamp(P, 13);
-    // x base sits in scr2, which the GEMM uses as scratch: move it to registers first
-    float xb[kTP];
-    if (t < nx) row_load(S.scr2 + t * kTP, xb);
-    cbar();
     mbar_wait(&S.mfull[3], mpar);
     tile_gemm<kEpiStore>(S.B, nx, nu, S.X1, S.Y, S.scr2, nullptr);                                   // B sum_path u
     if (t < nx) {
-        float y[kTP];
+        float y[kTP], xb[kTP];
         row_load(S.Y + t * kTP, y);
+        row_load(xbase + t * kTP, xb);
 #pragma unroll
         for (int s = 0; s < kTP; s++) y[s] = s < ncols ? xb[s] + y[s] : 0.f;
         row_store(S.Y + t * kTP, y);
@@ -1058,88 +1072,154 @@ __device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderS
     (void)cyc_empty; (void)cyc_vec; (void)cyc_go;
 }
 
-// ---- GEMV warps: part[m][node] = (factor matrix m of the node) x (w segment), warp = column, lane = rows lane + 32 k.
-// Rows >= nv of the last 32-row group read the neighbouring column (or the stage's slack): those lanes' sums are
-// never used, so the inner loop carries no row predicate.
-template <int NR>
-__device__ __forceinline__ void gemv_role(const PArgs &P, const Slice &R, GemvState &G) {
+// ---- GEMV warps: part[m][node] = (factor matrix m of the node) x (w segment).  A warp owns a contiguous block of the
+// chunk's columns; lane = rows lane + 32 k of NR row groups, four columns per trip with every load of the trip issued
+// before the first FMA (the function is not inlined so that it has its own register budget: inlined into the kernel
+// body ptxas serialised load -> FMA pairs through one register and the warps sat on shared-memory latency).
+// The nv mod 32 rows that do not fill a row group run in "dot mode" when there are at most 8 of them (RD > 0): lane =
+// column, one load + FMA per row and 32 columns, a shuffle reduction per unit -- nv = 97 costs 3 row groups + 1 dot
+// row instead of 4 row groups.  Otherwise (RD == 0) the last group over-reads the neighbouring column (or the
+// stage's slack): those lanes' sums are never used, so the inner loop carries no row predicate.
+template <int NR, int RD>
+__device__ __noinline__ void gemv_role(const PArgs &P, const Slice &R, GemvState &G) {
     const Pipe M = pipe_smem();
+    constexpr int NA = NR > 0 ? NR : 1, NT = RD > 0 ? RD : 1;
     const int nx = P.nx, nu = P.nu, nv = P.nv, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_stages = P.n_stages, stage_stride = P.stage_stride;
+    const int n_stages = P.n_stages, stage_stride = P.stage_stride, n_mats = P.n_mats, cpc = P.cols_per_chunk;
+    const int u_begin = R.u_begin, u_end = R.u_end, rem = nv & 31, tail0 = nv - rem;
+    // only the 16-byte phase of a chunk's global address matters here (the loader copies 16-byte windows): keep the
+    // low four bits of the four array bases in one register
+    const unsigned mlow = (unsigned)(reinterpret_cast<uintptr_t>(P.mat[0]) & 15) | (unsigned)(reinterpret_cast<uintptr_t>(P.mat[1]) & 15) << 4 |
+                          (unsigned)(reinterpret_cast<uintptr_t>(P.mat[2]) & 15) << 8 | (unsigned)(reinterpret_cast<uintptr_t>(P.mat[3]) & 15) << 12;
     int st = G.st, wb = G.wb, rb = G.rb; uint32_t ph = G.ph, wph = G.wph, rph = G.rph;
-    int node_prev = -1;
     const bool dbg = blockIdx.x == P.clock_cta && threadIdx.x == 0;
-    long long cyc_full = 0, cyc_w = 0, cyc_red = 0, cyc_cmp = 0;
-    for (int u = R.u_begin; u < R.u_end; u++) {
-        const int node = u / P.n_mats, m = u - node * P.n_mats;
-        if (node != node_prev) {
-            if (node_prev >= 0) {   // done with the previous node's w
+    unsigned cyc_full = 0, cyc_w = 0, cyc_red = 0, cyc_cmp = 0;   // low 32 bits of clock differences
+    int node = u_begin / n_mats, m = u_begin - node * n_mats;
+    bool have_w = false;
+    for (int u = u_begin; u < u_end; u++) {
+        if (!have_w || m == 0) {
+            if (have_w) {   // done with the previous node's w
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&M.wempty[wb]);
                 if (++wb == 2) { wb = 0; wph ^= 1; }
             }
-            { const long long c_ = clock64(); mbar_wait(&M.wfull[wb], wph); cyc_w += clock64() - c_; }
-            node_prev = node;
+            { const unsigned c_ = (unsigned)clock64(); mbar_wait(&M.wfull[wb], wph); cyc_w += (unsigned)clock64() - c_; }
+            have_w = true;
         }
         const bool xi_type = (m & 1) == 0;
         const int ncols = xi_type ? 2 * nx : nu;
         const float *wseg = M.wbuf + wb * kWStride + (xi_type ? 0 : kVStride);
-        const float *base = P.mat[m] + (size_t)node * nv * ncols;
-        float acc[NR];
+        const unsigned base = ((mlow >> (4 * m)) & 15u) + 4u * (unsigned)node * (unsigned)(nv * ncols);   // mod 16 is all that counts
+        float acc[NA], tl[NT];
 #pragma unroll
-        for (int k = 0; k < NR; k++) acc[k] = 0.f;
-        for (int c0 = 0; c0 < ncols; c0 += P.cols_per_chunk) {
-            const int cc = min(P.cols_per_chunk, ncols - c0);
-            const int off = (int)((reinterpret_cast<uintptr_t>(base + (size_t)c0 * nv) & 15) >> 2);
-            const long long c1_ = clock64();
+        for (int k = 0; k < NA; k++) acc[k] = 0.f;
+#pragma unroll
+        for (int r = 0; r < NT; r++) tl[r] = 0.f;
+        for (int c0 = 0; c0 < ncols; c0 += cpc) {
+            const int cc = min(cpc, ncols - c0);
+            const int off = (int)(((base + 4u * (unsigned)(c0 * nv)) & 15u) >> 2);
+            const unsigned c1_ = (unsigned)clock64();
             mbar_wait(&M.full[st], ph);
-            const long long c2_ = clock64();
+            const unsigned c2_ = (unsigned)clock64();
             cyc_full += c2_ - c1_;
-            const float *sb = M.ring + st * stage_stride + off + lane;
+            const float *sb = M.ring + st * stage_stride + off;
             const float *wc = wseg + c0;
-            int j = warp;
-            for (; j + 3 * kGemvWarps < cc; j += 4 * kGemvWarps) {   // four columns per trip: all loads first
-                const float w0 = wc[j], w1 = wc[j + kGemvWarps], w2 = wc[j + 2 * kGemvWarps], w3 = wc[j + 3 * kGemvWarps];
-                const float *col0 = sb + j * nv, *col1 = col0 + kGemvWarps * nv, *col2 = col1 + kGemvWarps * nv, *col3 = col2 + kGemvWarps * nv;
-                float a[NR], b[NR], c[NR], d[NR];
+            const int ca = cc * warp / kGemvWarps, cb = cc * (warp + 1) / kGemvWarps;   // this warp's columns of the chunk
+            if (NR > 0) {
+                // volatile shared loads: the compiler keeps their order, so the 4 (NR + 1) loads of a trip are in flight
+                // together (written as plain C++ the trip was re-rolled into a load -> FMA chain per column)
+                const uint32_t sbase = smem_u32(sb) + 4u * (uint32_t)lane, wbase = smem_u32(wc);
+#pragma unroll 1
+                for (int j = ca; j < cb; j += 4) {
+                    float wv[4], a[4][NA];
 #pragma unroll
-                for (int k = 0; k < NR; k++) { a[k] = col0[32 * k]; b[k] = col1[32 * k]; c[k] = col2[32 * k]; d[k] = col3[32 * k]; }
+                    for (int i = 0; i < 4; i++) {
+                        const int jj = min(j + i, cb - 1);
+                        wv[i] = lds_f32(wbase + 4u * (uint32_t)jj);
+                        const uint32_t ad = sbase + 4u * (uint32_t)(jj * nv);
 #pragma unroll
-                for (int k = 0; k < NR; k++) {
-                    acc[k] = fmaf(a[k], w0, acc[k]); acc[k] = fmaf(b[k], w1, acc[k]);
-                    acc[k] = fmaf(c[k], w2, acc[k]); acc[k] = fmaf(d[k], w3, acc[k]);
+                        for (int k = 0; k < NA; k++) a[i][k] = lds_f32(ad + 128u * k);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) if (j + i >= cb) wv[i] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int k = 0; k < NA; k++) acc[k] = fmaf(a[i][k], wv[i], acc[k]);
                 }
             }
-            for (; j < cc; j += kGemvWarps) {
-                const float w0 = wc[j];
-                const float *col0 = sb + j * nv;
-                float a[NR];
+            if (RD > 0) {   // dot mode: lane = column (a warp's block has at most kDimMax * 2 / kGemvWarps <= 32 columns)
+                const int jj = ca + lane;
+                if (jj < cb) {
+                    const float wl = wc[jj];
+                    const float *tp = sb + jj * nv + tail0;
+                    float tv[NT];
 #pragma unroll
-                for (int k = 0; k < NR; k++) a[k] = col0[32 * k];
+                    for (int r = 0; r < NT; r++) tv[r] = (RD == 1 || r < rem) ? tp[r] : 0.f;
 #pragma unroll
-                for (int k = 0; k < NR; k++) acc[k] = fmaf(a[k], w0, acc[k]);
+                    for (int r = 0; r < NT; r++) tl[r] = fmaf(tv[r], wl, tl[r]);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&M.empty[st]);
             if (++st == n_stages) { st = 0; ph ^= 1; }
-            cyc_cmp += clock64() - c2_;
+            cyc_cmp += (unsigned)clock64() - c2_;
+        }
+        if (RD > 0) {
+#pragma unroll
+            for (int r = 0; r < NT; r++)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tl[r] += __shfl_xor_sync(0xffffffffu, tl[r], o);
         }
         // hand the per-warp partial sums to the element-wise warps
-        { const long long c_ = clock64(); mbar_wait(&M.rempty[rb], rph ^ 1); cyc_red += clock64() - c_; }
-        float *rd = M.red + (rb * kGemvWarps + warp) * kDimMax + lane;
+        { const unsigned c_ = (unsigned)clock64(); mbar_wait(&M.rempty[rb], rph ^ 1); cyc_red += (unsigned)clock64() - c_; }
+        float *rd = M.red + (rb * kGemvWarps + warp) * kDimMax;
+        if (NR > 0) {
 #pragma unroll
-        for (int k = 0; k < NR; k++) rd[32 * k] = acc[k];
+            for (int k = 0; k < NA; k++) rd[lane + 32 * k] = acc[k];
+        }
+        if (RD > 0) {
+#pragma unroll
+            for (int r = 0; r < NT; r++) if (lane == r && r < rem) rd[tail0 + r] = tl[r];
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&M.rfull[rb]);
         if (++rb == 2) { rb = 0; rph ^= 1; }
+        if (++m == n_mats) { m = 0; node++; }
     }
-    if (node_prev >= 0) {
+    if (have_w) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&M.wempty[wb]);
         if (++wb == 2) { wb = 0; wph ^= 1; }
     }
     G.st = st; G.ph = ph; G.wb = wb; G.wph = wph; G.rb = rb; G.rph = rph;
     if (dbg) { unsigned long long *c = clk_smem(); c[24] += cyc_full; c[25] += cyc_w; c[26] += cyc_red; c[27] += cyc_cmp; }
+}
+// row groups / dot rows for a given nv: nv mod 32 in 1..8 -> dot mode
+__device__ __forceinline__ void gemv_dispatch(const PArgs &P, const Slice &R, GemvState &G) {
+    const int nf = P.nv >> 5, rem = P.nv & 31;
+    if (rem == 0 || rem > 8) {
+        switch (nf + (rem ? 1 : 0)) {
+            case 1: gemv_role<1, 0>(P, R, G); break;
+            case 2: gemv_role<2, 0>(P, R, G); break;
+            case 3: gemv_role<3, 0>(P, R, G); break;
+            default: gemv_role<4, 0>(P, R, G); break;
+        }
+    } else if (rem == 1) {
+        switch (nf) {
+            case 0: gemv_role<0, 1>(P, R, G); break;
+            case 1: gemv_role<1, 1>(P, R, G); break;
+            case 2: gemv_role<2, 1>(P, R, G); break;
+            default: gemv_role<3, 1>(P, R, G); break;
+        }
+    } else {
+        switch (nf) {
+            case 0: gemv_role<0, 8>(P, R, G); break;
+            case 1: gemv_role<1, 8>(P, R, G); break;
+            case 2: gemv_role<2, 8>(P, R, G); break;
+            default: gemv_role<3, 8>(P, R, G); break;
+        }
+    }
 }
 
 // ---- element-wise warps: fused finalisation (previous iteration) + extrapolation (this one), one node ahead of the
@@ -1232,10 +1312,189 @@ __device__ __noinline__ void ew_role(const PArgs &P, const Slice &R, EwState &E,
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
+// Per-thread state that lives across iterations.  It sits in local memory and the two halves of an iteration are
+// non-inlined functions that get it by reference: the kernel body keeps almost nothing live across the calls, so every
+// role / sweep function below has (nearly) the whole 128-register budget of a 512-thread CTA.  (With the iteration
+// inlined into the kernel, ptxas ran out of registers and scheduled every inner loop as load -> use pairs.)
+struct KState {
+    Slice R;
+    unsigned int bar_target;
+    StagePhase SP;
+    GemvState GS;
+    EwState ES;
+    LoaderState LS;
+    double s1, s2;
+};
+
+// first half of iteration `it`: global distances of the previous prox, phase S, infeasibility log of iteration it-1
+__device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
+    double *dsh = reinterpret_cast<double *>(smem_f(kOffDsh));      // 2 * 16 doubles
+    Cand *csh = reinterpret_cast<Cand *>(smem_f(kOffCsh));          // 2 * 16 candidates
+    float *sd = smem_f(kOffSd);                                     // d1, d2
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- global distances of the previous iteration's prox (cublasSnrm2, :792, :810); zeros at it == 0
+    if (P.n_ranks > 1) {   // every rank published its share (crown counted by rank 0 only); same order everywhere
+        if (tid == 0) {
+            double t1 = 0, t2 = 0;
+            const double *ds = P.dslot_peer[P.rank] + 2 * ((it + 1) & 1);
+            if (it > 0) for (int r = 0; r < P.n_ranks; r++) { t1 += __ldcg(ds + 4 * r); t2 += __ldcg(ds + 4 * r + 1); }
+            sd[0] = (float)sqrt(t1); sd[1] = (float)sqrt(t2);
+        }
+        cbar();
+    } else {
+        double p1 = 0, p2 = 0;
+        for (int k = tid; k < (int)gridDim.x; k += kPC) { p1 += __ldcg(P.dist_part + 2 * k); p2 += __ldcg(P.dist_part + 2 * k + 1); }
+        for (int o = 16; o > 0; o >>= 1) { p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o); }
+        if (lane == 0) { dsh[warp] = p1; dsh[kPC / 32 + warp] = p2; }
+        cbar();
+        if (tid == 0) {
+            double t1 = 0, t2 = 0;
+            for (int w = 0; w < kPC / 32; w++) { t1 += dsh[w]; t2 += dsh[kPC / 32 + w]; }
+            sd[0] = (float)sqrt(t1); sd[1] = (float)sqrt(t2);
+        }
+        cbar();
+    }
+    Cand bx{-1.f, 0.f, 0x7fffffff}, bp{-1.f, 0.f, 0x7fffffff};
+
+    // ---- phase S: three-role pipeline.  loader -> [ring] -> GEMV warps -> [red] -> element-wise warps -> [wbuf] -> GEMV
+    if (warp < kGemvWarps) {
+        gemv_dispatch(P, K.R, K.GS);
+    } else if (warp == kLoaderWarp) {
+        loader_role(P, K.R, K.LS, it);
+    } else {
+        const float lam = __ldg(P.lambda_tab + it);
+        const float d1 = sd[0], d2 = sd[1];
+        const float thr1 = P.inv_step * P.pen_x, thr2 = P.inv_step * P.pen_xs;
+        EwIter I;
+        I.a1 = 1.f + lam; I.a2 = -lam; I.cur = it & 1;
+        I.br1 = d1 > thr1; I.br2 = d2 > thr2;
+        I.sc1 = I.br1 ? 1.f - thr1 / d1 : 0.f; I.sc2 = I.br2 ? 1.f - thr2 / d2 : 0.f;
+        ew_role(P, K.R, K.ES, I, bx, bp);
+    }
+    // infeasibility candidates of iteration it-1 (updatePrimalInfeasibity, :1480-1496)
+    if (it > 0) {
+        bx = cand_warp(bx); bp = cand_warp(bp);
+        if (lane == 0) { csh[warp] = bx; csh[kPC / 32 + warp] = bp; }
+        cbar();
+        if (tid == 0) {
+            Cand x = csh[0], p = csh[kPC / 32];
+            for (int w = 1; w < kPC / 32; w++) { cand_merge(x, csh[w]); cand_merge(p, csh[kPC / 32 + w]); }
+            float *o = P.pinf_part + 6 * (size_t)blockIdx.x;
+            o[0] = x.a; o[1] = x.v; o[2] = __int_as_float(x.idx); o[3] = p.a; o[4] = p.v; o[5] = __int_as_float(p.idx);
+        }
+    }
+    // the stream ring is idle now: pull the shared sweep matrices over it while the grid barrier is pending
+    cbar();
+    if (tid == 0) issue_matrix_loads(P);
+    dstamp(P, 0);
+    grid_sync(P.bar, K.bar_target);
+    dstamp(P, 1);
+    if (it > 0 && blockIdx.x == 0 && warp == 0) {
+        Cand x{-1.f, 0.f, 0x7fffffff}, p{-1.f, 0.f, 0x7fffffff};
+        for (int b = lane; b < (int)gridDim.x; b += 32) {
+            const float *o = P.pinf_part + 6 * (size_t)b;
+            Cand cx{__ldcg(o), __ldcg(o + 1), __float_as_int(__ldcg(o + 2))}, cp{__ldcg(o + 3), __ldcg(o + 4), __float_as_int(__ldcg(o + 5))};
+            cand_merge(x, cx); cand_merge(p, cp);
+        }
+        x = cand_warp(x); p = cand_warp(p);
+        if (lane == 0) {
+            P.pinf[it - 1] = fmaxf(x.v, p.v);    // max(maxValueXi, maxValuePsi) (:1495)
+            float *o4 = P.pinf4 + 4 * (size_t)(it - 1);
+            o4[0] = x.a; o4[1] = x.v; o4[2] = p.a; o4[3] = p.v;   // for the cross-rank merge on the host
+        }
+    }
+}
+
+// second half of iteration `it`: the sweeps (phases B, C, F), this CTA's share of the prox distances, closing barrier.
+// Three functions, each with little state of its own, so that the sweep steps below them keep their register budget.
+struct CrownTiles { int tile_w, n_tiles; };
+__device__ __forceinline__ CrownTiles crown_tiles(const PArgs &P) {   // as narrow as the grid allows (every CTA is free during phase C)
+    CrownTiles C;
+    C.tile_w = min(kTP / 2, max(1, (P.n_crown + (int)gridDim.x - 1) / (int)gridDim.x));
+    C.n_tiles = (P.n_crown + C.tile_w - 1) / C.tile_w;
+    return C;
+}
+
+__device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
+    const uint32_t mpar = (uint32_t)(it & 1);
+    const int grid = (int)gridDim.x, j0 = (int)blockIdx.x, nK = P.K;
+    // ---- phase B: backward sweep of the chains (operand blocks by bulk TMA, one chain ahead)
+    dstamp(P, 2);
+    if (threadIdx.x == 0 && j0 < nK) issue_chain_backward_loads(P, j0);
+    for (int j = j0; j < nK; j += grid) chain_backward(P, j, j + grid < nK ? j + grid : -1, mpar, K.SP);
+    dstamp(P, 10);
+    // ---- phase C: backward sweep of the crown (tiles are dealt from the last CTA down: those have the fewest chains)
+    if (P.n_crown > 0) {
+        // the crown needs the heads of every chain: with several GPUs their q, r were stored into every rank's
+        // table (chain_qscan / chain_rscan), and this barrier spans the GPUs
+        if (P.n_ranks > 1) grid_sync_cross(P, K.bar_target, P.epoch0 + 2u * (unsigned)it + 1u, [] {});
+        else grid_sync(P.bar, K.bar_target);
+        dstamp(P, 20);
+        const CrownTiles C = crown_tiles(P);
+        const int n_crown = P.n_crown;
+        for (int tl = grid - 1 - j0; tl < C.n_tiles; tl += grid)
+            crown_backward(P, tl * C.tile_w, min(C.tile_w, n_crown - tl * C.tile_w), mpar, K.SP);
+        dstamp(P, 21);
+    }
+    // G has done its work for this iteration: B takes its place (every step above ended with a CTA barrier)
+    if (threadIdx.x == 0) issue_b_load(P);
+    if (P.n_crown > 0) {
+        grid_sync(P.bar, K.bar_target);
+        dstamp(P, 22);
+    }
+}
+
+// ---- phase F: forward sweep + prox boxes; leaves this CTA's sums of squared distances in K.s1, K.s2
+__device__ __noinline__ void iter_forward(const PArgs &P, KState &K, int it) {
+    const uint32_t mpar = (uint32_t)(it & 1);
+    const int grid = (int)gridDim.x, j0 = (int)blockIdx.x, nK = P.K;
+    const float *wxi = P.Wxi[it & 1], *wpsi = P.Wpsi[it & 1];
+    if (threadIdx.x == 0 && j0 < nK) issue_chain_forward_loads(P, j0);
+    K.s1 = 0; K.s2 = 0;
+    if (P.n_crown > 0) {
+        double c1 = 0, c2 = 0;
+        const CrownTiles C = crown_tiles(P);
+        const int n_crown = P.n_crown;
+        for (int tl = grid - 1 - j0; tl < C.n_tiles; tl += grid)
+            crown_forward(P, tl * C.tile_w, min(C.tile_w, n_crown - tl * C.tile_w), mpar, wxi, wpsi, c1, c2);
+        if (P.rank == 0) { K.s1 = c1; K.s2 = c2; }   // the crown is replicated: it counts once in the global distances
+    }
+    for (int j = j0; j < nK; j += grid) chain_forward(P, j, j + grid < nK ? j + grid : -1, mpar, K.SP, wxi, wpsi, K.s1, K.s2);
+    dstamp(P, 23);
+}
+
+__device__ __noinline__ void iter_close(const PArgs &P, KState &K, int it) {
+    double *dsh = reinterpret_cast<double *>(smem_f(kOffDsh));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {   // this CTA's share of the two squared distances
+        double s1 = K.s1, s2 = K.s2;
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        if (lane == 0) { dsh[warp] = s1; dsh[kPC / 32 + warp] = s2; }
+        cbar();
+        if (tid == 0) {
+            double t1 = 0, t2 = 0;
+            for (int w = 0; w < kPC / 32; w++) { t1 += dsh[w]; t2 += dsh[kPC / 32 + w]; }
+            P.dist_part[2 * blockIdx.x] = t1; P.dist_part[2 * blockIdx.x + 1] = t2;
+        }
+    }
+    dstamp(P, 28);
+    if (P.n_ranks > 1) {
+        grid_sync_cross(P, K.bar_target, P.epoch0 + 2u * (unsigned)it + 2u, [&] {
+            double t1 = 0, t2 = 0;   // this rank's share, CTA order
+            for (int k = 0; k < (int)gridDim.x; k++) { t1 += __ldcg(P.dist_part + 2 * k); t2 += __ldcg(P.dist_part + 2 * k + 1); }
+            for (int r = 0; r < P.n_ranks; r++) {
+                double *ds = P.dslot_peer[r] + 2 * (it & 1) + 4 * P.rank;
+                ds[0] = t1; ds[1] = t2;
+            }
+        });
+    } else grid_sync(P.bar, K.bar_target);
+    dstamp(P, 29);
+}
+
 __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant__ PArgs P) {
-    // The non-inlined role / sweep functions get the arguments through a reference; reads of the kernel-parameter
-    // space behind a generic pointer cost about a microsecond each (ncu: 12 % of all stall samples sat on them), so
-    // those functions are handed a shared-memory copy instead.
+    // The non-inlined functions get the arguments through a reference; reads of the kernel-parameter space behind a
+    // generic pointer cost about a microsecond each (ncu: 12 % of all stall samples sat on them), so they are handed a
+    // shared-memory copy instead.
     static_assert(sizeof(PArgs) <= kPArgsWords * 4 && sizeof(PArgs) % 4 == 0, "PArgs copy");
     {
         const int *src = reinterpret_cast<const int *>(&P);
@@ -1243,14 +1502,9 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
         for (int k = threadIdx.x; k < (int)(sizeof(PArgs) / 4); k += kPC) dst[k] = src[k];
     }
     const PArgs &PS = *reinterpret_cast<const PArgs *>(smem_f(kOffPArgs));
-    const int nv = P.nv;
-    const Pipe M = pipe_smem();
-    double *dsh = reinterpret_cast<double *>(smem_f(kOffDsh));      // 2 * 16 doubles
-    Cand *csh = reinterpret_cast<Cand *>(smem_f(kOffCsh));          // 2 * 16 candidates
-    float *sd = smem_f(kOffSd);                                     // d1, d2
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     if (tid == 0) {
+        const Pipe M = pipe_smem();
         for (int s = 0; s < kPStages; s++) { mbar_init(&M.full[s], 1); mbar_init(&M.empty[s], kGemvWarps); }
         for (int s = 0; s < kVecSlots; s++) { mbar_init(&M.vfull[s], 32); mbar_init(&M.vempty[s], kEwWarps); }
         for (int s = 0; s < 2; s++) {
@@ -1259,169 +1513,33 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
         }
         for (int s = 0; s < 8; s++) mbar_init(&M.rempty[2 + s], 1);   // = SweepSmem::mfull, sfull
         mbar_fence_init();
-    }
-    __syncthreads();
-
-    // this CTA's slice of the stream: matrix units [u_begin, u_end) in node-major order
-    const long long n_units = (long long)P.nodes * P.n_mats;
-    Slice R;
-    R.u_begin = (int)(n_units * blockIdx.x / gridDim.x);
-    R.u_end = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
-    R.node_first = R.u_begin < R.u_end ? R.u_begin / P.n_mats : 0;
-    R.node_last = R.u_begin < R.u_end ? (R.u_end - 1) / P.n_mats : -1;
-
-    unsigned int bar_target = 0;
-    StagePhase SP{0u, 0u, 0u, 0u};
-    GemvState GS{0, 0u, 0, 0u, 0, 0u};
-    EwState ES{0, 0u, 0, 0u, 0, 0u};
-    LoaderState LS{0, 0u, 0, 0u, 0};
-    double s1 = 0, s2 = 0;
-    if (tid == 0) {
         unsigned long long *c = clk_smem();
         for (int k = 0; k < 32; k++) c[k] = 0;
         c[32] = globaltimer(); c[33] = blockIdx.x == P.clock_cta ? 1 : 0;
     }
     __syncthreads();
-    auto stamp = [&](int idx) { dstamp(P, idx); };
-    const bool is_gemv = warp < kGemvWarps;
-    const int nr = (nv + 31) >> 5;
 
-    for (int it = 0; it < P.iters; it++) {
-        const float lam = __ldg(P.lambda_tab + it);
-        const int cur = it & 1;
-        // ---- global distances of the previous iteration's prox (cublasSnrm2, :792, :810); zeros at it == 0
-        if (P.n_ranks > 1) {   // every rank published its share (crown counted by rank 0 only); same order everywhere
-            if (tid == 0) {
-                double t1 = 0, t2 = 0;
-                const double *ds = P.dslot_peer[P.rank] + 2 * ((it + 1) & 1);
-                if (it > 0) for (int r = 0; r < P.n_ranks; r++) { t1 += __ldcg(ds + 4 * r); t2 += __ldcg(ds + 4 * r + 1); }
-                sd[0] = (float)sqrt(t1); sd[1] = (float)sqrt(t2);
-            }
-            cbar();
-        } else {
-            double p1 = 0, p2 = 0;
-            for (int k = tid; k < (int)gridDim.x; k += kPC) { p1 += __ldcg(P.dist_part + 2 * k); p2 += __ldcg(P.dist_part + 2 * k + 1); }
-            for (int o = 16; o > 0; o >>= 1) { p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o); }
-            if (lane == 0) { dsh[warp] = p1; dsh[kPC / 32 + warp] = p2; }
-            cbar();
-            if (tid == 0) {
-                double t1 = 0, t2 = 0;
-                for (int w = 0; w < kPC / 32; w++) { t1 += dsh[w]; t2 += dsh[kPC / 32 + w]; }
-                sd[0] = (float)sqrt(t1); sd[1] = (float)sqrt(t2);
-            }
-            cbar();
-        }
-        Cand bx{-1.f, 0.f, 0x7fffffff}, bp{-1.f, 0.f, 0x7fffffff};
+    KState K;
+    // this CTA's slice of the stream: matrix units [u_begin, u_end) in node-major order
+    const long long n_units = (long long)P.nodes * P.n_mats;
+    K.R.u_begin = (int)(n_units * blockIdx.x / gridDim.x);
+    K.R.u_end = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
+    K.R.node_first = K.R.u_begin < K.R.u_end ? K.R.u_begin / P.n_mats : 0;
+    K.R.node_last = K.R.u_begin < K.R.u_end ? (K.R.u_end - 1) / P.n_mats : -1;
+    K.bar_target = 0;
+    K.SP = StagePhase{0u, 0u, 0u, 0u};
+    K.GS = GemvState{0, 0u, 0, 0u, 0, 0u};
+    K.ES = EwState{0, 0u, 0, 0u, 0, 0u};
+    K.LS = LoaderState{0, 0u, 0, 0u, 0};
+    K.s1 = 0; K.s2 = 0;
 
-        // ---- phase S: three-role pipeline.  loader -> [ring] -> GEMV warps -> [red] -> element-wise warps -> [wbuf] -> GEMV
-        if (is_gemv) {
-            if (nr == 4) gemv_role<4>(P, R, GS); else if (nr == 3) gemv_role<3>(P, R, GS);
-            else if (nr == 2) gemv_role<2>(P, R, GS); else gemv_role<1>(P, R, GS);
-        } else if (warp == kLoaderWarp) {
-            loader_role(PS, R, LS, it);
-        } else {
-            const float d1 = sd[0], d2 = sd[1];
-            const float thr1 = P.inv_step * P.pen_x, thr2 = P.inv_step * P.pen_xs;
-            EwIter I;
-            I.a1 = 1.f + lam; I.a2 = -lam; I.cur = cur;
-            I.br1 = d1 > thr1; I.br2 = d2 > thr2;
-            I.sc1 = I.br1 ? 1.f - thr1 / d1 : 0.f; I.sc2 = I.br2 ? 1.f - thr2 / d2 : 0.f;
-            ew_role(PS, R, ES, I, bx, bp);
-        }
-        // infeasibility candidates of iteration it-1 (updatePrimalInfeasibity, :1480-1496)
-        if (it > 0) {
-            bx = cand_warp(bx); bp = cand_warp(bp);
-            if (lane == 0) { csh[warp] = bx; csh[kPC / 32 + warp] = bp; }
-            cbar();
-            if (tid == 0) {
-                Cand x = csh[0], p = csh[kPC / 32];
-                for (int w = 1; w < kPC / 32; w++) { cand_merge(x, csh[w]); cand_merge(p, csh[kPC / 32 + w]); }
-                float *o = P.pinf_part + 6 * (size_t)blockIdx.x;
-                o[0] = x.a; o[1] = x.v; o[2] = __int_as_float(x.idx); o[3] = p.a; o[4] = p.v; o[5] = __int_as_float(p.idx);
-            }
-        }
-        // the stream ring is idle now: pull the shared sweep matrices over it while the grid barrier is pending
-        cbar();
-        if (tid == 0) issue_matrix_loads(PS);
-        stamp(0);
-        grid_sync(P.bar, bar_target);
-        stamp(1);
-        if (it > 0 && blockIdx.x == 0 && warp == 0) {
-            Cand x{-1.f, 0.f, 0x7fffffff}, p{-1.f, 0.f, 0x7fffffff};
-            for (int b = lane; b < (int)gridDim.x; b += 32) {
-                const float *o = P.pinf_part + 6 * (size_t)b;
-                Cand cx{__ldcg(o), __ldcg(o + 1), __float_as_int(__ldcg(o + 2))}, cp{__ldcg(o + 3), __ldcg(o + 4), __float_as_int(__ldcg(o + 5))};
-                cand_merge(x, cx); cand_merge(p, cp);
-            }
-            x = cand_warp(x); p = cand_warp(p);
-            if (lane == 0) {
-                P.pinf[it - 1] = fmaxf(x.v, p.v);    // max(maxValueXi, maxValuePsi) (:1495)
-                float *o4 = P.pinf4 + 4 * (size_t)(it - 1);
-                o4[0] = x.a; o4[1] = x.v; o4[2] = p.a; o4[3] = p.v;   // for the cross-rank merge on the host
-            }
-        }
-        const uint32_t mpar = (uint32_t)(it & 1);
-        // crown tiles: as narrow as the grid allows (every CTA is free during phase C)
-        const int tile_w = min(kTP / 2, max(1, (P.n_crown + (int)gridDim.x - 1) / (int)gridDim.x));
-        const int n_tiles = (P.n_crown + tile_w - 1) / tile_w;
-        const int grid = (int)gridDim.x, j0 = (int)blockIdx.x;
-
-        // ---- phase B: backward sweep of the chains (operand blocks by bulk TMA, one chain ahead)
-        stamp(2);
-        if (tid == 0 && j0 < P.K) issue_chain_backward_loads(PS, j0);
-        for (int j = j0; j < P.K; j += grid) chain_backward(PS, j, j + grid < P.K ? j + grid : -1, mpar, SP);
-        stamp(10);
-        // ---- phase C: backward sweep of the crown (tiles are dealt from the last CTA down: those have the fewest chains)
-        if (P.n_crown > 0) {
-            // the crown needs the heads of every chain: with several GPUs their q, r were stored into every rank's
-            // table (chain_qscan / chain_rscan), and this barrier spans the GPUs
-            if (P.n_ranks > 1) grid_sync_cross(P, bar_target, P.epoch0 + 2u * (unsigned)it + 1u, [] {});
-            else grid_sync(P.bar, bar_target);
-            stamp(20);
-            for (int tl = grid - 1 - j0; tl < n_tiles; tl += grid)
-                crown_backward(PS, tl * tile_w, min(tile_w, P.n_crown - tl * tile_w), mpar, SP);
-            stamp(21);
-        }
-        // G has done its work for this iteration: B takes its place (every step above ended with a CTA barrier)
-        if (tid == 0) issue_b_load(PS);
-        if (P.n_crown > 0) {
-            grid_sync(P.bar, bar_target);
-            stamp(22);
-        }
-        // ---- phase F: forward sweep + prox boxes
-        const float *wxi = P.Wxi[cur], *wpsi = P.Wpsi[cur];
-        if (tid == 0 && j0 < P.K) issue_chain_forward_loads(PS, j0);
-        {
-            double c1 = 0, c2 = 0;
-            for (int tl = grid - 1 - j0; tl < n_tiles; tl += grid)
-                crown_forward(PS, tl * tile_w, min(tile_w, P.n_crown - tl * tile_w), mpar, wxi, wpsi, c1, c2);
-            if (P.rank == 0) { s1 += c1; s2 += c2; }   // the crown is replicated: it counts once in the global distances
-        }
-        for (int j = j0; j < P.K; j += grid) chain_forward(PS, j, j + grid < P.K ? j + grid : -1, mpar, SP, wxi, wpsi, s1, s2);
-        stamp(23);
-        {   // this CTA's share of the two squared distances
-            for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-            if (lane == 0) { dsh[warp] = s1; dsh[kPC / 32 + warp] = s2; }
-            cbar();
-            if (tid == 0) {
-                double t1 = 0, t2 = 0;
-                for (int w = 0; w < kPC / 32; w++) { t1 += dsh[w]; t2 += dsh[kPC / 32 + w]; }
-                P.dist_part[2 * blockIdx.x] = t1; P.dist_part[2 * blockIdx.x + 1] = t2;
-            }
-            s1 = 0; s2 = 0;
-        }
-        stamp(28);
-        if (P.n_ranks > 1) {
-            grid_sync_cross(P, bar_target, P.epoch0 + 2u * (unsigned)it + 2u, [&] {
-                double t1 = 0, t2 = 0;   // this rank's share, CTA order
-                for (int k = 0; k < (int)gridDim.x; k++) { t1 += __ldcg(P.dist_part + 2 * k); t2 += __ldcg(P.dist_part + 2 * k + 1); }
-                for (int r = 0; r < P.n_ranks; r++) {
-                    double *ds = P.dslot_peer[r] + 2 * (it & 1) + 4 * P.rank;
-                    ds[0] = t1; ds[1] = t2;
-                }
-            });
-        } else grid_sync(P.bar, bar_target);
-        stamp(29);
+    const int iters = P.iters;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+        iter_stream(PS, K, it);
+        iter_backward(PS, K, it);
+        iter_forward(PS, K, it);
+        iter_close(PS, K, it);
     }
     if (P.n_ranks > 1 && blockIdx.x == 0 && tid == 0) {   // k_finalize reads the global sums from slot 0
         double t1 = 0, t2 = 0;
@@ -1440,7 +1558,7 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 struct SweepLayout {
-    int oG, oOm, oL, oX1, oY, oV, oScr2, oStg, end;   // shared-memory float offsets
+    int oG, oOm, oL, oX1, oY, oV, oScr2, oStg, oXb, end;   // shared-memory float offsets
     int pG, pOm, pL, pB, pack_floats;                 // float offsets inside the pack
     int nxp, nup, nvp;
 };
@@ -1457,7 +1575,8 @@ static SweepLayout sweep_layout(const Handle *h) {
     Y.oV = Y.oY + std::max(std::max(nv, nu), nx) * kTP;
     Y.oScr2 = Y.oV + std::max(nv, nu) * kTP;
     Y.oStg = Y.oScr2 + 128 * kTP;
-    Y.end = Y.oStg + std::max(T * Y.nxp + 5 * T * Y.nvp, 2 * T * Y.nup + T * Y.nxp);
+    Y.oXb = Y.oStg + std::max(T * Y.nxp + 5 * T * Y.nvp, 2 * T * Y.nup + T * Y.nxp);
+    Y.end = Y.oXb + nx * kTP;
     return Y;
 }
 // matrix ring of phase S: whole factor matrices per stage when three of them fit next to the sweep region's size,
@@ -1636,7 +1755,7 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     P.lambda_tab = h->lambda_tab; P.bar = h->grid_bar; P.iter_dev = h->iter_dev; P.phase_ns = h->phase_ns;
     P.step = h->step; P.inv_step = 1 / h->step; P.pen_x = h->pen_x; P.pen_xs = h->pen_xs;
     const SweepLayout Y = sweep_layout(h);
-    P.oG = Y.oG; P.oOm = Y.oOm; P.oL = Y.oL; P.oX1 = Y.oX1; P.oY = Y.oY; P.oV = Y.oV; P.oScr2 = Y.oScr2; P.oStg = Y.oStg;
+    P.oG = Y.oG; P.oOm = Y.oOm; P.oL = Y.oL; P.oX1 = Y.oX1; P.oY = Y.oY; P.oV = Y.oV; P.oScr2 = Y.oScr2; P.oStg = Y.oStg; P.oXb = Y.oXb;
     P.pG = Y.pG; P.pOm = Y.pOm; P.pL = Y.pL; P.pB = Y.pB;
     P.bG = (unsigned)(Y.pOm - Y.pG) * 4u; P.bOm = (unsigned)(Y.pL - Y.pOm) * 4u; P.bL = (unsigned)(Y.pB - Y.pL) * 4u;
     P.bB = (unsigned)(Y.pack_floats - Y.pB) * 4u;

@@ -8,7 +8,7 @@ mkdir -p "$OUT"
 nvidia-smi -L > "$OUT/gpu.txt" 2>&1
 nproc >> "$OUT/gpu.txt"
 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/summary.txt"
-timeout 1500 python -m pytest tests -m gpu ${PYTEST_X:--x} -q -s --timeout 400 > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/summary.txt"
+timeout 1500 python -m pytest tests -m gpu ${PYTEST_X--x} -q -s --timeout 400 > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/summary.txt"
 tail -5 "$OUT/pytest_gpu.log"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; echo "bench ref rc=$?" | tee -a "$OUT/summary.txt"
 timeout 600 python bench.py --steps 5 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?" | tee -a "$OUT/summary.txt"
