@@ -108,7 +108,7 @@ struct Handle {
     float *pinf4 = nullptr;
     int pinf4_cap = 0;
     float *cm_c = nullptr, *cm_lv = nullptr, *cm_beta = nullptr, *cm_uhat = nullptr, *cm_e = nullptr;   // chain-major arrays
-    int *crown_rng = nullptr, *pos_dev = nullptr;
+    int *crown_rng = nullptr, *pos_dev = nullptr, *crown_path = nullptr;
     unsigned int *grid_bar = nullptr;
     unsigned long long *phase_ns = nullptr;
     bool persist_ready = false;

@@ -55,6 +55,8 @@ struct PArgs {
     const int *parent, *child_first, *child_count, *omega_idx, *cum, *stages;
     const int *pos;                             // [nodes] chain-major row of a node (crown: its id; chain j, stage s: n_crown + j T + s)
     const int *crown_rng;                       // [n_crown][kMaxCs + 1][2]: descendant id range of a crown node per stage
+    const int *crown_path;                      // [n_crown][kMaxCs]: path root -> node of every crown node (entry k = its stage-k ancestor)
+    unsigned int branch_mask;                   // bit s: stage s has more nodes than stage s-1 (the reference's branching stages, :699-719)
     int N, cs, K, nodes, n_crown, n_mats, df_mode, iters, nx, nu, nv, cols_per_chunk, clock_cta;
     int n_stages, stage_stride;                 // matrix ring: stages and floats per stage (payload + 32 floats of slack)
     const float *mat[4];                        // D, F, Phi, Psi (packed per node, Engine.cu:201-207)
@@ -82,6 +84,7 @@ struct PArgs {
     float *pinf, *pinf_part;                    // [iters], [grid*6]
     const float *lambda_tab;
     unsigned int *bar;
+    unsigned int *heads_ctr;                    // chains whose head q, r are published (single GPU: the crown waits on it instead of a grid barrier)
     int *iter_dev;
     unsigned long long *phase_ns;               // [32] fine-grained phase clock of one CTA (see cabi.PHASE_NAMES)
     float step, inv_step, pen_x, pen_xs;
@@ -109,7 +112,7 @@ __device__ __forceinline__ unsigned long long globaltimer() {
 // fine-grained clock of one CTA (thread 0): accumulates the time since the previous stamp into a shared-memory slot
 // (flushed to phase_ns at the end of the kernel; a global read-modify-write per stamp would cost a microsecond each)
 __device__ __forceinline__ unsigned long long *clk_smem();
-__device__ __forceinline__ void dstamp(const PArgs &P, int idx) {
+__device__ __noinline__ void dstamp_at(int idx) {
     if (threadIdx.x == 0) {
         unsigned long long *c = clk_smem();
         if (c[33]) {   // this CTA is the clock CTA
@@ -119,6 +122,7 @@ __device__ __forceinline__ void dstamp(const PArgs &P, int idx) {
         }
     }
 }
+__device__ __forceinline__ void dstamp(const PArgs &, int idx) { dstamp_at(idx); }   // a call: the sweeps are bound by instruction fetch
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -133,7 +137,7 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
 
 // grid barrier over all CTAs (the grid is co-resident: cooperative launch).  Same protocol as
 // cooperative_groups::grid_group::sync: CTA barrier, one thread fences + arrives + spins + fences, CTA barrier.
-__device__ __forceinline__ void grid_sync(unsigned int *ctr, unsigned int &target) {
+__device__ __noinline__ void grid_sync(unsigned int *ctr, unsigned int &target) {
     cbar();
     if (threadIdx.x == 0) {
         target += gridDim.x;
@@ -167,12 +171,12 @@ __device__ __forceinline__ void wait_sys(const unsigned int *p, unsigned int wan
 }
 
 // Grid barrier that is also a barrier across the GPUs of the partition: every CTA arrives on the local counter; CTA 0
-// waits for all of them, runs `mid()` (its thread 0: publish this rank's contribution to the peers), signals epoch
-// `ep` into every peer's flag array (NVLink stores), waits for every peer's signal, then releases the local CTAs.
-// Peer data written by any thread of this GPU before the barrier is ordered before the signal by the CTA barriers +
-// the system-scope fence (cumulativity), like cooperative_groups' grid sync does at device scope.
-template <typename Mid>
-__device__ __forceinline__ void grid_sync_cross(const PArgs &P, unsigned int &target, unsigned int ep, Mid mid) {
+// waits for all of them, (publish_it >= 0: thread 0 publishes this rank's share of the squared prox distances of
+// iteration publish_it to the peers), signals epoch `ep` into every peer's flag array (NVLink stores), waits for every
+// peer's signal, then releases the local CTAs.  Peer data written by any thread of this GPU before the barrier is
+// ordered before the signal by the CTA barriers + the system-scope fence (cumulativity), like cooperative_groups'
+// grid sync does at device scope.
+__device__ __noinline__ void grid_sync_cross(const PArgs &P, unsigned int &target, unsigned int ep, int publish_it) {
     cbar();
     if (threadIdx.x == 0) {
         target += gridDim.x;
@@ -180,7 +184,14 @@ __device__ __forceinline__ void grid_sync_cross(const PArgs &P, unsigned int &ta
         atomicAdd(P.bar, 1u);
         if (blockIdx.x == 0) {
             while (ld_acquire_u32(P.bar) < target) {}
-            mid();
+            if (publish_it >= 0) {
+                double t1 = 0, t2 = 0;   // this rank's share, CTA order
+                for (int k = 0; k < (int)gridDim.x; k++) { t1 += __ldcg(P.dist_part + 2 * k); t2 += __ldcg(P.dist_part + 2 * k + 1); }
+                for (int r = 0; r < P.n_ranks; r++) {
+                    double *ds = P.dslot_peer[r] + 2 * (publish_it & 1) + 4 * P.rank;
+                    ds[0] = t1; ds[1] = t2;
+                }
+            }
             __threadfence_system();
             for (int r = 0; r < P.n_ranks; r++) st_release_sys_u32(P.xflag_peer[r] + P.rank, ep);
             for (int r = 0; r < P.n_ranks; r++) wait_sys(P.xflag_peer[P.rank] + r, ep, P.xerr);
@@ -203,7 +214,9 @@ constexpr int kOffDsh = kOffScr + kPC;                                  // 2 x 1
 constexpr int kOffCsh = kOffDsh + 2 * 2 * (kPC / 32);                   // 2 x 16 candidates (3 words each)
 constexpr int kOffSd = kOffCsh + 3 * 2 * (kPC / 32);                    // d1, d2
 constexpr int kOffMisc = kOffSd + 4;                                    // 4 x kTP words: column -> row / node maps etc.
-constexpr int kOffClk = (kOffMisc + 4 * kTP + 1) & ~1;                   // 34 x u64: phase clock accumulators, t_prev, enabled
+constexpr int kOffMeta = kOffMisc + 4 * kTP;                             // 64 words: column maps of this CTA's first chain (cache)
+constexpr int kOffFix = kOffMeta + 64;                                  // u_prev | uhat_prev | x_cur, kVStride floats each (per launch)
+constexpr int kOffClk = (kOffFix + 3 * kVStride + 1) & ~1;                   // 34 x u64: phase clock accumulators, t_prev, enabled
 constexpr int kOffPArgs = kOffClk + 2 * 34;                            // a copy of the kernel arguments (see k_apg_persistent)
 constexpr int kPArgsWords = 256;
 constexpr int kOffBar = kOffPArgs + kPArgsWords;                                  // mbarriers
@@ -292,18 +305,32 @@ __device__ __forceinline__ void issue_chain_backward_loads(const PArgs &P, int j
         bulk_g2s(d, P.part[3] + row0 * P.nvp, bv, &S.sfull[2]);
     }
 }
-// one thread: the forward operand blocks of chain j -> staging.  Layout: uhat | L v | e
-__device__ __forceinline__ void issue_chain_forward_loads(const PArgs &P, int j) {
+// one thread: the forward operand blocks of chain j -> staging.  Layout: uhat | L v | e (T rows each), then the rows of
+// the chain's crown path (root first): uhat [cs][nup] | L v [cs][nup] | e [cs][nxp] -- the scans read shared memory only
+__device__ __noinline__ void issue_chain_forward_loads(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
-    const int T = P.N - P.cs;
+    const int T = P.N - P.cs, cs = P.cs, nup = P.nup, nxp = P.nxp;
     const size_t row0 = (size_t)P.n_crown + (size_t)j * T;
-    const uint32_t bx = (uint32_t)(T * P.nxp * 4), bu = (uint32_t)(T * P.nup * 4);
+    const uint32_t bx = (uint32_t)(T * nxp * 4), bu = (uint32_t)(T * nup * 4);
     float *d = S.stg;
     fence_proxy_async_all();
-    mbar_expect_tx(&S.sfull[3], 2 * bu + bx);
-    bulk_g2s(d, P.cm_uhat + row0 * P.nup, bu, &S.sfull[3]); d += T * P.nup;
-    bulk_g2s(d, P.cm_lv + row0 * P.nup, bu, &S.sfull[3]); d += T * P.nup;
-    bulk_g2s(d, P.cm_e + row0 * P.nxp, bx, &S.sfull[3]);
+    mbar_expect_tx(&S.sfull[3], 2 * bu + bx + (uint32_t)cs * (uint32_t)(2 * nup + nxp) * 4u);
+    bulk_g2s(d, P.cm_uhat + row0 * nup, bu, &S.sfull[3]); d += T * nup;
+    bulk_g2s(d, P.cm_lv + row0 * nup, bu, &S.sfull[3]); d += T * nup;
+    bulk_g2s(d, P.cm_e + row0 * nxp, bx, &S.sfull[3]); d += T * nxp;
+    if (cs > 0) {
+        const int *meta = reinterpret_cast<const int *>(smem_f(kOffMeta));
+        const bool hit = meta[0] == j;
+        int a = hit ? 0 : __ldg(P.parent + __ldg(P.cum + cs) + j);
+#pragma unroll 1
+        for (int k = cs - 1; k >= 0; k--) {
+            if (hit) a = meta[1 + 2 * kTP + k];
+            bulk_g2s(d + k * nup, P.cm_uhat + (size_t)a * nup, (uint32_t)nup * 4u, &S.sfull[3]);
+            bulk_g2s(d + (cs + k) * nup, P.cm_lv + (size_t)a * nup, (uint32_t)nup * 4u, &S.sfull[3]);
+            bulk_g2s(d + 2 * cs * nup + k * nxp, P.cm_e + (size_t)a * nxp, (uint32_t)nxp * 4u, &S.sfull[3]);
+            if (!hit) a = __ldg(P.parent + a);
+        }
+    }
 }
 
 __device__ __forceinline__ void row_load(const float *row, float (&v)[kTP]) {
@@ -319,25 +346,10 @@ __device__ __forceinline__ void row_store(float *row, const float (&v)[kTP]) {
         *reinterpret_cast<float4 *>(row + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
 
-// what tile_gemm does with its result
-enum GemmEpi { kEpiStore = 0, kEpiV = 1, kEpiLv = 2 };
-struct EpiArgs {
-    const int *colnode, *colid;   // per column: chain-major row / node id
-    const float *colp;            // per column: probability
-    const float *p2, *p3;         // kEpiV: Phi xi, Psi psi of the columns -- staged [col][ld23] or (staged == 0) chain-major global
-    float *out_g;                 // kEpiV: devVecV [node][ld_g];  kEpiLv: chain-major L v [row][ld_g]
-    int ncols, ld23, ld_g, staged, df;
-};
-
 // Y[r][c] = sum_k M[r + k*m] X[k][c],  r < m, c < kTP.  M (m x K, column-major), X, Y and scr2 in shared memory.
 // 256 threads compute: thread = (rows {rp, rp + 64}, 12 columns, one half of k); the upper half of k is handed over
-// through scr2.  Epilogue (fused into the hand-over so that no extra pass / barrier is needed):
-//   kEpiStore  Y = result
-//   kEpiV      v = ((result / p_col) + Psi psi) + Phi xi  [df: result / p_col]  -> Y (next GEMM's input) and devVecV
-//   kEpiLv     result -> the chain-major L v array only
-// All kPC threads call; ends with a CTA barrier.
-template <int EPI>
-__device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float *X, float *Y, float *scr2, const EpiArgs *E) {
+// through scr2.  All kPC threads call; ends with a CTA barrier.
+__device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float *X, float *Y, float *scr2) {
     const int t = threadIdx.x, ks = t >> 7, u = t & 127, rp = u & 63, cg = u >> 6;
     const bool work = ks < 2 && rp < m;
     const bool two = rp + 64 < m;
@@ -372,75 +384,27 @@ __device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float
     if (work && ks == 0) {
         const float4 *sp = reinterpret_cast<const float4 *>(scr2 + u * kTP);
         const float4 p0 = sp[0], p1 = sp[1], p2 = sp[2], p3 = sp[3], p4 = sp[4], p5 = sp[5];
-        a0[0] += p0.x; a0[1] += p0.y; a0[2] += p0.z; a0[3] += p0.w; a0[4] += p1.x; a0[5] += p1.y; a0[6] += p1.z; a0[7] += p1.w;
-        a0[8] += p2.x; a0[9] += p2.y; a0[10] += p2.z; a0[11] += p2.w;
-        a1[0] += p3.x; a1[1] += p3.y; a1[2] += p3.z; a1[3] += p3.w; a1[4] += p4.x; a1[5] += p4.y; a1[6] += p4.z; a1[7] += p4.w;
-        a1[8] += p5.x; a1[9] += p5.y; a1[10] += p5.z; a1[11] += p5.w;
-        if (EPI != kEpiStore) {
-            // everything out of *E first (it sits behind a generic pointer: the global stores below would force re-reads)
-            const int c0 = cg * 12, ncols = E->ncols, ldg = E->ld_g, ld23 = E->ld23;
-            const bool staged = E->staged != 0, df = E->df != 0;
-            float *__restrict__ og = E->out_g;
-            const float *__restrict__ p2g = E->p2, *__restrict__ p3g = E->p3;
-            const int *rows = EPI == kEpiV ? E->colid : E->colnode, *cn = E->colnode;
-            const float *colp = E->colp;
-            int rg[12], r23[12];
-            float pinv[12];
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                const int c = c0 + i;
-                rg[i] = c < ncols ? rows[c] : 0;
-                r23[i] = staged ? c : (c < ncols ? cn[c] : 0);
-                pinv[i] = EPI == kEpiV ? colp[c] : 1.f;
-            }
-            if (EPI == kEpiV) {
-                float b30[12], b20[12], b31[12], b21[12];
-#pragma unroll
-                for (int i = 0; i < 12; i++) {
-                    b30[i] = b20[i] = b31[i] = b21[i] = 0.f;
-                    if (!df && c0 + i < ncols) {
-                        const float *q3 = p3g + (size_t)r23[i] * ld23 + rp, *q2 = p2g + (size_t)r23[i] * ld23 + rp;
-                        if (staged) { b30[i] = q3[0]; b20[i] = q2[0]; if (two) { b31[i] = q3[64]; b21[i] = q2[64]; } }
-                        else { b30[i] = __ldcg(q3); b20[i] = __ldcg(q2); if (two) { b31[i] = __ldcg(q3 + 64); b21[i] = __ldcg(q2 + 64); } }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 12; i++) {
-                    a0[i] = (a0[i] * pinv[i] + b30[i]) + b20[i];
-                    a1[i] = (a1[i] * pinv[i] + b31[i]) + b21[i];
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                if (c0 + i < ncols) {
-                    og[(size_t)rg[i] * ldg + rp] = a0[i];
-                    if (two) og[(size_t)rg[i] * ldg + rp + 64] = a1[i];
-                } else { a0[i] = 0.f; a1[i] = 0.f; }
-            }
-        }
-        if (EPI != kEpiLv) {
-            float4 *y0 = reinterpret_cast<float4 *>(Y + rp * kTP + cg * 12);
-            y0[0] = make_float4(a0[0], a0[1], a0[2], a0[3]); y0[1] = make_float4(a0[4], a0[5], a0[6], a0[7]);
-            y0[2] = make_float4(a0[8], a0[9], a0[10], a0[11]);
-            if (two) {
-                float4 *y1 = reinterpret_cast<float4 *>(Y + (rp + 64) * kTP + cg * 12);
-                y1[0] = make_float4(a1[0], a1[1], a1[2], a1[3]); y1[1] = make_float4(a1[4], a1[5], a1[6], a1[7]);
-                y1[2] = make_float4(a1[8], a1[9], a1[10], a1[11]);
-            }
+        float4 *y0 = reinterpret_cast<float4 *>(Y + rp * kTP + cg * 12);
+        y0[0] = make_float4(a0[0] + p0.x, a0[1] + p0.y, a0[2] + p0.z, a0[3] + p0.w);
+        y0[1] = make_float4(a0[4] + p1.x, a0[5] + p1.y, a0[6] + p1.z, a0[7] + p1.w);
+        y0[2] = make_float4(a0[8] + p2.x, a0[9] + p2.y, a0[10] + p2.z, a0[11] + p2.w);
+        if (two) {
+            float4 *y1 = reinterpret_cast<float4 *>(Y + (rp + 64) * kTP + cg * 12);
+            y1[0] = make_float4(a1[0] + p3.x, a1[1] + p3.y, a1[2] + p3.z, a1[3] + p3.w);
+            y1[1] = make_float4(a1[4] + p4.x, a1[5] + p4.y, a1[6] + p4.z, a1[7] + p4.w);
+            y1[2] = make_float4(a1[8] + p5.x, a1[9] + p5.y, a1[10] + p5.z, a1[11] + p5.w);
         }
     }
     cbar();
 }
 
 // all threads: dst[row(col)*ld + e] = src[e][col] for col < ncols, e < dim (rows from `rows`: node ids or chain-major rows)
-__device__ __forceinline__ void cols_to_global(const float *src, const int *rows, int ncols, int dim, int ld, float *__restrict__ dst) {
-    const int e = threadIdx.x & 127, s0 = threadIdx.x >> 7;
+__device__ __noinline__ void cols_to_global(const float *src, const int *rows, int ncols, int dim, int ld, float *__restrict__ dst) {
+    const int e = threadIdx.x & 127;
     if (e >= dim) return;
-#pragma unroll
-    for (int k = 0; k < kTP / 4; k++) {
-        const int s = s0 + 4 * k;
-        if (s < ncols) dst[(size_t)rows[s] * ld + e] = src[e * kTP + s];
-    }
+    src += e * kTP; dst += e;
+#pragma unroll 2
+    for (int s = threadIdx.x >> 7; s < ncols; s += 4) dst[(size_t)rows[s] * ld] = src[s];
 }
 
 __device__ __forceinline__ bool stage_branches(const int *__restrict__ cum, int s) {   // more nodes than the stage above (:699-719)
@@ -451,32 +415,28 @@ __device__ __forceinline__ bool stage_branches(const int *__restrict__ cum, int 
 // -1/2 Omega Bbar', Engine.cu:729-734) [df: v = -1/2 Omega r]: Y = OmegaBar X1s on entry, Omega_i = OmegaBar / p_i
 // (colp holds 1 / p_i).  All threads: thread = (row, every 4th column).  V rows (next GEMM's input) and devVecV.
 __device__ __forceinline__ void sweep_vcombine(const PArgs &P, const SweepSmem &S, int ncols, bool staged) {
-    const int e = threadIdx.x & 127, s0 = threadIdx.x >> 7, nv = P.nv, nvp = P.nvp, T = P.N - P.cs;
+    const int e = threadIdx.x & 127, nv = P.nv, nvp = P.nvp, T = P.N - P.cs;
     if (e >= nv) return;
     const bool df = P.df_mode != 0;
-    const float *__restrict__ g2 = P.part[2], *__restrict__ g3 = P.part[3];
-    float *__restrict__ Vg = P.V;
-    const float *s2 = S.stg + T * P.nxp + 3 * T * nvp, *s3 = s2 + T * nvp;
-    float y[kTP / 4], b2[kTP / 4], b3[kTP / 4];
-#pragma unroll
-    for (int k = 0; k < kTP / 4; k++) {
-        const int s = s0 + 4 * k;
-        y[k] = S.Y[e * kTP + s];
-        b2[k] = b3[k] = 0.f;
-        if (!df && s < ncols) {
-            b3[k] = staged ? s3[s * nvp + e] : __ldcg(g3 + (size_t)S.colnode[s] * nvp + e);
-            b2[k] = staged ? s2[s * nvp + e] : __ldcg(g2 + (size_t)S.colnode[s] * nvp + e);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kTP / 4; k++) {
-        const int s = s0 + 4 * k;
+    // Phi xi, Psi psi of the columns: staged [col][nvp] (chains) or chain-major global rows (crown tiles: a few columns)
+    const float *b2p = staged ? S.stg + T * P.nxp + 3 * T * nvp + e : P.part[2] + e, *b3p = staged ? b2p + T * nvp : P.part[3] + e;
+    float *__restrict__ Vg = P.V + e;
+    const float *y = S.Y + e * kTP;
+    float *vr = S.V + e * kTP;
+#pragma unroll 1
+    for (int s = threadIdx.x >> 7; s < kTP; s += 4) {
         float v = 0.f;
         if (s < ncols) {
-            v = (y[k] * S.colp[s] + b3[k]) + b2[k];
-            Vg[(size_t)S.colid[s] * nv + e] = v;
+            float b3 = 0.f, b2 = 0.f;
+            if (!df) {
+                const size_t row = staged ? (size_t)s : (size_t)S.colnode[s];
+                b3 = staged ? b3p[row * nvp] : __ldcg(b3p + row * nvp);
+                b2 = staged ? b2p[row * nvp] : __ldcg(b2p + row * nvp);
+            }
+            v = (y[s] * S.colp[s] + b3) + b2;
+            Vg[(size_t)S.colid[s] * nv] = v;
         }
-        S.V[e * kTP + s] = v;
+        vr[s] = v;
     }
 }
 
@@ -486,7 +446,7 @@ __device__ __noinline__ void sweep_backward_finish(const PArgs &P, int ncols, bo
     const int nv = P.nv, nu = P.nu, nup = P.nup;
     float *LVg = P.cm_lv;
     mbar_wait(&S.mfull[1], mpar);
-    tile_gemm<kEpiStore>(S.Om, nv, nv, S.X1 + P.nx * kTP, S.Y, S.scr2, nullptr);   // OmegaBar (sigma + G q_bar) (-1/2 folded in)
+    tile_gemm(S.Om, nv, nv, S.X1 + P.nx * kTP, S.Y, S.scr2);   // OmegaBar (sigma + G q_bar) (-1/2 folded in)
     dstamp(P, 6);
     if (staged && !P.df_mode) { mbar_wait(&S.sfull[2], ph.v); ph.v ^= 1; }
     sweep_vcombine(P, S, ncols, staged);
@@ -495,7 +455,7 @@ __device__ __noinline__ void sweep_backward_finish(const PArgs &P, int ncols, bo
     if (next_chain >= 0 && threadIdx.x == 0) issue_chain_backward_loads(P, next_chain);
     dstamp(P, 7);
     mbar_wait(&S.mfull[2], mpar);
-    tile_gemm<kEpiStore>(S.L, nu, nv, S.V, S.Y, S.scr2, nullptr);                  // L v   (:701, :727)
+    tile_gemm(S.L, nu, nv, S.V, S.Y, S.scr2);                  // L v   (:701, :727)
     dstamp(P, 8);
     cols_to_global(S.Y, S.colnode, ncols, nu, nup, LVg);
     cbar();
@@ -503,14 +463,25 @@ __device__ __noinline__ void sweep_backward_finish(const PArgs &P, int ncols, bo
 }
 
 // ---- chains ------------------------------------------------------------------------------------------------------
-// columns of chain j: s = 0 .. T-1 <-> node cum[cs + s] + j; also the chain's crown path (root first) for the forward sweep
-__device__ __forceinline__ void chain_columns(const PArgs &P, int j) {
+// columns of chain j: s = 0 .. T-1 <-> node cum[cs + s] + j; also the chain's crown path (root first) for the forward sweep.
+// The maps of the CTA's first chain are kept in shared memory for the whole launch (they cost chains of dependent
+// global loads: parent pointers, omega_idx -> prob), so with K <= grid they are computed once.
+__device__ __noinline__ void chain_columns(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
     const int t = threadIdx.x, T = P.N - P.cs;
+    int *meta = reinterpret_cast<int *>(smem_f(kOffMeta));   // [0] chain id, colid[kTP], colp[kTP], anc[kMaxCs]
+    static_assert(1 + 2 * kTP + kMaxCs <= 64, "chain metadata cache");
+    const bool hit = meta[0] == j;
+    if (t < kTP) S.colnode[t] = t < T ? P.n_crown + j * T + t : 0;
+    if (hit) {
+        if (t < kTP) { S.colid[t] = meta[1 + t]; S.colp[t] = __int_as_float(meta[1 + kTP + t]); }
+        if (t < kMaxCs) S.anc[t] = meta[1 + 2 * kTP + t];
+        cbar();
+        return;
+    }
     if (t < kTP) {
         const int node = t < T ? __ldg(P.cum + P.cs + t) + j : 0;
         S.colid[t] = node;
-        S.colnode[t] = t < T ? P.n_crown + j * T + t : 0;
         S.colp[t] = t < T ? 1.f / __ldg(P.prob + __ldg(P.omega_idx + node)) : 1.f;   // Omega_i = OmegaBar / p_i
     }
     if (t == 32) {
@@ -518,25 +489,33 @@ __device__ __forceinline__ void chain_columns(const PArgs &P, int j) {
         for (int k = P.cs - 1; k >= 0; k--) { S.anc[k] = a; a = a >= 0 ? __ldg(P.parent + a) : -1; }
     }
     cbar();
+    if (j == (int)blockIdx.x) {   // every later call is separated from this one by CTA barriers
+        if (t < kTP) { meta[1 + t] = S.colid[t]; meta[1 + kTP + t] = __float_as_int(S.colp[t]); }
+        if (t < kMaxCs) meta[1 + 2 * kTP + t] = t < P.cs ? S.anc[t] : -1;
+        if (t == 0) meta[0] = j;
+    }
 }
+
+// The scans below are short loops over the chain's stages with scalar shared-memory accesses on purpose: the sweep
+// phases are bound by instruction fetch (ncu: "no instruction" is 60-85 % of their stall samples -- every step runs
+// once per chain and iteration, and the whole iteration's code does not fit the instruction cache), so a 24-step
+// unrolled body costs more in fetch than the bank conflicts of the [element][kTP] column arrays cost here.
 
 // q-scan: q = c + q_child (:651-658).  X1 rows 0..nx-1 get q_bar (q of the child, 0 at the leaf); head q -> qh[j]
 __device__ __noinline__ void chain_qscan(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
     const int e = threadIdx.x, T = P.N - P.cs, nx = P.nx, nxp = P.nxp;
     if (e >= nx) return;
-    const float *cs_ = S.stg;
-    float cv[kTP];
-#pragma unroll
-    for (int s = 0; s < kTP; s++) cv[s] = s < T ? cs_[s * nxp + e] : 0.f;
+    const float *cs_ = S.stg + e;
+    float *x1 = S.X1 + e * kTP;
+    for (int s = T; s < kTP; s++) x1[s] = 0.f;
     float qrun = 0.f;
-#pragma unroll
-    for (int s = kTP - 1; s >= 0; s--) {
-        const float c = cv[s];
-        cv[s] = s < T ? qrun : 0.f;
-        if (s < T) qrun = c + qrun;
+#pragma unroll 4
+    for (int s = T - 1; s >= 0; s--) {
+        const float c = cs_[s * nxp];
+        x1[s] = qrun;
+        qrun = c + qrun;
     }
-    row_store(S.X1 + e * kTP, cv);
     const size_t hrow = (size_t)(P.chain_off + j) * nx + e;   // every rank's copy of the table (own copy: plain store)
     for (int r = 0; r < P.n_ranks; r++) P.qh_peer[r][hrow] = qrun;
 }
@@ -548,21 +527,18 @@ __device__ __noinline__ void chain_rscan(const PArgs &P, int j) {
     const int e = threadIdx.x, T = P.N - P.cs, nv = P.nv, nvp = P.nvp;
     if (e >= nv) return;
     const bool df = P.df_mode != 0;
-    const float *sb = S.stg + T * P.nxp, *s0 = sb + T * nvp, *s1 = s0 + T * nvp;
-    float y[kTP];
-    row_load(S.Y + e * kTP, y);
+    const float *sb = S.stg + T * P.nxp + e, *s0 = sb + T * nvp, *s1 = s0 + T * nvp;
+    const float *y = S.Y + e * kTP;
+    float *x1 = S.X1 + (P.nx + e) * kTP;
+    for (int s = T; s < kTP; s++) x1[s] = 0.f;
     float rrun = 0.f;
-#pragma unroll
-    for (int s = kTP - 1; s >= 0; s--) {
-        float out = 0.f;
-        if (s < T) {
-            const float sg = sb[s * nvp + e] + rrun;
-            rrun = ((sg + s0[s * nvp + e]) + s1[s * nvp + e]) + y[s];
-            out = -0.5f * (df ? rrun : sg + y[s]);
-        }
-        y[s] = out;
+#pragma unroll 4
+    for (int s = T - 1; s >= 0; s--) {
+        const float ys = y[s];
+        const float sg = sb[s * nvp] + rrun;
+        rrun = ((sg + s0[s * nvp]) + s1[s * nvp]) + ys;
+        x1[s] = -0.5f * (df ? rrun : sg + ys);
     }
-    row_store(S.X1 + (P.nx + e) * kTP, y);
     const size_t hrow = (size_t)(P.chain_off + j) * nv + e;
     for (int r = 0; r < P.n_ranks; r++) P.rh_peer[r][hrow] = rrun;
 }
@@ -575,184 +551,146 @@ __device__ __noinline__ void chain_backward(const PArgs &P, int j, int next_chai
     cbar();
     dstamp(P, 3);
     mbar_wait(&S.mfull[0], mpar);
-    tile_gemm<kEpiStore>(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2, nullptr);                               // G q_bar   (:644-646)
+    tile_gemm(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2);                               // G q_bar   (:644-646)
     dstamp(P, 4);
     mbar_wait(&S.sfull[1], ph.r); ph.r ^= 1;
     chain_rscan(P, j);
     cbar();
+    if (threadIdx.x == 0 && P.n_ranks == 1 && P.n_crown > 0) {   // this chain's head q, r are in the tables: tell the crown
+        __threadfence();
+        atomicAdd(P.heads_ctr, 1u);
+    }
     dstamp(P, 5);
     sweep_backward_finish(P, P.N - P.cs, true, mpar, ph, next_chain);
 }
 
-// the read-only inputs of the forward recursion along a crown path, read out of P once per step
-struct FwdIn { const float *uprev, *uhat_prev, *uhat, *LV; const int *cum; int nup; };
-__device__ __forceinline__ FwdIn fwd_in(const PArgs &P) { return FwdIn{P.uprev, P.uhat_prev, P.cm_uhat, P.cm_lv, P.cum, P.nup}; }
-
-// u along the crown path root -> path[len-1] (reference recursion :683-728, element e): returns u of the last node,
-// adds every u on the path to usum.  Crown nodes sit at row = node id of the chain-major arrays.
-__device__ __forceinline__ float path_u(const FwdIn &I, const int *path, int len, int e, float &usum, float &uh_last) {
+// u along the crown path root -> path[len-1] (reference recursion :683-728, element e) for a crown tile: returns u of
+// the last node, adds every u on the path to usum.  Crown nodes sit at row = node id of the chain-major arrays.
+__device__ __forceinline__ float path_u(const PArgs &P, const int *path, int len, int e, float &usum) {
+    const float *__restrict__ uhat = P.cm_uhat + e, *__restrict__ LV = P.cm_lv + e;
+    const int nup = P.nup;
+    const unsigned bm = P.branch_mask;
     float uh[kMaxCs], lv[kMaxCs];
 #pragma unroll
     for (int k = 0; k < kMaxCs; k++)
-        if (k < len) { uh[k] = __ldg(I.uhat + (size_t)path[k] * I.nup + e); lv[k] = __ldcg(I.LV + (size_t)path[k] * I.nup + e); }
-    float up = __ldg(I.uprev + e), uhp = __ldg(I.uhat_prev + e);
+        if (k < len) { uh[k] = __ldg(uhat + (size_t)path[k] * nup); lv[k] = __ldcg(LV + (size_t)path[k] * nup); }
+    const float *fix = smem_f(kOffFix);
+    float up = fix[e], uhp = fix[kVStride + e];
 #pragma unroll
     for (int k = 0; k < kMaxCs; k++)
         if (k < len) {
-            const float u = stage_branches(I.cum, k) ? (up + -1.f * uhp) + (uh[k] + lv[k]) : ((uh[k] + up) + -1.f * uhp) + lv[k];
+            const float u = (bm >> k & 1u) ? (up + -1.f * uhp) + (uh[k] + lv[k]) : ((uh[k] + up) + -1.f * uhp) + lv[k];
             usum += u;
             up = u; uhp = uh[k];
         }
-    uh_last = uhp;
     return up;
 }
 
-// u-scan of a chain: u = ((uhat + u_par) - uhat_par) + L v (:722-728); the chain's first stage is a branching stage of
-// the reference's loop when it has more nodes than its parent stage (:699-719).  X1 rows 0..nu-1 = u, column T = the
-// sum of u over the crown path (for x of the chain's parent)
+// u-scan of a chain: u = ((uhat + u_par) - uhat_par) + L v (:722-728), first along the crown path (its rows are staged
+// behind the chain's blocks), then down the chain; the chain's first stage is a branching stage of the reference's loop
+// when it has more nodes than its parent stage (:699-719).  X1 rows 0..nu-1 = u, column T = the sum of u over the crown
+// path (for x of the chain's parent)
 __device__ __noinline__ void chain_uscan(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, T = P.N - P.cs, nu = P.nu, nup = P.nup;
+    const int e = threadIdx.x, T = P.N - P.cs, nu = P.nu, nup = P.nup, cs = P.cs;
     if (e >= nu) return;
-    const FwdIn I = fwd_in(P);
-    const int cs = P.cs;
-    const float *su = S.stg, *sl = su + T * nup;
-    float usum = 0.f, uhp;
-    float up = path_u(I, S.anc, cs, e, usum, uhp);
-    const bool head_br = stage_branches(I.cum, cs);
-    // two halves of 12 columns: 12 live outputs instead of 24
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        float out[kTP / 2];
-#pragma unroll
-        for (int s2 = 0; s2 < kTP / 2; s2++) {
-            const int s = h * (kTP / 2) + s2;
-            float u = 0.f;
-            if (s < T) {
-                const float uh = su[s * nup + e], lv = sl[s * nup + e];
-                u = (s == 0 && head_br) ? (up + -1.f * uhp) + (uh + lv) : ((uh + up) + -1.f * uhp) + lv;
-                up = u; uhp = uh;
-            } else if (s == T) u = usum;
-            out[s2] = u;
-        }
-        float4 *d = reinterpret_cast<float4 *>(S.X1 + e * kTP + h * (kTP / 2));
-        d[0] = make_float4(out[0], out[1], out[2], out[3]); d[1] = make_float4(out[4], out[5], out[6], out[7]);
-        d[2] = make_float4(out[8], out[9], out[10], out[11]);
+    const unsigned bm = P.branch_mask;
+    const float *sue = S.stg + e, *sle = sue + T * nup;
+    const float *pu = S.stg + 2 * T * nup + T * P.nxp + e, *pl = pu + cs * nup;
+    const float *fix = smem_f(kOffFix);
+    float up = fix[e], uhp = fix[kVStride + e], usum = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < cs; k++) {
+        const float uh = pu[k * nup], lv = pl[k * nup];
+        const float u = (bm >> k & 1u) ? (up + -1.f * uhp) + (uh + lv) : ((uh + up) + -1.f * uhp) + lv;
+        usum += u;
+        up = u; uhp = uh;
     }
+    const bool head_br = (bm >> cs & 1u) != 0;
+    float *x1 = S.X1 + e * kTP;
+#pragma unroll 4
+    for (int s = 0; s < T; s++) {
+        const float uh = sue[s * nup], lv = sle[s * nup];
+        const float u = (s == 0 && head_br) ? (up + -1.f * uhp) + (uh + lv) : ((uh + up) + -1.f * uhp) + lv;
+        x1[s] = u;
+        up = u; uhp = uh;
+    }
+    if (T < kTP) x1[T] = usum;
+    for (int s = T + 1; s < kTP; s++) x1[s] = 0.f;
 }
 
 // x-scan: x = (x_par + e) + B u (:730-737).  Y = B [u | usum] on entry, Y rows = x on exit
 __device__ __noinline__ void chain_xscan(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, T = P.N - P.cs, nx = P.nx, nxp = P.nxp;
+    const int e = threadIdx.x, T = P.N - P.cs, nx = P.nx, nxp = P.nxp, cs = P.cs;
     if (e >= nx) return;
-    const float *__restrict__ eg = P.cm_e;
-    const int cs = P.cs;
-    const bool head_br = stage_branches(P.cum, cs);
-    const float *se = S.stg + 2 * T * P.nup;
-    float pe[kMaxCs];
-#pragma unroll
-    for (int k = 0; k < kMaxCs; k++) if (k < cs) pe[k] = __ldg(eg + (size_t)S.anc[k] * nxp + e);
-    float xrun = __ldg(P.xcur + e);
-#pragma unroll
-    for (int k = 0; k < kMaxCs; k++) if (k < cs) xrun += pe[k];
-    if (cs > 0) xrun += S.Y[e * kTP + T];   // (B usum)[e] sits in column T
-    // two halves of 12 columns: 12 live values instead of 24
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        float4 *yp = reinterpret_cast<float4 *>(S.Y + e * kTP + h * (kTP / 2));
-        const float4 q0 = yp[0], q1 = yp[1], q2 = yp[2];
-        float y[kTP / 2] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-#pragma unroll
-        for (int s2 = 0; s2 < kTP / 2; s2++) {
-            const int s = h * (kTP / 2) + s2;
-            if (s < T) {
-                const float ev = se[s * nxp + e];
-                const float x = (s == 0 && head_br) ? xrun + (ev + y[s2]) : (xrun + ev) + y[s2];
-                y[s2] = x; xrun = x;
-            }
-        }
-        yp[0] = make_float4(y[0], y[1], y[2], y[3]); yp[1] = make_float4(y[4], y[5], y[6], y[7]);
-        yp[2] = make_float4(y[8], y[9], y[10], y[11]);
+    const bool head_br = (P.branch_mask >> cs & 1u) != 0;
+    const float *see = S.stg + 2 * T * P.nup + e;
+    const float *pe = see + T * nxp + 2 * cs * P.nup;
+    float xrun = smem_f(kOffFix)[2 * kVStride + e];
+#pragma unroll 1
+    for (int k = 0; k < cs; k++) xrun += pe[k * nxp];
+    float *y = S.Y + e * kTP;
+    if (cs > 0) xrun += y[T];   // (B usum)[e] sits in column T
+#pragma unroll 4
+    for (int s = 0; s < T; s++) {
+        const float ev = see[s * nxp], ys = y[s];
+        const float x = (s == 0 && head_br) ? xrun + (ev + ys) : (xrun + ev) + ys;
+        y[s] = x; xrun = x;
     }
 }
 
 // Hx = sysF x, Hu = sysG u (:744-747), t = Hx + w/step, box projections (Utilities.cu:237-254) and the partial sums of
-// the two global distances (:792, :810) for every column.  x in Y rows, u in `urows` rows.  Two uniform passes (xi part,
-// psi part); item = (column, element), all threads, every load of a batch issued before its first use
+// the two global distances (:792, :810) for every column.  x in Y rows, u in `urows` rows.  Thread = element of the
+// stacked dual [state box | safety level | control box] (so the operand pointers are chosen once), two thread groups
+// split the columns, kB columns in flight per trip.
 __device__ __noinline__ void sweep_epilogue(const PArgs &P, int ncols, const float *urows, const float *wxi, const float *wpsi,
                                             double &s1, double &s2) {
     const SweepSmem S = sweep_smem(P);
     const int nx = P.nx, nu = P.nu, ny = 2 * nx + nu;
+    const int el = threadIdx.x & 255, g = threadIdx.x >> 8;
+    static_assert(2 * kDimMax <= 256 && kPC == 512, "one thread per dual element, two groups");
+    if (el >= ny) return;
+    const int type = el < nx ? 0 : (el < 2 * nx ? 1 : 2);
+    const int jx = el - type * nx;                         // index inside the block
+    const int bdim = type == 2 ? nu : nx, wdim = type == 2 ? nu : 2 * nx, wo = type == 2 ? jx : el;
+    const float *__restrict__ lo_p = (type == 0 ? P.sxmin : (type == 1 ? P.sxs : P.sumin)) + jx;
+    const float *__restrict__ hi_p = (type == 2 ? P.sumax : P.sxmax) + jx;
+    const float *__restrict__ w_p = (type == 2 ? wpsi : wxi) + wo;
+    float *__restrict__ pri = (type == 2 ? P.pri_psi : P.pri_xi) + wo, *__restrict__ dual = (type == 2 ? P.dual_psi : P.dual_xi) + wo;
+    const float *__restrict__ diag = P.diag + el;
+    const float *vrow = (type == 2 ? urows : S.Y) + jx * kTP;
     const float inv_step = P.inv_step;
-    const float *__restrict__ diag = P.diag, *__restrict__ sxmin = P.sxmin, *__restrict__ sxmax = P.sxmax,
-                *__restrict__ sxs = P.sxs, *__restrict__ sumin = P.sumin, *__restrict__ sumax = P.sumax;
-    float *__restrict__ pri_xi = P.pri_xi, *__restrict__ pri_psi = P.pri_psi, *__restrict__ dual_xi = P.dual_xi,
-          *__restrict__ dual_psi = P.dual_psi;
-    const float *xrows = S.Y;
     constexpr int kB = 6;
-    double l1 = 0, l2 = 0;
-    {   // xi part: element e < 2 nx of column c; e < nx: state box, else safety level
-        const int dim = 2 * nx, items = ncols * dim;
-        for (int base = threadIdx.x; base < items; base += kB * kPC) {
-            float dgv[kB], wv[kB], lo[kB], hi[kB], val[kB];
-            size_t off[kB];
+    double l = 0;
+#pragma unroll 1
+    for (int c0 = g; c0 < ncols; c0 += 2 * kB) {
+        float dgv[kB], wv[kB], lo[kB], hi[kB], val[kB];
+        int ni[kB];
 #pragma unroll
-            for (int b = 0; b < kB; b++) {
-                const int it = min(base + b * kPC, items - 1);
-                const int c = it / dim, e = it - c * dim, jx = e < nx ? e : e - nx;
-                const size_t i = (size_t)S.colid[c];
-                off[b] = i * dim + e;
-                dgv[b] = __ldg(diag + i * ny + e);
-                wv[b] = __ldcg(wxi + off[b]);
-                lo[b] = __ldg((e < nx ? sxmin : sxs) + i * nx + jx);
-                hi[b] = e < nx ? __ldg(sxmax + i * nx + jx) : __int_as_float(0x7F7F7F7F);
-                val[b] = xrows[jx * kTP + c];
-            }
+        for (int b = 0; b < kB; b++) {
+            const int c = min(c0 + 2 * b, ncols - 1);
+            const int i = S.colid[c];
+            ni[b] = i;
+            dgv[b] = __ldg(diag + (size_t)i * ny);
+            wv[b] = __ldcg(w_p + (size_t)i * wdim);
+            lo[b] = __ldg(lo_p + (size_t)i * bdim);
+            hi[b] = type == 1 ? __int_as_float(0x7F7F7F7F) : __ldg(hi_p + (size_t)i * bdim);
+            val[b] = vrow[c];
+        }
 #pragma unroll
-            for (int b = 0; b < kB; b++) {
-                const int it = base + b * kPC;
-                if (it < items) {
-                    const float h = dgv[b] * val[b];
-                    const float tt = h + inv_step * wv[b];
-                    const float z = clampf(tt, lo[b], hi[b]);
-                    pri_xi[off[b]] = h; dual_xi[off[b]] = z;
-                    const float df = tt + -1.f * z;
-                    const int e = it % dim;
-                    if (e < nx) l1 += (double)df * df; else l2 += (double)df * df;
-                }
+        for (int b = 0; b < kB; b++) {
+            if (c0 + 2 * b < ncols) {
+                const float h = dgv[b] * val[b];
+                const float tt = h + inv_step * wv[b];
+                const float z = clampf(tt, lo[b], hi[b]);
+                pri[(size_t)ni[b] * wdim] = h; dual[(size_t)ni[b] * wdim] = z;
+                const float df = tt + -1.f * z;
+                l += (double)df * df;
             }
         }
     }
-    {   // psi part
-        const int items = ncols * nu;
-        for (int base = threadIdx.x; base < items; base += kB * kPC) {
-            float dgv[kB], wv[kB], lo[kB], hi[kB], val[kB];
-            size_t off[kB];
-#pragma unroll
-            for (int b = 0; b < kB; b++) {
-                const int it = min(base + b * kPC, items - 1);
-                const int c = it / nu, e = it - c * nu;
-                const size_t i = (size_t)S.colid[c];
-                off[b] = i * nu + e;
-                dgv[b] = __ldg(diag + i * ny + 2 * nx + e);
-                wv[b] = __ldcg(wpsi + off[b]);
-                lo[b] = __ldg(sumin + off[b]);
-                hi[b] = __ldg(sumax + off[b]);
-                val[b] = urows[e * kTP + c];
-            }
-#pragma unroll
-            for (int b = 0; b < kB; b++) {
-                const int it = base + b * kPC;
-                if (it < items) {
-                    const float h = dgv[b] * val[b];
-                    pri_psi[off[b]] = h;
-                    dual_psi[off[b]] = clampf(h + inv_step * wv[b], lo[b], hi[b]);
-                }
-            }
-        }
-    }
-    s1 += l1; s2 += l2;
+    if (type == 0) s1 += l; else if (type == 1) s2 += l;
 }
 
 __device__ __noinline__ void chain_forward(const PArgs &P, int j, int next_chain, uint32_t mpar, StagePhase &ph, const float *wxi,
@@ -769,7 +707,7 @@ __device__ __noinline__ void chain_forward(const PArgs &P, int j, int next_chain
     cols_to_global(S.X1, S.colid, T, nu, nu, Ug);                                 // devVecU
     dstamp(P, 16);
     mbar_wait(&S.mfull[3], mpar);
-    tile_gemm<kEpiStore>(S.B, nx, nu, S.X1, S.Y, S.scr2, nullptr);                                   // B u   (:715, :736)
+    tile_gemm(S.B, nx, nu, S.X1, S.Y, S.scr2);                                   // B u   (:715, :736)
     dstamp(P, 17);
     chain_xscan(P, j);
     cbar();
@@ -898,7 +836,7 @@ __device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, u
     crown_sums(P, i0, ncols);
     dstamp(P, 11);
     mbar_wait(&S.mfull[0], mpar);
-    tile_gemm<kEpiStore>(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2, nullptr);                               // G [QS | q_bar]
+    tile_gemm(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2);                               // G [QS | q_bar]
     crown_sigma(P, ncols);
     cbar();
     dstamp(P, 12);
@@ -910,28 +848,25 @@ __device__ __noinline__ void crown_forward(const PArgs &P, int i0, int ncols, ui
                                            double &s1, double &s2) {
     const SweepSmem S = sweep_smem(P);
     const int t = threadIdx.x, g = t >> 7, e = t & 127, nx = P.nx, nu = P.nu, nxp = P.nxp;
-    const FwdIn I = fwd_in(P);
-    const int *__restrict__ stages = P.stages, *__restrict__ parent = P.parent;
-    const float *__restrict__ eg = P.cm_e, *__restrict__ xcur = P.xcur;
-    float *Ug = P.U, *Xg = P.X;
+    const int *__restrict__ stages = P.stages, *__restrict__ cpath = P.crown_path;
+    const float *__restrict__ eg = P.cm_e + e;
     float *xbase = S.xb;   // x_cur + sum_path e per column (kept in shared memory: 24 registers live across the GEMM call otherwise)
     if (t < kTP) { S.colnode[t] = t < ncols ? i0 + t : 0; S.colid[t] = S.colnode[t]; }
     cbar();
+#pragma unroll 1
     for (int col = g; col < kTP; col += 4) {
         float usum = 0.f, xb = 0.f, u = 0.f;
         if (col < ncols) {
             const int i = i0 + col, si = __ldg(stages + i);
             int path[kMaxCs];
-            int a = i;
 #pragma unroll
-            for (int k = kMaxCs - 1; k >= 0; k--)
-                if (k <= si) { path[k] = a; a = __ldg(parent + a); }
-            if (e < nu) { float uhl; u = path_u(I, path, si + 1, e, usum, uhl); }
+            for (int k = 0; k < kMaxCs; k++) path[k] = k <= si ? __ldg(cpath + (size_t)i * kMaxCs + k) : 0;
+            if (e < nu) u = path_u(P, path, si + 1, e, usum);
             if (e < nx) {
                 float pe[kMaxCs];
 #pragma unroll
-                for (int k = 0; k < kMaxCs; k++) if (k <= si) pe[k] = __ldg(eg + (size_t)path[k] * nxp + e);
-                xb = __ldg(xcur + e);
+                for (int k = 0; k < kMaxCs; k++) if (k <= si) pe[k] = __ldg(eg + (size_t)path[k] * nxp);
+                xb = smem_f(kOffFix)[2 * kVStride + e];
 #pragma unroll
                 for (int k = 0; k < kMaxCs; k++) if (k <= si) xb += pe[k];
             }
@@ -940,20 +875,18 @@ __device__ __noinline__ void crown_forward(const PArgs &P, int i0, int ncols, ui
         if (e < nx) xbase[e * kTP + col] = xb;
     }
     cbar();
-    cols_to_global(S.V, S.colid, ncols, nu, nu, Ug);                              // devVecU
+    cols_to_global(S.V, S.colid, ncols, nu, nu, P.U);                             // devVecU
     dstamp(P, 13);
     mbar_wait(&S.mfull[3], mpar);
-    tile_gemm<kEpiStore>(S.B, nx, nu, S.X1, S.Y, S.scr2, nullptr);                                   // B sum_path u
+    tile_gemm(S.B, nx, nu, S.X1, S.Y, S.scr2);                                   // B sum_path u
     if (t < nx) {
-        float y[kTP], xb[kTP];
-        row_load(S.Y + t * kTP, y);
-        row_load(xbase + t * kTP, xb);
-#pragma unroll
-        for (int s = 0; s < kTP; s++) y[s] = s < ncols ? xb[s] + y[s] : 0.f;
-        row_store(S.Y + t * kTP, y);
+        float *y = S.Y + t * kTP;
+        const float *xbr = xbase + t * kTP;
+#pragma unroll 4
+        for (int c = 0; c < kTP; c++) y[c] = c < ncols ? xbr[c] + y[c] : 0.f;
     }
     cbar();
-    cols_to_global(S.Y, S.colid, ncols, nx, nx, Xg);                              // devVecX
+    cols_to_global(S.Y, S.colid, ncols, nx, nx, P.X);                             // devVecX
     sweep_epilogue(P, ncols, S.V, wxi, wpsi, s1, s2);
     cbar();
     dstamp(P, 14);
@@ -1326,6 +1259,32 @@ struct KState {
     double s1, s2;
 };
 
+// infeasibility log entry of iteration it-1 from the per-CTA candidates (one warp; every load issued before the merge)
+__device__ __noinline__ void pinf_merge(const PArgs &P, int it) {
+    const int lane = threadIdx.x & 31, grid = (int)gridDim.x;
+    Cand x{-1.f, 0.f, 0x7fffffff}, p{-1.f, 0.f, 0x7fffffff};
+    for (int b0 = 0; b0 < grid; b0 += 128) {
+        float2 v[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int b = min(b0 + lane + 32 * k, grid - 1);
+            const float2 *o = reinterpret_cast<const float2 *>(P.pinf_part + 6 * (size_t)b);   // 24-byte records
+            v[k][0] = __ldcg(o); v[k][1] = __ldcg(o + 1); v[k][2] = __ldcg(o + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {   // a clamped duplicate merges to itself
+            cand_merge(x, Cand{v[k][0].x, v[k][0].y, __float_as_int(v[k][1].x)});
+            cand_merge(p, Cand{v[k][1].y, v[k][2].x, __float_as_int(v[k][2].y)});
+        }
+    }
+    x = cand_warp(x); p = cand_warp(p);
+    if (lane == 0) {
+        P.pinf[it - 1] = fmaxf(x.v, p.v);    // max(maxValueXi, maxValuePsi) (:1495)
+        float *o4 = P.pinf4 + 4 * (size_t)(it - 1);
+        o4[0] = x.a; o4[1] = x.v; o4[2] = p.a; o4[3] = p.v;   // for the cross-rank merge on the host
+    }
+}
+
 // first half of iteration `it`: global distances of the previous prox, phase S, infeasibility log of iteration it-1
 __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
     double *dsh = reinterpret_cast<double *>(smem_f(kOffDsh));      // 2 * 16 doubles
@@ -1389,20 +1348,9 @@ __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
     dstamp(P, 0);
     grid_sync(P.bar, K.bar_target);
     dstamp(P, 1);
-    if (it > 0 && blockIdx.x == 0 && warp == 0) {
-        Cand x{-1.f, 0.f, 0x7fffffff}, p{-1.f, 0.f, 0x7fffffff};
-        for (int b = lane; b < (int)gridDim.x; b += 32) {
-            const float *o = P.pinf_part + 6 * (size_t)b;
-            Cand cx{__ldcg(o), __ldcg(o + 1), __float_as_int(__ldcg(o + 2))}, cp{__ldcg(o + 3), __ldcg(o + 4), __float_as_int(__ldcg(o + 5))};
-            cand_merge(x, cx); cand_merge(p, cp);
-        }
-        x = cand_warp(x); p = cand_warp(p);
-        if (lane == 0) {
-            P.pinf[it - 1] = fmaxf(x.v, p.v);    // max(maxValueXi, maxValuePsi) (:1495)
-            float *o4 = P.pinf4 + 4 * (size_t)(it - 1);
-            o4[0] = x.a; o4[1] = x.v; o4[2] = p.a; o4[3] = p.v;   // for the cross-rank merge on the host
-        }
-    }
+    // merged by one warp of a CTA that has no chain to sweep (or the fewest): it is off the critical path there
+    const int pcta = P.K < (int)gridDim.x ? P.K : (int)gridDim.x - 1;
+    if (it > 0 && (int)blockIdx.x == pcta && warp == 0) pinf_merge(P, it);
 }
 
 // second half of iteration `it`: the sweeps (phases B, C, F), this CTA's share of the prox distances, closing barrier.
@@ -1421,17 +1369,28 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
     // ---- phase B: backward sweep of the chains (operand blocks by bulk TMA, one chain ahead)
     dstamp(P, 2);
     if (threadIdx.x == 0 && j0 < nK) issue_chain_backward_loads(P, j0);
+#pragma unroll 1
     for (int j = j0; j < nK; j += grid) chain_backward(P, j, j + grid < nK ? j + grid : -1, mpar, K.SP);
     dstamp(P, 10);
     // ---- phase C: backward sweep of the crown (tiles are dealt from the last CTA down: those have the fewest chains)
     if (P.n_crown > 0) {
         // the crown needs the heads of every chain: with several GPUs their q, r were stored into every rank's
-        // table (chain_qscan / chain_rscan), and this barrier spans the GPUs
-        if (P.n_ranks > 1) grid_sync_cross(P, K.bar_target, P.epoch0 + 2u * (unsigned)it + 1u, [] {});
-        else grid_sync(P.bar, K.bar_target);
-        dstamp(P, 20);
+        // table (chain_qscan / chain_rscan), and this barrier spans the GPUs.  On one GPU only the CTAs that own crown
+        // tiles wait, and only for the heads (a counter the chains bump after their r-scan): the crown overlaps the
+        // rest of the chains' backward sweep
         const CrownTiles C = crown_tiles(P);
         const int n_crown = P.n_crown;
+        if (P.n_ranks > 1) grid_sync_cross(P, K.bar_target, P.epoch0 + 2u * (unsigned)it + 1u, -1);
+        else if (grid - 1 - j0 < C.n_tiles) {
+            if (threadIdx.x == 0) {
+                const unsigned int want = (unsigned)nK * (unsigned)(it + 1);
+                while ((int)(ld_acquire_u32(P.heads_ctr) - want) < 0) {}
+                __threadfence();
+            }
+            cbar();
+        }
+        dstamp(P, 20);
+#pragma unroll 1
         for (int tl = grid - 1 - j0; tl < C.n_tiles; tl += grid)
             crown_backward(P, tl * C.tile_w, min(C.tile_w, n_crown - tl * C.tile_w), mpar, K.SP);
         dstamp(P, 21);
@@ -1455,10 +1414,12 @@ __device__ __noinline__ void iter_forward(const PArgs &P, KState &K, int it) {
         double c1 = 0, c2 = 0;
         const CrownTiles C = crown_tiles(P);
         const int n_crown = P.n_crown;
+#pragma unroll 1
         for (int tl = grid - 1 - j0; tl < C.n_tiles; tl += grid)
             crown_forward(P, tl * C.tile_w, min(C.tile_w, n_crown - tl * C.tile_w), mpar, wxi, wpsi, c1, c2);
         if (P.rank == 0) { K.s1 = c1; K.s2 = c2; }   // the crown is replicated: it counts once in the global distances
     }
+#pragma unroll 1
     for (int j = j0; j < nK; j += grid) chain_forward(P, j, j + grid < nK ? j + grid : -1, mpar, K.SP, wxi, wpsi, K.s1, K.s2);
     dstamp(P, 23);
 }
@@ -1479,14 +1440,7 @@ __device__ __noinline__ void iter_close(const PArgs &P, KState &K, int it) {
     }
     dstamp(P, 28);
     if (P.n_ranks > 1) {
-        grid_sync_cross(P, K.bar_target, P.epoch0 + 2u * (unsigned)it + 2u, [&] {
-            double t1 = 0, t2 = 0;   // this rank's share, CTA order
-            for (int k = 0; k < (int)gridDim.x; k++) { t1 += __ldcg(P.dist_part + 2 * k); t2 += __ldcg(P.dist_part + 2 * k + 1); }
-            for (int r = 0; r < P.n_ranks; r++) {
-                double *ds = P.dslot_peer[r] + 2 * (it & 1) + 4 * P.rank;
-                ds[0] = t1; ds[1] = t2;
-            }
-        });
+        grid_sync_cross(P, K.bar_target, P.epoch0 + 2u * (unsigned)it + 2u, it);
     } else grid_sync(P.bar, K.bar_target);
     dstamp(P, 29);
 }
@@ -1516,6 +1470,12 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
         unsigned long long *c = clk_smem();
         for (int k = 0; k < 32; k++) c[k] = 0;
         c[32] = globaltimer(); c[33] = blockIdx.x == P.clock_cta ? 1 : 0;
+        reinterpret_cast<int *>(smem_f(kOffMeta))[0] = -1;
+    }
+    {   // u_prev, uhat_prev, x_cur: read by every forward scan, fixed for the launch
+        float *fix = smem_f(kOffFix);
+        for (int k = tid; k < P.nu; k += kPC) { fix[k] = __ldg(P.uprev + k); fix[kVStride + k] = __ldg(P.uhat_prev + k); }
+        for (int k = tid; k < P.nx; k += kPC) fix[2 * kVStride + k] = __ldg(P.xcur + k);
     }
     __syncthreads();
 
@@ -1575,7 +1535,8 @@ static SweepLayout sweep_layout(const Handle *h) {
     Y.oV = Y.oY + std::max(std::max(nv, nu), nx) * kTP;
     Y.oScr2 = Y.oV + std::max(nv, nu) * kTP;
     Y.oStg = Y.oScr2 + 128 * kTP;
-    Y.oXb = Y.oStg + std::max(T * Y.nxp + 5 * T * Y.nvp, 2 * T * Y.nup + T * Y.nxp);
+    const int cs = h->chain_stage;
+    Y.oXb = Y.oStg + std::max(T * Y.nxp + 5 * T * Y.nvp, 2 * T * Y.nup + T * Y.nxp + cs * (2 * Y.nup + Y.nxp));
     Y.end = Y.oXb + nx * kTP;
     return Y;
 }
@@ -1656,7 +1617,7 @@ rn_status persistent_prepare(Handle *h) {
     RN_CHECK(dev_alloc(h, &h->cm_c, n * Y.nxp)); RN_CHECK(dev_alloc(h, &h->cm_lv, n * Y.nup));
     RN_CHECK(dev_alloc(h, &h->cm_beta, n * Y.nvp)); RN_CHECK(dev_alloc(h, &h->cm_uhat, n * Y.nup)); RN_CHECK(dev_alloc(h, &h->cm_e, n * Y.nxp));
     RN_CHECK(ensure_xchg(h));
-    RN_CHECK(dev_alloc(h, &h->grid_bar, 8));
+    RN_CHECK(dev_alloc(h, &h->grid_bar, 64));   // [0] grid barrier, [32] heads counter (its own 128-byte line)
     RN_CHECK(dev_alloc(h, &h->phase_ns, 32));
     // G | OmegaBar | L | B, each padded to 16 bytes: the four bulk copies of the sweeps
     RN_CHECK(dev_alloc(h, &h->sweep_pack, (size_t)Y.pack_floats));
@@ -1689,6 +1650,14 @@ rn_status persistent_prepare(Handle *h) {
             rng[((size_t)i * (kMaxCs + 1) + s) * 2] = a; rng[((size_t)i * (kMaxCs + 1) + s) * 2 + 1] = b;
         }
     }
+    // path root -> node of every crown node
+    std::vector<int> cpath((size_t)std::max(n_crown, 1) * kMaxCs, 0);
+    for (int i = 0; i < n_crown; i++) {
+        int a = i;
+        for (int k = h->h_stages[i]; k >= 0 && a >= 0; k--) { if (k < kMaxCs) cpath[(size_t)i * kMaxCs + k] = a; a = h->h_parent[a]; }
+    }
+    RN_CHECK(dev_alloc(h, &h->crown_path, cpath.size()));
+    RN_CUDA(h, cudaMemcpyAsync(h->crown_path, cpath.data(), cpath.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     RN_CHECK(dev_alloc(h, &h->crown_rng, rng.size()));
     RN_CUDA(h, cudaMemcpyAsync(h->crown_rng, rng.data(), rng.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     RN_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1710,7 +1679,10 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     const rn_dims &d = h->d;
     PArgs P{};
     P.parent = h->t.parent; P.child_first = h->t.child_first; P.child_count = h->t.child_count; P.omega_idx = h->t.omega_idx;
-    P.cum = h->cum_dev; P.stages = h->t.stages; P.crown_rng = h->crown_rng; P.pos = h->pos_dev;
+    P.cum = h->cum_dev; P.stages = h->t.stages; P.crown_rng = h->crown_rng; P.pos = h->pos_dev; P.crown_path = h->crown_path;
+    P.branch_mask = 0;
+    for (int st_ = 1; st_ < d.N && st_ < 32; st_++)
+        if (h->h_cum[st_ + 1] - h->h_cum[st_] > h->h_cum[st_] - h->h_cum[st_ - 1]) P.branch_mask |= 1u << st_;
     P.N = d.N; P.cs = h->chain_stage; P.K = d.K; P.nodes = d.nodes; P.n_crown = h->h_cum[h->chain_stage];
     P.n_mats = h->factor_mode == RN_FACTORS_FULL ? 4 : 2;
     P.df_mode = h->factor_mode == RN_FACTORS_DF ? 1 : 0;
@@ -1752,7 +1724,7 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     P.pinf4 = h->pinf4;
     P.cm_c = h->cm_c; P.cm_lv = h->cm_lv; P.cm_beta = h->cm_beta; P.cm_uhat = h->cm_uhat; P.cm_e = h->cm_e;
     P.dist_part = h->dist_part; P.pinf = h->pinf; P.pinf_part = h->pinf_part;
-    P.lambda_tab = h->lambda_tab; P.bar = h->grid_bar; P.iter_dev = h->iter_dev; P.phase_ns = h->phase_ns;
+    P.lambda_tab = h->lambda_tab; P.bar = h->grid_bar; P.heads_ctr = h->grid_bar + 32; P.iter_dev = h->iter_dev; P.phase_ns = h->phase_ns;
     P.step = h->step; P.inv_step = 1 / h->step; P.pen_x = h->pen_x; P.pen_xs = h->pen_xs;
     const SweepLayout Y = sweep_layout(h);
     P.oG = Y.oG; P.oOm = Y.oOm; P.oL = Y.oL; P.oX1 = Y.oX1; P.oY = Y.oY; P.oV = Y.oV; P.oScr2 = Y.oScr2; P.oStg = Y.oStg; P.oXb = Y.oXb;
@@ -1765,7 +1737,7 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     k_to_chain_major<<<d.nodes, 128, 0, st>>>(d.nodes, d.nu, Y.nup, h->pos_dev, h->uhat, h->cm_uhat);
     k_to_chain_major<<<d.nodes, 128, 0, st>>>(d.nodes, d.nx, Y.nxp, h->pos_dev, h->e, h->cm_e);
     h->launches += 3;
-    RN_CUDA(h, cudaMemsetAsync(h->grid_bar, 0, sizeof(unsigned int), st));
+    RN_CUDA(h, cudaMemsetAsync(h->grid_bar, 0, 64 * sizeof(unsigned int), st));
     RN_CUDA(h, cudaMemsetAsync(h->dist_part, 0, 2 * sizeof(double) * h->persist_grid, st));
     void *args[] = {&P};
     RN_CUDA(h, cudaLaunchCooperativeKernel((const void *)k_apg_persistent, dim3(h->persist_grid), dim3(kPT), args,
