@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librapidnet_b200.so")
+LIB_PATH = os.environ.get("RAPIDNET_B200_LIB") or os.path.join(_HERE, "librapidnet_b200.so")   # override: A/B builds
 
 FP = C.POINTER(C.c_float)
 IP = C.POINTER(C.c_int)

@@ -398,6 +398,31 @@ __device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float
     cbar();
 }
 
+// The same product for two columns c0, c1 only (a crown tile of one node: the 24-column GEMM would spend 3 us on 1-2
+// useful columns).  Thread = (row r = t & 127, quarter of k = t >> 7); the quarters are summed through scr2 in a fixed
+// order.  All kPC threads call; ends with a CTA barrier.
+__device__ __noinline__ void tile_gemv2(const float *M, int m, int K, const float *X, float *Y, float *scr2, int c0, int c1) {
+    const int t = threadIdx.x, r = t & 127, kq = t >> 7;
+    const int kn = (K + 3) >> 2, k0 = kq * kn, k1 = min(K, k0 + kn);
+    float a0 = 0.f, a1 = 0.f;
+    if (r < m) {
+        const float *mp = M + (size_t)k0 * m + r, *x0 = X + c0, *x1 = X + c1;
+#pragma unroll 4
+        for (int k = k0; k < k1; k++, mp += m) {
+            const float mv = *mp;
+            a0 = fmaf(mv, x0[k * kTP], a0);
+            a1 = fmaf(mv, x1[k * kTP], a1);
+        }
+    }
+    scr2[kq * 256 + r] = a0; scr2[kq * 256 + 128 + r] = a1;
+    cbar();
+    if (kq == 0 && r < m) {
+        Y[r * kTP + c0] = ((scr2[r] + scr2[256 + r]) + scr2[512 + r]) + scr2[768 + r];
+        Y[r * kTP + c1] = ((scr2[128 + r] + scr2[384 + r]) + scr2[640 + r]) + scr2[896 + r];
+    }
+    cbar();
+}
+
 // all threads: dst[row(col)*ld + e] = src[e][col] for col < ncols, e < dim (rows from `rows`: node ids or chain-major rows)
 __device__ __noinline__ void cols_to_global(const float *src, const int *rows, int ncols, int dim, int ld, float *__restrict__ dst) {
     const int e = threadIdx.x & 127;
@@ -445,8 +470,10 @@ __device__ __noinline__ void sweep_backward_finish(const PArgs &P, int ncols, bo
     const SweepSmem S = sweep_smem(P);
     const int nv = P.nv, nu = P.nu, nup = P.nup;
     float *LVg = P.cm_lv;
+    const bool one = !staged && ncols == 1;   // a crown tile of one node
     mbar_wait(&S.mfull[1], mpar);
-    tile_gemm(S.Om, nv, nv, S.X1 + P.nx * kTP, S.Y, S.scr2);   // OmegaBar (sigma + G q_bar) (-1/2 folded in)
+    if (one) tile_gemv2(S.Om, nv, nv, S.X1 + P.nx * kTP, S.Y, S.scr2, 0, 0);
+    else tile_gemm(S.Om, nv, nv, S.X1 + P.nx * kTP, S.Y, S.scr2);   // OmegaBar (sigma + G q_bar) (-1/2 folded in)
     dstamp(P, 6);
     if (staged && !P.df_mode) { mbar_wait(&S.sfull[2], ph.v); ph.v ^= 1; }
     sweep_vcombine(P, S, ncols, staged);
@@ -455,7 +482,8 @@ __device__ __noinline__ void sweep_backward_finish(const PArgs &P, int ncols, bo
     if (next_chain >= 0 && threadIdx.x == 0) issue_chain_backward_loads(P, next_chain);
     dstamp(P, 7);
     mbar_wait(&S.mfull[2], mpar);
-    tile_gemm(S.L, nu, nv, S.V, S.Y, S.scr2);                  // L v   (:701, :727)
+    if (one) tile_gemv2(S.L, nu, nv, S.V, S.Y, S.scr2, 0, 0);
+    else tile_gemm(S.L, nu, nv, S.V, S.Y, S.scr2);             // L v   (:701, :727)
     dstamp(P, 8);
     cols_to_global(S.Y, S.colnode, ncols, nu, nup, LVg);
     cbar();
@@ -726,56 +754,68 @@ __device__ __noinline__ void chain_forward(const PArgs &P, int j, int next_chain
 //   QS_i    = sum_{crown j below i} q_bar_j = sum_{crown j below i} (s_j - s_i - 1) c_j + (cs - 1 - s_i) sum_{heads} q_h
 // (the descendants of a node are one contiguous id range per stage: children are contiguous, Utilities.cu:184-199).
 // X1 q-rows: columns 0..n-1 = QS_i, columns 12..12+n-1 = q_bar_i (one G GEMM gives both products); V rows = base_i
-__device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols) {
+// sums over the rows lo + g, lo + g + 4, ... < hi (g = thread group) of a[row][lda] and of b0[row][ldb] (three:
+// (b0 + b1) + b2, same rows), eight rows in flight per trip; rows are added in ascending order
+__device__ __noinline__ void range_sum(const float *__restrict__ a, int lda, bool ea, const float *__restrict__ b0, const float *__restrict__ b1,
+                                       const float *__restrict__ b2, int ldb, bool eb, bool three, int lo, int hi, float &sa, float &sb) {
+    const int g = threadIdx.x >> 7;
+    float accA = 0.f, accB = 0.f;
+#pragma unroll 1
+    for (int jn = lo + g; jn < hi; jn += 32) {
+        float av[8], bv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int r = jn + 4 * k;
+            const bool ok = r < hi;
+            const size_t rr = (size_t)(ok ? r : lo);
+            av[k] = (ea && ok) ? __ldcg(a + rr * lda) : 0.f;
+            float bb = 0.f;
+            if (eb && ok) {
+                bb = __ldcg(b0 + rr * ldb);
+                if (three) bb = (bb + __ldcg(b1 + rr * ldb)) + __ldcg(b2 + rr * ldb);
+            }
+            bv[k] = bb;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) { accA += av[k]; accB += bv[k]; }
+    }
+    sa = accA; sb = accB;
+}
+
+// `wait_heads`: single GPU -- the heads' q, r are awaited here (a counter the chains bump after their r-scan), after the
+// first column's sums over its crown descendants, so that the crown overlaps the chains' backward sweep
+__device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols, unsigned int wait_heads, uint32_t mpar) {
     const SweepSmem S = sweep_smem(P);
     const int t = threadIdx.x, g = t >> 7, e = t & 127, nx = P.nx, nv = P.nv, cs = P.cs, nxp = P.nxp, nvp = P.nvp;
-    const int *__restrict__ stages = P.stages, *__restrict__ crown_rng = P.crown_rng;
-    const float *__restrict__ cg = P.cm_c, *__restrict__ bg = P.cm_beta, *__restrict__ p0 = P.part[0], *__restrict__ p1 = P.part[1],
-                *__restrict__ qhg = P.qh_peer[P.rank], *__restrict__ rhg = P.rh_peer[P.rank];
     const bool ex = e < nx, ev = e < nv;
+#pragma unroll 1
     for (int col = 0; col < ncols; col++) {
-        const int i = i0 + col, si = __ldg(stages + i);
-        const int *rng = crown_rng + (size_t)i * (kMaxCs + 1) * 2;
+        const int i = i0 + col, si = __ldg(P.stages + i);
+        const int *rng = P.crown_rng + (size_t)i * (kMaxCs + 1) * 2;
         float qb = 0.f, qs = 0.f, bs = 0.f;
+#pragma unroll 1
         for (int s = si + 1; s < cs; s++) {
-            const int lo = __ldg(rng + 2 * s), hi = __ldg(rng + 2 * s + 1);
-            float cpart = 0.f, bpart = 0.f;
-            int jn = lo + g;
-            for (; jn + 28 < hi; jn += 32) {   // eight rows in flight
-                float c4[8], b4[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const size_t r = (size_t)(jn + 4 * k);
-                    c4[k] = ex ? __ldcg(cg + r * nxp + e) : 0.f;
-                    b4[k] = ev ? (__ldg(bg + r * nvp + e) + __ldcg(p0 + r * nvp + e)) + __ldcg(p1 + r * nvp + e) : 0.f;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; k++) { cpart += c4[k]; bpart += b4[k]; }
-            }
-            for (; jn < hi; jn += 4) {
-                if (ex) cpart += __ldcg(cg + (size_t)jn * nxp + e);
-                if (ev) bpart += (__ldg(bg + (size_t)jn * nvp + e) + __ldcg(p0 + (size_t)jn * nvp + e)) + __ldcg(p1 + (size_t)jn * nvp + e);
-            }
+            float cpart, bpart;
+            range_sum(P.cm_c + e, nxp, ex, P.cm_beta + e, P.part[0] + e, P.part[1] + e, nvp, ev, true, __ldg(rng + 2 * s), __ldg(rng + 2 * s + 1),
+                      cpart, bpart);
             qb += cpart; qs += (float)(s - si - 1) * cpart; bs += bpart;
         }
+        if (col == 0 && wait_heads) {
+            // while the chains are still scanning: run the GEMM once on whatever X1 holds (two k-steps, result overwritten
+            // later) -- it pulls tile_gemm's code into the instruction cache, which is cold at this point of every iteration
+            mbar_wait(&S.mfull[0], mpar);
+            if (ncols == 1) tile_gemv2(S.G, nv, 4, S.X1, S.Y, S.scr2, 0, 12);
+            else tile_gemm(S.G, nv, 2, S.X1, S.Y, S.scr2);
+            if (t == 0) {
+                while ((int)(ld_acquire_u32(P.heads_ctr) - wait_heads) < 0) {}
+                __threadfence();
+            }
+            cbar();
+        }
         {
-            const int lo = __ldg(rng + 2 * cs), hi = __ldg(rng + 2 * cs + 1);   // (global) chain indices of the heads below i
-            float hq = 0.f, hr = 0.f;
-            int h = lo + g;
-            for (; h + 28 < hi; h += 32) {
-                float q4[8], r4[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    q4[k] = ex ? __ldcg(qhg + (size_t)(h + 4 * k) * nx + e) : 0.f;
-                    r4[k] = ev ? __ldcg(rhg + (size_t)(h + 4 * k) * nv + e) : 0.f;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; k++) { hq += q4[k]; hr += r4[k]; }
-            }
-            for (; h < hi; h += 4) {
-                if (ex) hq += __ldcg(qhg + (size_t)h * nx + e);
-                if (ev) hr += __ldcg(rhg + (size_t)h * nv + e);
-            }
+            float hq, hr;   // (global) chain indices of the heads below i
+            range_sum(P.qh_peer[P.rank] + e, nx, ex, P.rh_peer[P.rank] + e, nullptr, nullptr, nv, ev, false, __ldg(rng + 2 * cs),
+                      __ldg(rng + 2 * cs + 1), hq, hr);
             qb += hq; qs += (float)(cs - 1 - si) * hq; bs += hr;
         }
         float *sc = S.scr2 + g * 3 * 128;
@@ -788,14 +828,15 @@ __device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols) {
                 S.X1[e * kTP + col] = ((s0[128 + e] + s0[512 + e]) + s0[896 + e]) + s0[1280 + e];                     // QS
             }
             if (ev)
-                S.V[e * kTP + col] = __ldg(bg + (size_t)i * nvp + e) +
+                S.V[e * kTP + col] = __ldg(P.cm_beta + (size_t)i * nvp + e) +
                                      (((s0[256 + e] + s0[640 + e]) + s0[1024 + e]) + s0[1408 + e]);                   // sigma - G QS
         }
         cbar();
     }
-    if (g == 0 && ex)   // unused columns: zeros
-        for (int col = 0; col < kTP; col++)
-            if ((col >= ncols && col < 12) || col >= 12 + ncols) S.X1[e * kTP + col] = 0.f;
+    if (g == 0 && ex) {   // unused columns: zeros
+        float *x1 = S.X1 + e * kTP;
+        for (int col = ncols; col < 12; col++) { x1[col] = 0.f; x1[12 + col] = 0.f; }
+    }
     cbar();
 }
 
@@ -805,26 +846,24 @@ __device__ __noinline__ void crown_sigma(const PArgs &P, int ncols) {
     const int e = threadIdx.x, nv = P.nv, nvp = P.nvp;
     if (e >= nv) return;
     const bool df = P.df_mode != 0;
-    const float *__restrict__ p0 = P.part[0], *__restrict__ p1 = P.part[1];
-    float y[kTP], b[kTP];
-    row_load(S.Y + e * kTP, y);
-    row_load(S.V + e * kTP, b);
-#pragma unroll
+    const float *__restrict__ p0 = P.part[0] + e, *__restrict__ p1 = P.part[1] + e;
+    const float *y = S.Y + e * kTP, *b = S.V + e * kTP;
+    float *x1 = S.X1 + (P.nx + e) * kTP;
+#pragma unroll 1
     for (int s = 0; s < 12; s++) {
         float out = 0.f;
         if (s < ncols) {
             const float sg = b[s] + y[s];
             if (df) {
-                const size_t idx = (size_t)S.colnode[s] * nvp + e;
+                const size_t idx = (size_t)S.colnode[s] * nvp;
                 out = -0.5f * (((sg + __ldcg(p0 + idx)) + __ldcg(p1 + idx)) + y[12 + s]);
             } else out = -0.5f * (sg + y[12 + s]);
         }
-        b[s] = out; b[12 + s] = 0.f;
+        x1[s] = out; x1[12 + s] = 0.f;
     }
-    row_store(S.X1 + (P.nx + e) * kTP, b);
 }
 
-__device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, uint32_t mpar, StagePhase &ph) {
+__device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, uint32_t mpar, StagePhase &ph, unsigned int wait_heads) {
     const SweepSmem S = sweep_smem(P);
     const int t = threadIdx.x;
     if (t < kTP) {
@@ -833,10 +872,11 @@ __device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, u
         S.colp[t] = t < ncols ? 1.f / __ldg(P.prob + __ldg(P.omega_idx + node)) : 1.f;
     }
     cbar();
-    crown_sums(P, i0, ncols);
+    crown_sums(P, i0, ncols, wait_heads, mpar);
     dstamp(P, 11);
     mbar_wait(&S.mfull[0], mpar);
-    tile_gemm(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2);                               // G [QS | q_bar]
+    if (ncols == 1) tile_gemv2(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2, 0, 12);
+    else tile_gemm(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2);                          // G [QS | q_bar]
     crown_sigma(P, ncols);
     cbar();
     dstamp(P, 12);
@@ -878,7 +918,8 @@ __device__ __noinline__ void crown_forward(const PArgs &P, int i0, int ncols, ui
     cols_to_global(S.V, S.colid, ncols, nu, nu, P.U);                             // devVecU
     dstamp(P, 13);
     mbar_wait(&S.mfull[3], mpar);
-    tile_gemm(S.B, nx, nu, S.X1, S.Y, S.scr2);                                   // B sum_path u
+    if (ncols == 1) tile_gemv2(S.B, nx, nu, S.X1, S.Y, S.scr2, 0, 0);
+    else tile_gemm(S.B, nx, nu, S.X1, S.Y, S.scr2);                              // B sum_path u
     if (t < nx) {
         float *y = S.Y + t * kTP;
         const float *xbr = xbase + t * kTP;
@@ -1381,18 +1422,13 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
         const CrownTiles C = crown_tiles(P);
         const int n_crown = P.n_crown;
         if (P.n_ranks > 1) grid_sync_cross(P, K.bar_target, P.epoch0 + 2u * (unsigned)it + 1u, -1);
-        else if (grid - 1 - j0 < C.n_tiles) {
-            if (threadIdx.x == 0) {
-                const unsigned int want = (unsigned)nK * (unsigned)(it + 1);
-                while ((int)(ld_acquire_u32(P.heads_ctr) - want) < 0) {}
-                __threadfence();
-            }
-            cbar();
-        }
+        unsigned int wait_heads = P.n_ranks > 1 ? 0u : (unsigned)nK * (unsigned)(it + 1);   // counter value once every head is in
         dstamp(P, 20);
 #pragma unroll 1
-        for (int tl = grid - 1 - j0; tl < C.n_tiles; tl += grid)
-            crown_backward(P, tl * C.tile_w, min(C.tile_w, n_crown - tl * C.tile_w), mpar, K.SP);
+        for (int tl = grid - 1 - j0; tl < C.n_tiles; tl += grid) {
+            crown_backward(P, tl * C.tile_w, min(C.tile_w, n_crown - tl * C.tile_w), mpar, K.SP, wait_heads);
+            wait_heads = 0u;   // awaited once
+        }
         dstamp(P, 21);
     }
     // G has done its work for this iteration: B takes its place (every step above ended with a CTA barrier)
