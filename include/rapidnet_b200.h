@@ -293,6 +293,9 @@ rn_status rn_profile_kernels(rn_handle *h, int iterations, float *ms_out);
 /* fine-grained phase clock of the last rn_profile_kernels run in persistent mode: 32 accumulators (ns per
  * iteration, CTA 0's %globaltimer); index meaning in DESIGN.md / rapidnet_b200/cabi.py PHASE_NAMES */
 rn_status rn_phase_times(rn_handle *h, double *ns_per_iteration /*[32]*/);
+/* Load balance of the factor stream in the last rn_profile_kernels run: out[2k] = ns per iteration CTA k spent in phase S,
+ * out[2k+1] = the SM it ran on.  n_ctas = size of the persistent grid. */
+rn_status rn_cta_times(rn_handle *h, double *out /*[2*cap_ctas]*/, int cap_ctas, int *n_ctas);
 
 #ifdef __cplusplus
 }

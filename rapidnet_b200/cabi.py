@@ -39,7 +39,7 @@ EXPORTS = [
     "rn_create", "rn_destroy", "rn_last_error", "rn_set_stream", "rn_get_stream", "rn_sync", "rn_set_modes",
     "rn_get_info", "rn_set_null_space", "rn_factor_step", "rn_update_state", "rn_eliminate_coupling",
     "rn_set_uncertainty", "rn_apg_init", "rn_step", "rn_apg_solve", "rn_control_action", "rn_move_forward",
-    "rn_buffer", "rn_read_buffer", "rn_write_buffer", "rn_profile_stream", "rn_profile_kernels", "rn_phase_times",
+    "rn_buffer", "rn_read_buffer", "rn_write_buffer", "rn_profile_stream", "rn_profile_kernels", "rn_phase_times", "rn_cta_times",
     "rn_dist_prepare", "rn_dist_connect", "rn_dist_fix_crown_beta", "rn_read_pinf_parts", "rn_dist_error",
 ]
 
@@ -113,6 +113,7 @@ def load():
     lib.rn_profile_stream.argtypes = [H, C.c_int, FP]
     lib.rn_profile_kernels.argtypes = [H, C.c_int, FP]
     lib.rn_phase_times.argtypes = [H, C.POINTER(C.c_double)]
+    lib.rn_cta_times.argtypes = [H, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
     lib.rn_dist_prepare.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, IP, IP, C.c_char_p]
     lib.rn_dist_connect.argtypes = [H, C.c_char_p]
     lib.rn_dist_fix_crown_beta.argtypes = [H, C.c_int, C.c_int, FP]
@@ -316,6 +317,12 @@ class Solver:
                    20: "C.barrier_in", 21: "C.idle", 22: "C.barrier_out", 23: "F.idle", 24: "cyc.gemv_wait_full",
                    25: "cyc.gemv_wait_w", 26: "cyc.gemv_wait_red", 27: "cyc.gemv_compute", 28: "F.dist", 29: "F.barrier",
                    30: "cyc.ew_wait_red", 31: "cyc.ew_prologue"}
+
+    def cta_times(self):
+        """(ns per iteration in phase S, SM id) of every CTA of the persistent grid in the last profile_kernels run"""
+        out, n = (C.c_double * 2048)(), C.c_int(0)
+        self._check(load().rn_cta_times(self.h, out, 1024, C.byref(n)), "rn_cta_times")
+        return [(out[2 * k], int(out[2 * k + 1])) for k in range(n.value)]
 
     def phase_times(self) -> dict:
         """ns per iteration of each phase of the persistent kernel in the last profile_kernels run (CTA 0's clock)"""

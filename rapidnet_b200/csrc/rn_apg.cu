@@ -839,6 +839,8 @@ rn_status profile_kernels(Handle *h, int iterations, float *ms_out) {
         RN_CUDA(h, cudaEventRecord(e1, h->stream));
         unsigned long long pn[32];
         RN_CUDA(h, cudaMemcpyAsync(pn, h->phase_ns, sizeof(pn), cudaMemcpyDeviceToHost, h->stream));
+        h->last_cta_ns.assign(2 * (size_t)h->persist_grid, 0ull);
+        RN_CUDA(h, cudaMemcpyAsync(h->last_cta_ns.data(), h->cta_ns, h->last_cta_ns.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
         RN_CUDA(h, cudaStreamSynchronize(h->stream));
         float total = 0.f;
         RN_CUDA(h, cudaEventElapsedTime(&total, e0, e1));
@@ -884,6 +886,7 @@ rn_status profile_kernels(Handle *h, int iterations, float *ms_out) {
 static rn_status enqueue_persistent(Handle *h, int iterations) {
     RN_CHECK(persistent_prepare(h));
     RN_CUDA(h, cudaMemsetAsync(h->phase_ns, 0, 32 * sizeof(unsigned long long), h->stream));
+    RN_CUDA(h, cudaMemsetAsync(h->cta_ns, 0, 2 * 1024 * sizeof(unsigned long long), h->stream));
     if (iterations > 0) {
         RN_CHECK(persistent_launch(h, h->stream, iterations));
         const int last = (iterations - 1) & 1;

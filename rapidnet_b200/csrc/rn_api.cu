@@ -565,4 +565,16 @@ rn_status rn_phase_times(rn_handle *hh, double *out) {
     return RN_OK;
 }
 
+rn_status rn_cta_times(rn_handle *hh, double *out, int cap_ctas, int *n_ctas) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !out || !n_ctas) return RN_ERR_INVALID;
+    const int n = (int)(h->last_cta_ns.size() / 2);
+    *n_ctas = n;
+    for (int k = 0; k < n && k < cap_ctas; k++) {
+        out[2 * k] = h->last_phase_iters > 0 ? (double)h->last_cta_ns[2 * k] / h->last_phase_iters : 0.0;
+        out[2 * k + 1] = (double)h->last_cta_ns[2 * k + 1];
+    }
+    return RN_OK;
+}
+
 }  // extern "C"

@@ -110,7 +110,8 @@ struct Handle {
     float *cm_c = nullptr, *cm_lv = nullptr, *cm_beta = nullptr, *cm_uhat = nullptr, *cm_e = nullptr;   // chain-major arrays
     int *crown_rng = nullptr, *pos_dev = nullptr, *crown_path = nullptr;
     unsigned int *grid_bar = nullptr;
-    unsigned long long *phase_ns = nullptr;
+    unsigned long long *phase_ns = nullptr, *cta_ns = nullptr;
+    std::vector<unsigned long long> last_cta_ns;
     bool persist_ready = false;
     unsigned long long last_phase_ns[32] = {0};
     int last_phase_iters = 0;

@@ -87,6 +87,7 @@ struct PArgs {
     unsigned int *heads_ctr;                    // chains whose head q, r are published (single GPU: the crown waits on it instead of a grid barrier)
     int *iter_dev;
     unsigned long long *phase_ns;               // [32] fine-grained phase clock of one CTA (see cabi.PHASE_NAMES)
+    unsigned long long *cta_ns;                 // [grid][2] per CTA: time spent in phase S (ns, summed over iterations), SM id
     float step, inv_step, pen_x, pen_xs;
     // sweep shared-memory layout (float offsets from the dynamic shared-memory base) and the pack's pieces
     int oG, oOm, oL, oX1, oY, oV, oScr2, oStg, oXb;
@@ -137,10 +138,15 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
 
 // grid barrier over all CTAs (the grid is co-resident: cooperative launch).  Same protocol as
 // cooperative_groups::grid_group::sync: CTA barrier, one thread fences + arrives + spins + fences, CTA barrier.
-__device__ __noinline__ void grid_sync(unsigned int *ctr, unsigned int &target) {
+// Every grid barrier of the launch has a fixed ordinal (iteration x barriers per iteration + position), so its arrival
+// count is known without per-thread state and any thread can be the one that arrives and polls.
+__device__ __forceinline__ unsigned int bar_count(const PArgs &P, int it, int pos) {
+    const int per_it = (P.n_crown > 0 ? 3 : 2) + (P.n_ranks > 1 && P.n_crown > 0 ? 1 : 0);
+    return (unsigned)(it * per_it + pos + 1) * gridDim.x;
+}
+__device__ __noinline__ void grid_sync(unsigned int *ctr, unsigned int target) {
     cbar();
     if (threadIdx.x == 0) {
-        target += gridDim.x;
         __threadfence();
         atomicAdd(ctr, 1u);
         while (ld_acquire_u32(ctr) < target) {}
@@ -176,10 +182,9 @@ __device__ __forceinline__ void wait_sys(const unsigned int *p, unsigned int wan
 // peer's signal, then releases the local CTAs.  Peer data written by any thread of this GPU before the barrier is
 // ordered before the signal by the CTA barriers + the system-scope fence (cumulativity), like cooperative_groups'
 // grid sync does at device scope.
-__device__ __noinline__ void grid_sync_cross(const PArgs &P, unsigned int &target, unsigned int ep, int publish_it) {
+__device__ __noinline__ void grid_sync_cross(const PArgs &P, unsigned int target, unsigned int ep, int publish_it) {
     cbar();
     if (threadIdx.x == 0) {
-        target += gridDim.x;
         __threadfence_system();
         atomicAdd(P.bar, 1u);
         if (blockIdx.x == 0) {
@@ -960,11 +965,14 @@ __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
 
 // ---- loader warp: matrices through the TMA ring, dual vectors through the cp.async vector ring -----------------
 struct LoaderState { int st; uint32_t ph; int vs; uint32_t vph; int skip; };
-__device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderState &L, int it) {
+// prefetch != 0: only the first ring-full of chunks of iteration `it` is issued (no vectors) and counted in L.skip --
+// called after the CTA's forward sweep, before the closing grid barrier: the factor matrices are constants, so the ring
+// fills while the barrier and the next iteration's prologue are pending
+__device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderState &L, int it, int prefetch) {
     const Pipe M = pipe_smem();
     const int nx = P.nx, nu = P.nu, nv = P.nv, ny = 2 * nx + nu, lane = threadIdx.x & 31;
     int st = L.st, vs = L.vs; uint32_t ph = L.ph, vph = L.vph;
-    const int skip = 0;
+    const int skip = prefetch ? 0 : L.skip;
     fence_proxy_async();   // the ring region was last written through the generic proxy by the sweeps
     long long cyc_empty = 0, cyc_vec = 0, cyc_go = 0;
     const bool pair_ok = (nu & 1) == 0;   // 8-byte copies: every vector starts on an 8-byte boundary when nu is even
@@ -1036,6 +1044,11 @@ __device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderS
         }
         return issued;
     };
+    if (prefetch) {
+        L.skip = stream_chunks(it, 0, n_stages, false);
+        L.st = st; L.ph = ph;
+        return;
+    }
     const long long cg_ = clock64();
     if (node_first <= node_last) load_vec(node_first, it);
     if (node_first + 1 <= node_last) load_vec(node_first + 1, it);
@@ -1292,7 +1305,6 @@ __device__ __noinline__ void ew_role(const PArgs &P, const Slice &R, EwState &E,
 // inlined into the kernel, ptxas ran out of registers and scheduled every inner loop as load -> use pairs.)
 struct KState {
     Slice R;
-    unsigned int bar_target;
     StagePhase SP;
     GemvState GS;
     EwState ES;
@@ -1332,6 +1344,7 @@ __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
     Cand *csh = reinterpret_cast<Cand *>(smem_f(kOffCsh));          // 2 * 16 candidates
     float *sd = smem_f(kOffSd);                                     // d1, d2
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned long long t_in = tid == 0 ? globaltimer() : 0ull;
     // ---- global distances of the previous iteration's prox (cublasSnrm2, :792, :810); zeros at it == 0
     if (P.n_ranks > 1) {   // every rank published its share (crown counted by rank 0 only); same order everywhere
         if (tid == 0) {
@@ -1360,7 +1373,7 @@ __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
     if (warp < kGemvWarps) {
         gemv_dispatch(P, K.R, K.GS);
     } else if (warp == kLoaderWarp) {
-        loader_role(P, K.R, K.LS, it);
+        loader_role(P, K.R, K.LS, it, 0);
     } else {
         const float lam = __ldg(P.lambda_tab + it);
         const float d1 = sd[0], d2 = sd[1];
@@ -1385,9 +1398,12 @@ __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
     }
     // the stream ring is idle now: pull the shared sweep matrices over it while the grid barrier is pending
     cbar();
-    if (tid == 0) issue_matrix_loads(P);
+    if (tid == 0) {
+        issue_matrix_loads(P);
+        P.cta_ns[2 * blockIdx.x] += globaltimer() - t_in;   // load balance of phase S (rn_cta_times)
+    }
     dstamp(P, 0);
-    grid_sync(P.bar, K.bar_target);
+    grid_sync(P.bar, bar_count(P, it, 0));
     dstamp(P, 1);
     // merged by one warp of a CTA that has no chain to sweep (or the fewest): it is off the critical path there
     const int pcta = P.K < (int)gridDim.x ? P.K : (int)gridDim.x - 1;
@@ -1421,7 +1437,7 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
         // rest of the chains' backward sweep
         const CrownTiles C = crown_tiles(P);
         const int n_crown = P.n_crown;
-        if (P.n_ranks > 1) grid_sync_cross(P, K.bar_target, P.epoch0 + 2u * (unsigned)it + 1u, -1);
+        if (P.n_ranks > 1) grid_sync_cross(P, bar_count(P, it, 1), P.epoch0 + 2u * (unsigned)it + 1u, -1);
         unsigned int wait_heads = P.n_ranks > 1 ? 0u : (unsigned)nK * (unsigned)(it + 1);   // counter value once every head is in
         dstamp(P, 20);
 #pragma unroll 1
@@ -1434,7 +1450,7 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
     // G has done its work for this iteration: B takes its place (every step above ended with a CTA barrier)
     if (threadIdx.x == 0) issue_b_load(P);
     if (P.n_crown > 0) {
-        grid_sync(P.bar, K.bar_target);
+        grid_sync(P.bar, bar_count(P, it, P.n_ranks > 1 ? 2 : 1));
         dstamp(P, 22);
     }
 }
@@ -1474,10 +1490,26 @@ __device__ __noinline__ void iter_close(const PArgs &P, KState &K, int it) {
             P.dist_part[2 * blockIdx.x] = t1; P.dist_part[2 * blockIdx.x + 1] = t2;
         }
     }
+    const int last_pos = (P.n_crown > 0 ? 2 : 1) + (P.n_ranks > 1 && P.n_crown > 0 ? 1 : 0);
+    const unsigned int target = bar_count(P, it, last_pos);
     dstamp(P, 28);
     if (P.n_ranks > 1) {
-        grid_sync_cross(P, K.bar_target, P.epoch0 + 2u * (unsigned)it + 2u, it);
-    } else grid_sync(P.bar, K.bar_target);
+        // the sweep region is dead (every warp passed the barrier above): start refilling the stream ring for iteration it+1
+        if (warp == kLoaderWarp && it + 1 < P.iters) loader_role(P, K.R, K.LS, it + 1, 1);
+        grid_sync_cross(P, target, P.epoch0 + 2u * (unsigned)it + 2u, it);
+    } else {
+        // closing grid barrier, run by the loader warp: arrive first (the fence would otherwise also wait for the bulk
+        // copies), then refill the stream ring for iteration it+1 -- the sweep region is dead, the factor matrices are
+        // constants -- and only then poll
+        cbar();
+        if (warp == kLoaderWarp) {
+            if (lane == 0) { __threadfence(); atomicAdd(P.bar, 1u); }
+            __syncwarp();
+            if (it + 1 < P.iters) loader_role(P, K.R, K.LS, it + 1, 1);
+            if (lane == 0) while (ld_acquire_u32(P.bar) < target) {}   // acquire + the CTA barrier below order the other threads' reads
+        }
+        cbar();
+    }
     dstamp(P, 29);
 }
 
@@ -1522,7 +1554,6 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
     K.R.u_end = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
     K.R.node_first = K.R.u_begin < K.R.u_end ? K.R.u_begin / P.n_mats : 0;
     K.R.node_last = K.R.u_begin < K.R.u_end ? (K.R.u_end - 1) / P.n_mats : -1;
-    K.bar_target = 0;
     K.SP = StagePhase{0u, 0u, 0u, 0u};
     K.GS = GemvState{0, 0u, 0, 0u, 0, 0u};
     K.ES = EwState{0, 0u, 0, 0u, 0, 0u};
@@ -1547,6 +1578,7 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
         const unsigned long long *c = clk_smem();
         for (int k = 0; k < 32; k++) P.phase_ns[k] += c[k];
     }
+    if (tid == 0) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); P.cta_ns[2 * blockIdx.x + 1] = smid; }
     if (blockIdx.x == 0 && tid == 0) *P.iter_dev = P.iters - 1;   // k_finalize finishes iteration iters-1
 }
 
@@ -1655,6 +1687,7 @@ rn_status persistent_prepare(Handle *h) {
     RN_CHECK(ensure_xchg(h));
     RN_CHECK(dev_alloc(h, &h->grid_bar, 64));   // [0] grid barrier, [32] heads counter (its own 128-byte line)
     RN_CHECK(dev_alloc(h, &h->phase_ns, 32));
+    RN_CHECK(dev_alloc(h, &h->cta_ns, 2 * 1024));
     // G | OmegaBar | L | B, each padded to 16 bytes: the four bulk copies of the sweeps
     RN_CHECK(dev_alloc(h, &h->sweep_pack, (size_t)Y.pack_floats));
     const size_t f = sizeof(float);
@@ -1760,7 +1793,7 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     P.pinf4 = h->pinf4;
     P.cm_c = h->cm_c; P.cm_lv = h->cm_lv; P.cm_beta = h->cm_beta; P.cm_uhat = h->cm_uhat; P.cm_e = h->cm_e;
     P.dist_part = h->dist_part; P.pinf = h->pinf; P.pinf_part = h->pinf_part;
-    P.lambda_tab = h->lambda_tab; P.bar = h->grid_bar; P.heads_ctr = h->grid_bar + 32; P.iter_dev = h->iter_dev; P.phase_ns = h->phase_ns;
+    P.lambda_tab = h->lambda_tab; P.bar = h->grid_bar; P.heads_ctr = h->grid_bar + 32; P.iter_dev = h->iter_dev; P.phase_ns = h->phase_ns; P.cta_ns = h->cta_ns;
     P.step = h->step; P.inv_step = 1 / h->step; P.pen_x = h->pen_x; P.pen_xs = h->pen_xs;
     const SweepLayout Y = sweep_layout(h);
     P.oG = Y.oG; P.oOm = Y.oOm; P.oL = Y.oL; P.oX1 = Y.oX1; P.oY = Y.oY; P.oV = Y.oV; P.oScr2 = Y.oScr2; P.oStg = Y.oStg; P.oXb = Y.oXb;

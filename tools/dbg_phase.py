@@ -15,3 +15,11 @@ for n in (1, 2, 20):
     s.apg_solve(n); print("solve", n, time.time() - t0, flush=True)
 print(name, "profile", s.profile_kernels(100), flush=True)
 print("phases /iter", {k: round(v) for k, v in s.phase_times().items()})
+ct = s.cta_times()
+if ct:
+    import numpy as np
+    t = np.array([c[0] for c in ct]); sm = np.array([c[1] for c in ct])
+    order = np.argsort(t)
+    print("phase S per CTA: min %.0f median %.0f max %.0f ns" % (t.min(), np.median(t), t.max()))
+    print("slowest (cta, sm, ns):", [(int(k), int(sm[k]), int(t[k])) for k in order[-12:]])
+    print("fastest (cta, sm, ns):", [(int(k), int(sm[k]), int(t[k])) for k in order[:12]])
