@@ -403,6 +403,7 @@ __device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float
     cbar();
 }
 
+
 // The same product for two columns c0, c1 only (a crown tile of one node: the 24-column GEMM would spend 3 us on 1-2
 // useful columns).  Thread = (row r = t & 127, quarter of k = t >> 7); the quarters are summed through scr2 in a fixed
 // order.  All kPC threads call; ends with a CTA barrier.
@@ -1354,19 +1355,7 @@ __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
             sd[0] = (float)sqrt(t1); sd[1] = (float)sqrt(t2);
         }
         cbar();
-    } else {
-        double p1 = 0, p2 = 0;
-        for (int k = tid; k < (int)gridDim.x; k += kPC) { p1 += __ldcg(P.dist_part + 2 * k); p2 += __ldcg(P.dist_part + 2 * k + 1); }
-        for (int o = 16; o > 0; o >>= 1) { p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o); }
-        if (lane == 0) { dsh[warp] = p1; dsh[kPC / 32 + warp] = p2; }
-        cbar();
-        if (tid == 0) {
-            double t1 = 0, t2 = 0;
-            for (int w = 0; w < kPC / 32; w++) { t1 += dsh[w]; t2 += dsh[kPC / 32 + w]; }
-            sd[0] = (float)sqrt(t1); sd[1] = (float)sqrt(t2);
-        }
-        cbar();
-    }
+    }   // one GPU: the loader warp left them in sd[] when it closed the previous iteration's barrier (iter_close)
     Cand bx{-1.f, 0.f, 0x7fffffff}, bp{-1.f, 0.f, 0x7fffffff};
 
     // ---- phase S: three-role pipeline.  loader -> [ring] -> GEMV warps -> [red] -> element-wise warps -> [wbuf] -> GEMV
@@ -1396,14 +1385,21 @@ __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
             o[0] = x.a; o[1] = x.v; o[2] = __int_as_float(x.idx); o[3] = p.a; o[4] = p.v; o[5] = __int_as_float(p.idx);
         }
     }
-    // the stream ring is idle now: pull the shared sweep matrices over it while the grid barrier is pending
+    // Grid barrier that ends phase S.  The stream ring is idle now: the shared sweep matrices are pulled over it while the
+    // barrier is pending -- after the arrive, because its fence would otherwise also wait for those bulk copies.
     cbar();
     if (tid == 0) {
-        issue_matrix_loads(P);
         P.cta_ns[2 * blockIdx.x] += globaltimer() - t_in;   // load balance of phase S (rn_cta_times)
+        __threadfence();
+        atomicAdd(P.bar, 1u);
+        issue_matrix_loads(P);
     }
     dstamp(P, 0);
-    grid_sync(P.bar, bar_count(P, it, 0));
+    if (tid == 0) {
+        const unsigned int target = bar_count(P, it, 0);
+        while (ld_acquire_u32(P.bar) < target) {}   // acquire + the CTA barrier below order the other threads' reads
+    }
+    cbar();
     dstamp(P, 1);
     // merged by one warp of a CTA that has no chain to sweep (or the fewest): it is off the critical path there
     const int pcta = P.K < (int)gridDim.x ? P.K : (int)gridDim.x - 1;
@@ -1447,12 +1443,20 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
         }
         dstamp(P, 21);
     }
-    // G has done its work for this iteration: B takes its place (every step above ended with a CTA barrier)
-    if (threadIdx.x == 0) issue_b_load(P);
+    // G has done its work for this iteration: B takes its place (every step above ended with a CTA barrier).  With a
+    // crown: grid barrier before phase F (the chains need the crown's L v), B's bulk copy between arrive and poll
     if (P.n_crown > 0) {
-        grid_sync(P.bar, bar_count(P, it, P.n_ranks > 1 ? 2 : 1));
+        cbar();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(P.bar, 1u);
+            issue_b_load(P);
+            const unsigned int target = bar_count(P, it, P.n_ranks > 1 ? 2 : 1);
+            while (ld_acquire_u32(P.bar) < target) {}
+        }
+        cbar();
         dstamp(P, 22);
-    }
+    } else if (threadIdx.x == 0) issue_b_load(P);
 }
 
 // ---- phase F: forward sweep + prox boxes; leaves this CTA's sums of squared distances in K.s1, K.s2
@@ -1507,6 +1511,13 @@ __device__ __noinline__ void iter_close(const PArgs &P, KState &K, int it) {
             __syncwarp();
             if (it + 1 < P.iters) loader_role(P, K.R, K.LS, it + 1, 1);
             if (lane == 0) while (ld_acquire_u32(P.bar) < target) {}   // acquire + the CTA barrier below order the other threads' reads
+            __syncwarp();
+            // the global distances of this iteration's prox (cublasSnrm2, :792, :810) for the next iteration's element-wise
+            // pass: every CTA adds the per-CTA partial sums in the same fixed order
+            double p1 = 0, p2 = 0;
+            for (int k = lane; k < (int)gridDim.x; k += 32) { p1 += __ldcg(P.dist_part + 2 * k); p2 += __ldcg(P.dist_part + 2 * k + 1); }
+            for (int o = 16; o > 0; o >>= 1) { p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o); }
+            if (lane == 0) { float *sd = smem_f(kOffSd); sd[0] = (float)sqrt(p1); sd[1] = (float)sqrt(p2); }
         }
         cbar();
     }
@@ -1539,6 +1550,7 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
         for (int k = 0; k < 32; k++) c[k] = 0;
         c[32] = globaltimer(); c[33] = blockIdx.x == P.clock_cta ? 1 : 0;
         reinterpret_cast<int *>(smem_f(kOffMeta))[0] = -1;
+        smem_f(kOffSd)[0] = 0.f; smem_f(kOffSd)[1] = 0.f;   // no prox before iteration 0
     }
     {   // u_prev, uhat_prev, x_cur: read by every forward scan, fixed for the launch
         float *fix = smem_f(kOffFix);

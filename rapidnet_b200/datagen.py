@@ -28,6 +28,7 @@ TREES = {
     "C3": [10, 8, 6],     # K=480,  10171 nodes
     "C3b": [10, 8, 6, 4],  # K=1920, 38971 nodes
     "C5": [8, 8, 6],      # K=384,  8137 nodes (with the 4x network)
+    "C5s": [2, 2],        # K=4,    91 nodes (4x network, small tree: parity tests at the 4x dimensions)
 }
 
 
@@ -200,15 +201,15 @@ def scaled_problem(tree: Tree, scale: int = 4, seed: int = SEED0 + 5, sim_horizo
 
 
 def named_problem(name: str, max_iter: int = 500) -> Problem:
-    """C1, C1r6, C1r30, C2, C3, C3b (Barcelona-shaped) or C5 (4x synthetic) of BASELINE.md section 3."""
-    idx = {"C1": 1, "C1r6": 11, "C1r30": 12, "C2": 2, "C3": 3, "C3b": 4, "C5": 5}[name]
+    """C1, C1r6, C1r30, C2, C3, C3b (Barcelona-shaped) or C5 / C5s (4x synthetic) of BASELINE.md section 3."""
+    idx = {"C1": 1, "C1r6": 11, "C1r30": 12, "C2": 2, "C3": 3, "C3b": 4, "C5": 5, "C5s": 15}[name]
     seed = SEED0 + idx
     if name == "C1r6":
         return barcelona_problem(real_tree("32"), seed=seed, max_iter=max_iter)
     if name == "C1r30":
         return barcelona_problem(real_tree("65"), seed=seed, max_iter=max_iter)
-    if name == "C5":
-        tree = make_tree(TREES["C5"], 24, 88 * 4, 114 * 4, seed)
+    if name in ("C5", "C5s"):
+        tree = make_tree(TREES[name], 24, 88 * 4, 114 * 4, seed)
         return scaled_problem(tree, 4, seed=seed, max_iter=max_iter)
     tree = make_tree(TREES[name], 24, 88, 114, seed)
     return barcelona_problem(tree, seed=seed, max_iter=max_iter)

@@ -112,6 +112,24 @@ def test_barcelona_iterates_match_oracle(name, sweep):
     s.close(); o.close(); o64.close()
 
 
+def test_scaled_network_matches_oracle():
+    """BASELINE config[4] dimensions (4x Barcelona: nx 252, nu 456, nv 388) on a small tree.  nv exceeds the persistent
+    kernel's 128-row tiles, so the library falls back to the stream kernel + per-stage sweeps: same iterates."""
+    prob = named_problem("C5s", max_iter=100)
+    s, o = _setup(prob, cabi.SWEEP_PERSISTENT, cabi.FACTORS_FULL)
+    for gname, oname in (("MAT_PHI", "Phi"), ("MAT_D", "D"), ("MAT_F", "F"), ("VEC_BETA", "beta")):
+        assert rel_err(s.read(gname), o.get(oname)) < 1e-5, gname
+    o64 = _setup64(prob, s)
+    for iters in (1, 10, 100):
+        u0, _ = s.apg_solve(iters)
+        o.apg(iters)
+        o64.apg(iters)
+        worst = _compare_state(s, o, f"C5s it={iters}", o64)
+        _check_u0(u0, o, o64, f"C5s it={iters}")
+        print(f"C5s it={iters}: worst rel err {worst:.2e}")
+    s.close(); o.close(); o64.close()
+
+
 def test_modes_agree_on_barcelona():
     """per-stage / chain sweeps and FULL / DF factor streams give the same iterates (fp32 rounding apart)."""
     prob = named_problem("C1r6")
