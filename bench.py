@@ -210,6 +210,38 @@ def bench_partition(args, rank, world, local, stream):
     return out
 
 
+def bench_closed_loop(args, rank, world, local, stream, barrier):
+    """A bounded sample of the 1024-instance x 24-step study: every rank factors once, then runs its instances' closed loops
+    (rn_control_action with host buffers + rn_move_forward).  Weak scaling: instances per rank fixed."""
+    import torch
+    from rapidnet_b200 import cabi, closed_loop
+    from rapidnet_b200.datagen import named_problem
+    prob = named_problem(args.closed_loop_workload, max_iter=args.iters)
+    s = cabi.Solver(prob, device=local)
+    s.set_stream(stream.cuda_stream)
+    s.factor_step()
+    total = args.closed_loop_instances * world
+    with torch.cuda.stream(stream):
+        closed_loop.run_instance(s, prob, closed_loop.make_instance(prob, 0, 1), args.iters)   # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        res = closed_loop.simulate(s, prob, total, args.closed_loop_steps, args.iters, rank=rank, world=world)
+        barrier()
+        sec = time.perf_counter() - t0
+    t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t[0])
+    solves = total * args.closed_loop_steps
+    finite = all(np.isfinite(u).all() and np.isfinite(x).all() for u, x in res.values())
+    s.close()
+    return {"workload": describe(args.closed_loop_workload, prob), "instances": total, "steps_per_instance": args.closed_loop_steps,
+            "iterations_per_solve": args.iters, "scaling": "weak", "solves_per_s": solves / sec, "ms_per_closed_loop_step": sec / max(1, len(res) * args.closed_loop_steps) * 1e3,
+            "apg_iterations_per_s": solves * args.iters / sec, "finite": bool(finite),
+            "note": "instances shard with no data-path collective; one factored handle per GPU is reused by all of its instances"}
+
+
 def describe(workload, prob):
     d = prob.dims
     return (f"{workload}: Barcelona-shaped DWN nx={d['nx']} nu={d['nu']} nd={d['nd']} nv={d['nv']} N={d['N']}, "
@@ -227,6 +259,10 @@ def main():
     ap.add_argument("--cpu-sample-iters", type=int, default=500)
     ap.add_argument("--cpu-reference", action="store_true", help="--impl reference: force the CPU oracle port")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the D, F-only formulation leg")
+    ap.add_argument("--closed-loop-instances", type=int, default=4, help="closed-loop Monte-Carlo leg: instances PER RANK (0 = skip)")
+    ap.add_argument("--closed-loop-steps", type=int, default=2, help="receding-horizon steps per instance in that leg")
+    ap.add_argument("--closed-loop-workload", default="C1r30", help="tree of that leg (SURVEY C4: the shipped K=30 tree)")
     ap.add_argument("--sweep", default="persistent", choices=["persistent", "chain", "per_stage"])
     ap.add_argument("--factors", default="full", choices=["full", "df"])
     ap.add_argument("--partition-workload", default="C3", help="N > 1: the tree that is cut across the GPUs ('' = skip)")
@@ -302,6 +338,36 @@ def main():
         ms_e2e = max(f0.elapsed_time(f1), wall_ms)
         clocks = sampler.stop() if rank == 0 else None
 
+    # the same solve with the D, F-only formulation (v = -1/2 Omega r, an exact identity of the factor step: half the
+    # streamed bytes).  Reported next to the headline, never instead of it; its roofline uses its own byte count.
+    alt = None
+    if world == 1 and args.factors == "full" and args.sweep == "persistent" and not args.no_alt:
+        s.set_modes(cabi.SWEEP_PERSISTENT, cabi.FACTORS_DF)
+        with torch.cuda.stream(stream):
+            s.apg_solve(iters, want_u0=False)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(args.steps):
+                s.apg_solve(iters, want_u0=False)
+            g1.record(stream)
+            barrier()
+            ms_df = g0.elapsed_time(g1)
+        prof_df = s.profile_kernels(min(iters, 100))
+        info_df = s.info()
+        peak_df, _ = measured_peaks()
+        ach = info_df.stream_bytes_per_iteration / (prof_df["stream"] * 1e-3) / 1e9 if prof_df["stream"] > 0 else 0.0
+        alt = {"formulation": "factors=df: only D, F streamed (v = -1/2 Omega r)", "value": args.steps * iters / (ms_df * 1e-3), "unit": UNIT,
+               "ms_per_solve": ms_df / args.steps,
+               "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_df, "unit": "GB/s", "frac": ach / peak_df,
+                            "algorithmic_bytes_per_launch": info_df.stream_bytes_per_iteration, "launch_ms": prof_df["stream"]}}
+        s.set_modes(cabi.SWEEP_PERSISTENT, cabi.FACTORS_FULL)
+
+    # closed-loop Monte-Carlo sample (BASELINE config[3]): instances sharded over the ranks, one factored handle per rank
+    loop = None
+    if args.closed_loop_instances > 0:
+        loop = bench_closed_loop(args, rank, world, local, stream, barrier)
+
     part = None
     if world > 1 and args.partition_workload:
         part = bench_partition(args, rank, world, local, stream)
@@ -362,6 +428,10 @@ def main():
         }
         if part is not None:
             line["tree_partition"] = part
+        if alt is not None:
+            line["alt_formulation"] = alt
+        if loop is not None:
+            line["closed_loop"] = loop
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = max(4, min(iters, args.cpu_sample_iters))

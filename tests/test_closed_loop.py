@@ -1,0 +1,57 @@
+"""Closed-loop Monte-Carlo driver (BASELINE config[3]): sharding and instance generation on the CPU, the loop itself on the
+GPU against the same calls made by hand."""
+import numpy as np
+import pytest
+
+from rapidnet_b200 import closed_loop
+from rapidnet_b200.datagen import named_problem
+
+
+def test_shards_tile_the_instances():
+    for instances, world in ((1024, 8), (10, 3), (5, 8), (0, 2)):
+        got = [i for r in range(world) for i in closed_loop.shard(instances, world, r)]
+        assert got == list(range(instances))
+        sizes = [len(closed_loop.shard(instances, world, r)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        closed_loop.shard(4, 2, 2)
+
+
+def test_instances_depend_on_their_index_only():
+    prob = named_problem("C1", max_iter=10)
+    a, b = closed_loop.make_instance(prob, 7, 3), closed_loop.make_instance(prob, 7, 3)
+    c = closed_loop.make_instance(prob, 8, 3)
+    assert np.array_equal(a.x0, b.x0) and all(np.array_equal(x, y) for x, y in zip(a.demand, b.demand))
+    assert not np.array_equal(a.x0, c.x0)
+    n = prob.network
+    assert np.all(a.x0 >= 0.3 * n.xmax - 1e-3) and np.all(a.x0 <= 0.9 * n.xmax + 1e-3)
+    assert len(a.demand) == 3 and a.demand[0].size == prob.forecast.N * n.nd and a.prices[0].size == prob.forecast.N * n.nu
+
+
+@pytest.mark.gpu
+def test_closed_loop_two_ranks_equal_one_rank():
+    """the instances of a 2-way sharded study are the instances of the unsharded one (same handle reuse, cold start at
+    every solve: SURVEY A.4-12), and every step is controlAction + moveForewardInTime"""
+    from rapidnet_b200 import cabi
+    prob = named_problem("C1", max_iter=30)
+    s = cabi.Solver(prob)
+    s.factor_step()
+    whole = closed_loop.simulate(s, prob, instances=3, steps=2, iterations=30)
+    parts = {}
+    for r in range(2):
+        parts.update(closed_loop.simulate(s, prob, instances=3, steps=2, iterations=30, rank=r, world=2))
+    assert sorted(parts) == [0, 1, 2]
+    for k in whole:
+        assert np.array_equal(whole[k][0], parts[k][0]) and np.array_equal(whole[k][1], parts[k][1])
+    # by hand for instance 1
+    inst = closed_loop.make_instance(prob, 1, 2)
+    c = prob.config
+    x, up, dp = inst.x0.copy(), c.prev_u.astype(np.float32), c.prev_demand.astype(np.float32)
+    for t in range(2):
+        s.control_action(x, up, dp, inst.demand[t], inst.prices[t], 30, clamp=True)
+        x, up = s.move_forward()
+        dp = inst.demand[t][: prob.network.nd]
+        assert np.array_equal(up, whole[1][0][t]) and np.array_equal(x, whole[1][1][t + 1])
+    B = prob.network.B.reshape(prob.network.nu, prob.network.nx).T.astype(np.float64)   # column-major nx x nu
+    assert np.allclose(whole[1][1][1], whole[1][1][0] + B @ whole[1][0][0], rtol=1e-5, atol=1e-2)
+    s.close()
