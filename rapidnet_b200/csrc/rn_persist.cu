@@ -1,30 +1,35 @@
 // rn_persist.cu -- the whole APG loop of SmpcController::algorithmApg as ONE persistent cooperative kernel.
 //
 // Reference hot loop: /root/reference/src/SmpcController.cu:1500-1525 (about 430 launches per iteration).
-// Here every iteration runs inside one resident grid (one CTA per SM, 16 warps) with four
-// software grid barriers per iteration ("persistent kernel"):
+// Here every iteration runs inside one resident grid (one CTA per SM, 16 warps) with three software grid barriers per
+// iteration (two for a tree without crown, four when the tree is cut across GPUs); DESIGN.md section 3.1:
 //
-//   phase S  factor stream.  Work unit = (node, matrix in {D, F, Phi, Psi}).  The loader warp keeps a 6-deep ring of
-//            16 KB stages full with 1-D bulk TMA copies (cp.async.bulk, SASS UBLKCP) of the node's packed Engine
-//            factor matrix and fetches the unit's dual vectors with cp.async into a 3-deep vector ring, one unit
-//            ahead.  The consumer prologue is the fused element-wise pass: finalisation of the PREVIOUS iteration's prox
+//   phase S  factor stream.  Work unit = (node, matrix in {D, F, Phi, Psi}).  The loader warp keeps a ring of
+//            whole-matrix stages full with 1-D bulk TMA copies (cp.async.bulk, SASS UBLKCP) of the node's packed Engine
+//            factor matrices and fetches the node's dual vectors with cp.async into a 3-deep vector ring, two nodes
+//            ahead.  The element-wise warps run the fused pass: finalisation of the PREVIOUS iteration's prox
 //            (distance branch), fixed-point residual, dual update y+ = w + step*res, infeasibility log, and the Nesterov
 //            extrapolation w = (1+l) y+ - l y of THIS iteration (:535-557, :792-864, :1480-1496) -- the duals are read
-//            once and written once per iteration.  Then partial products D xi_w, F psi_w, Phi xi_w, Psi psi_w.
-//   sweeps   (:593-747).  The shared matrices G = Bbar', [OmegaBar | ThetaBar], L and B (every Omega_i / Theta_i is
-//            OmegaBar / p_i, ThetaBar / p_i: Engine.cu:707-747) are pulled into shared memory once per iteration by
-//            four bulk TMA copies that overlay the (then idle) stream ring, so every sweep product is a GEMM
+//            once and written once per iteration.  The GEMV warps form D xi_w, F psi_w, Phi xi_w, Psi psi_w.
+//   sweeps   (:593-747).  The shared matrices G = Bbar', OmegaBar, L and B (every Omega_i is OmegaBar / p_i and
+//            Theta q = -1/2 Omega (G q): Engine.cu:707-747) are pulled into shared memory once per iteration by bulk TMA
+//            copies that overlay the (then idle) stream ring, so every sweep product is a GEMM
 //            [matrix in smem] x [24 columns in smem] across nodes.
 //     phase B  chains: below the last branching stage every scenario is an independent chain owned by one CTA; the
 //            stage recursion becomes scans (q = c + q_child; sigma = beta + r_child, r = sigma + D xi + F psi +
 //            G q_child) around GEMMs across the chain's stages -- no barrier per stage.
 //     phase C  crown (stages above the chains): the child->parent sums of solveSumChildren (Utilities.cu:168-201) are
 //            unrolled into sums over each node's descendants (contiguous id ranges per stage), so all crown nodes are
-//            independent and the crown costs ONE barrier instead of one per stage.
+//            independent; on one GPU they wait for a counter of published chain heads instead of a grid barrier.
 //     phase F  forward sweep (:675-747): u and x are path sums from the root; crown nodes and chains run in the same
 //            phase (a chain recomputes its parent's u, x from the crown's L v).  Epilogue: Hx = sysF x, Hu = sysG u,
 //            t = Hx + w/step, box projections (Utilities.cu:237-254) and the partial sums of the two global
 //            distances of proximalFunG (:792, :810).
+//
+// Two things shape the code: a 512-thread CTA caps ptxas at 128 registers, and when any function of the
+// kernel runs out, EVERY inner loop is scheduled as load -> use pairs -- hence the non-inlined iteration halves with
+// their state in local memory; and the sweeps are bound by instruction fetch (32 KB L1.5 instruction cache against
+// >200 KB of code per iteration) -- hence compact loops, calls instead of inlined helpers, and per-launch caches.
 //
 // The last iteration's finalisation is done by k_finalize (rn_apg.cu) after the kernel.
 #include <algorithm>
@@ -144,17 +149,6 @@ __device__ __forceinline__ unsigned int bar_count(const PArgs &P, int it, int po
     const int per_it = (P.n_crown > 0 ? 3 : 2) + (P.n_ranks > 1 && P.n_crown > 0 ? 1 : 0);
     return (unsigned)(it * per_it + pos + 1) * gridDim.x;
 }
-__device__ __noinline__ void grid_sync(unsigned int *ctr, unsigned int target) {
-    cbar();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        while (ld_acquire_u32(ctr) < target) {}
-        __threadfence();
-    }
-    cbar();
-}
-
 __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -311,18 +305,24 @@ __device__ __forceinline__ void issue_chain_backward_loads(const PArgs &P, int j
     }
 }
 // one thread: the forward operand blocks of chain j -> staging.  Layout: uhat | L v | e (T rows each), then the rows of
-// the chain's crown path (root first): uhat [cs][nup] | L v [cs][nup] | e [cs][nxp] -- the scans read shared memory only
-__device__ __noinline__ void issue_chain_forward_loads(const PArgs &P, int j) {
+// the chain's crown path (root first): uhat [cs][nup] | L v [cs][nup] | e [cs][nxp] -- the scans read shared memory only.
+// parts & 1: everything that does not depend on the crown of this iteration (the chain's own blocks, the path's uhat and
+// e rows) -- issued while the grid barrier before phase F is pending; parts & 2: the path's L v rows (written by the
+// crown tiles of other CTAs) and the arrive on the staging barrier.
+__device__ __noinline__ void issue_chain_forward_loads(const PArgs &P, int j, int parts) {
     const SweepSmem S = sweep_smem(P);
     const int T = P.N - P.cs, cs = P.cs, nup = P.nup, nxp = P.nxp;
     const size_t row0 = (size_t)P.n_crown + (size_t)j * T;
     const uint32_t bx = (uint32_t)(T * nxp * 4), bu = (uint32_t)(T * nup * 4);
-    float *d = S.stg;
+    float *d = S.stg, *dp = S.stg + 2 * T * nup + T * nxp;
     fence_proxy_async_all();
-    mbar_expect_tx(&S.sfull[3], 2 * bu + bx + (uint32_t)cs * (uint32_t)(2 * nup + nxp) * 4u);
-    bulk_g2s(d, P.cm_uhat + row0 * nup, bu, &S.sfull[3]); d += T * nup;
-    bulk_g2s(d, P.cm_lv + row0 * nup, bu, &S.sfull[3]); d += T * nup;
-    bulk_g2s(d, P.cm_e + row0 * nxp, bx, &S.sfull[3]); d += T * nxp;
+    if (parts & 1) {
+        mbar_expect_tx_only(&S.sfull[3], 2 * bu + bx + (uint32_t)cs * (uint32_t)(nup + nxp) * 4u);
+        bulk_g2s(d, P.cm_uhat + row0 * nup, bu, &S.sfull[3]); d += T * nup;
+        bulk_g2s(d, P.cm_lv + row0 * nup, bu, &S.sfull[3]); d += T * nup;
+        bulk_g2s(d, P.cm_e + row0 * nxp, bx, &S.sfull[3]);
+    }
+    if (parts & 2) mbar_expect_tx(&S.sfull[3], (uint32_t)cs * (uint32_t)nup * 4u);
     if (cs > 0) {
         const int *meta = reinterpret_cast<const int *>(smem_f(kOffMeta));
         const bool hit = meta[0] == j;
@@ -330,9 +330,11 @@ __device__ __noinline__ void issue_chain_forward_loads(const PArgs &P, int j) {
 #pragma unroll 1
         for (int k = cs - 1; k >= 0; k--) {
             if (hit) a = meta[1 + 2 * kTP + k];
-            bulk_g2s(d + k * nup, P.cm_uhat + (size_t)a * nup, (uint32_t)nup * 4u, &S.sfull[3]);
-            bulk_g2s(d + (cs + k) * nup, P.cm_lv + (size_t)a * nup, (uint32_t)nup * 4u, &S.sfull[3]);
-            bulk_g2s(d + 2 * cs * nup + k * nxp, P.cm_e + (size_t)a * nxp, (uint32_t)nxp * 4u, &S.sfull[3]);
+            if (parts & 1) {
+                bulk_g2s(dp + k * nup, P.cm_uhat + (size_t)a * nup, (uint32_t)nup * 4u, &S.sfull[3]);
+                bulk_g2s(dp + 2 * cs * nup + k * nxp, P.cm_e + (size_t)a * nxp, (uint32_t)nxp * 4u, &S.sfull[3]);
+            }
+            if (parts & 2) bulk_g2s(dp + (cs + k) * nup, P.cm_lv + (size_t)a * nup, (uint32_t)nup * 4u, &S.sfull[3]);
             if (!hit) a = __ldg(P.parent + a);
         }
     }
@@ -745,7 +747,7 @@ __device__ __noinline__ void chain_forward(const PArgs &P, int j, int next_chain
     dstamp(P, 17);
     chain_xscan(P, j);
     cbar();
-    if (next_chain >= 0 && threadIdx.x == 0) issue_chain_forward_loads(P, next_chain);
+    if (next_chain >= 0 && threadIdx.x == 0) issue_chain_forward_loads(P, next_chain, 3);
     cols_to_global(S.Y, S.colid, T, nx, nx, Xg);                                  // devVecX
     dstamp(P, 18);
     sweep_epilogue(P, T, S.X1, wxi, wpsi, s1, s2);
@@ -1451,6 +1453,7 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
             __threadfence();
             atomicAdd(P.bar, 1u);
             issue_b_load(P);
+            if (j0 < nK) issue_chain_forward_loads(P, j0, 1);   // the staging area is free: this CTA's sweeps are done
             const unsigned int target = bar_count(P, it, P.n_ranks > 1 ? 2 : 1);
             while (ld_acquire_u32(P.bar) < target) {}
         }
@@ -1464,7 +1467,7 @@ __device__ __noinline__ void iter_forward(const PArgs &P, KState &K, int it) {
     const uint32_t mpar = (uint32_t)(it & 1);
     const int grid = (int)gridDim.x, j0 = (int)blockIdx.x, nK = P.K;
     const float *wxi = P.Wxi[it & 1], *wpsi = P.Wpsi[it & 1];
-    if (threadIdx.x == 0 && j0 < nK) issue_chain_forward_loads(P, j0);
+    if (threadIdx.x == 0 && j0 < nK) issue_chain_forward_loads(P, j0, P.n_crown > 0 ? 2 : 3);   // (with a crown: the rest went out at the barrier)
     K.s1 = 0; K.s2 = 0;
     if (P.n_crown > 0) {
         double c1 = 0, c2 = 0;
