@@ -184,7 +184,7 @@ def bench_partition(args, rank, world, local, stream):
     prob = named_problem(args.partition_workload, max_iter=args.iters)
     ds = DistributedSolver(prob, rank, world, device=local)
     ds.solver.set_stream(stream.cuda_stream)
-    ds.solver.set_modes(cabi.SWEEP_PERSISTENT, cabi.FACTORS_FULL if args.factors == "full" else cabi.FACTORS_DF)
+    ds.solver.set_modes(cabi.SWEEP_PERSISTENT, {"full": cabi.FACTORS_FULL, "df": cabi.FACTORS_DF, "shared": cabi.FACTORS_SHARED}[args.factors])
     ds.setup(slot=0)
     iters, steps = args.iters, max(1, min(args.steps, 3))
     with torch.cuda.stream(stream):
@@ -259,12 +259,12 @@ def main():
     ap.add_argument("--cpu-sample-iters", type=int, default=500)
     ap.add_argument("--cpu-reference", action="store_true", help="--impl reference: force the CPU oracle port")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-alt", action="store_true", help="skip the D, F-only formulation leg")
+    ap.add_argument("--no-alt", action="store_true", help="skip the legs of the two reformulations (D, F only; shared factors)")
     ap.add_argument("--closed-loop-instances", type=int, default=4, help="closed-loop Monte-Carlo leg: instances PER RANK (0 = skip)")
     ap.add_argument("--closed-loop-steps", type=int, default=2, help="receding-horizon steps per instance in that leg")
     ap.add_argument("--closed-loop-workload", default="C1r30", help="tree of that leg (SURVEY C4: the shipped K=30 tree)")
     ap.add_argument("--sweep", default="persistent", choices=["persistent", "chain", "per_stage"])
-    ap.add_argument("--factors", default="full", choices=["full", "df"])
+    ap.add_argument("--factors", default="full", choices=["full", "df", "shared"])
     ap.add_argument("--partition-workload", default="C3", help="N > 1: the tree that is cut across the GPUs ('' = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -296,7 +296,7 @@ def main():
     stream = torch.cuda.Stream()
     s.set_stream(stream.cuda_stream)          # torch.cuda.Event sees the stream the kernels are launched on
     s.set_modes({"persistent": cabi.SWEEP_PERSISTENT, "chain": cabi.SWEEP_CHAIN, "per_stage": cabi.SWEEP_PER_STAGE}[args.sweep],
-                cabi.FACTORS_FULL if args.factors == "full" else cabi.FACTORS_DF)
+                {"full": cabi.FACTORS_FULL, "df": cabi.FACTORS_DF, "shared": cabi.FACTORS_SHARED}[args.factors])
     s.factor_step()
     s.update_state()
     s.eliminate_coupling(fc.demand[0], fc.prices[0])
@@ -338,29 +338,43 @@ def main():
         ms_e2e = max(f0.elapsed_time(f1), wall_ms)
         clocks = sampler.stop() if rank == 0 else None
 
-    # the same solve with the D, F-only formulation (v = -1/2 Omega r, an exact identity of the factor step: half the
-    # streamed bytes).  Reported next to the headline, never instead of it; its roofline uses its own byte count.
-    alt = None
+    # the same solve with the two exact reformulations of the factor step.  Reported next to the headline, never instead of
+    # it; each roofline uses the bytes its own formulation has to move:
+    #   df      only D, F streamed (v = -1/2 Omega r): half the matrix bytes
+    #   shared  no per-node matrix at all ("Tier B"): D xi = G (sysF' xi), F psi = L' (s_u o psi) from the shared matrices
+    alt, alt_shared = None, None
     if world == 1 and args.factors == "full" and args.sweep == "persistent" and not args.no_alt:
-        s.set_modes(cabi.SWEEP_PERSISTENT, cabi.FACTORS_DF)
-        with torch.cuda.stream(stream):
-            s.apg_solve(iters, want_u0=False)
-            barrier()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record(stream)
-            for _ in range(args.steps):
+        def alt_leg(mode, text):
+            s.set_modes(cabi.SWEEP_PERSISTENT, mode)
+            with torch.cuda.stream(stream):
                 s.apg_solve(iters, want_u0=False)
-            g1.record(stream)
-            barrier()
-            ms_df = g0.elapsed_time(g1)
-        prof_df = s.profile_kernels(min(iters, 100))
-        info_df = s.info()
-        peak_df, _ = measured_peaks()
-        ach = info_df.stream_bytes_per_iteration / (prof_df["stream"] * 1e-3) / 1e9 if prof_df["stream"] > 0 else 0.0
-        alt = {"formulation": "factors=df: only D, F streamed (v = -1/2 Omega r)", "value": args.steps * iters / (ms_df * 1e-3), "unit": UNIT,
-               "ms_per_solve": ms_df / args.steps,
-               "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_df, "unit": "GB/s", "frac": ach / peak_df,
-                            "algorithmic_bytes_per_launch": info_df.stream_bytes_per_iteration, "launch_ms": prof_df["stream"]}}
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
+                for _ in range(args.steps):
+                    s.apg_solve(iters, want_u0=False)
+                g1.record(stream)
+                barrier()
+                ms_alt = g0.elapsed_time(g1)
+            prof_alt = s.profile_kernels(min(iters, 100))
+            info_alt = s.info()
+            try:
+                ph_alt = {k: round(v) for k, v in s.phase_times().items()}
+            except Exception:
+                ph_alt = None
+            peak_alt, _ = measured_peaks()
+            ach = info_alt.stream_bytes_per_iteration / (prof_alt["stream"] * 1e-3) / 1e9 if prof_alt["stream"] > 0 else 0.0
+            it_ms = ms_alt / args.steps / iters
+            return {"formulation": text, "value": args.steps * iters / (ms_alt * 1e-3), "unit": UNIT, "ms_per_solve": ms_alt / args.steps,
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_alt, "unit": "GB/s", "frac": ach / peak_alt,
+                                 "algorithmic_bytes_per_launch": info_alt.stream_bytes_per_iteration, "launch_ms": prof_alt["stream"],
+                                 "iteration_ms_by_kernel": prof_alt, "phase_clock_ns_per_iteration": ph_alt,
+                                 "whole_iteration": {"bytes": info_alt.apg_bytes_per_iteration,
+                                                     "achieved": info_alt.apg_bytes_per_iteration / (it_ms * 1e-3) / 1e9,
+                                                     "frac": info_alt.apg_bytes_per_iteration / (it_ms * 1e-3) / 1e9 / peak_alt}}}
+        alt = alt_leg(cabi.FACTORS_DF, "factors=df: only D, F streamed (v = -1/2 Omega r)")
+        alt_shared = alt_leg(cabi.FACTORS_SHARED, "factors=shared (Tier B): no per-node matrix; D xi = G (sysF' xi), F psi = L' (s_u o psi) "
+                                                  "from the shared matrices in shared memory, v = -1/2 Omega r")
         s.set_modes(cabi.SWEEP_PERSISTENT, cabi.FACTORS_FULL)
 
     # closed-loop Monte-Carlo sample (BASELINE config[3]): instances sharded over the ranks, one factored handle per rank
@@ -430,6 +444,8 @@ def main():
             line["tree_partition"] = part
         if alt is not None:
             line["alt_formulation"] = alt
+        if alt_shared is not None:
+            line["alt_formulation_shared"] = alt_shared
         if loop is not None:
             line["closed_loop"] = loop
         if world == 1 and not args.no_cpu_baseline:

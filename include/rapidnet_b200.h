@@ -99,7 +99,12 @@ typedef enum rn_sweep_mode {
 /* Which per-node factor matrices the stream kernel reads (DESIGN.md "formulations"). */
 typedef enum rn_factor_mode {
     RN_FACTORS_FULL = 0,     /* Phi, Psi, D, F  (what solveStep reads; Tier-A bytes)            */
-    RN_FACTORS_DF = 1        /* D, F only; v = -1/2 Omega r (exact identity, half the bytes)    */
+    RN_FACTORS_DF = 1,       /* D, F only; v = -1/2 Omega r (exact identity, half the bytes)    */
+    RN_FACTORS_SHARED = 2    /* no per-node matrix is read ("Tier B"): D_i = G sysF_i',
+                                F_i = L' sysG_i' (Engine.cu:720-728) with sysF, sysG diagonal, so
+                                D xi = G (sysF' xi) and F psi = L' (s_u o psi) come from the two SHARED
+                                matrices held in shared memory; v = -1/2 Omega r as in RN_FACTORS_DF.
+                                Persistent sweep only; rounding differs from the streamed products  */
 } rn_factor_mode;
 
 /* Single APG sub-steps, for the golden-vector tests (TestSmpcController.cu:114-398 calls

@@ -21,7 +21,7 @@ STATUS_NAMES = {0: "RN_OK", 1: "RN_ERR_INVALID", 2: "RN_ERR_CUDA", 3: "RN_ERR_ST
                 5: "RN_ERR_NOMEM"}
 
 SWEEP_PER_STAGE, SWEEP_CHAIN, SWEEP_PERSISTENT = 0, 1, 2
-FACTORS_FULL, FACTORS_DF = 0, 1
+FACTORS_FULL, FACTORS_DF, FACTORS_SHARED = 0, 1, 2
 STEP_EXTRAPOLATE, STEP_SOLVE, STEP_PROX, STEP_RESIDUAL, STEP_DUAL_UPDATE = range(5)
 
 BUFFER_IDS = [

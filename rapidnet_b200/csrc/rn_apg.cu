@@ -647,8 +647,14 @@ void fill_lambda_table(std::vector<float> &tab, int iters) {
 
 double stream_bytes_per_iteration(const Handle *h) {
     const rn_dims &d = h->d;
-    const double per_node_mats = (double)d.nv * (2.0 * d.nx + d.nu) * (h->factor_mode == RN_FACTORS_FULL ? 2.0 : 1.0);
     const double ny = 2.0 * d.nx + d.nu;
+    if (h->factor_mode == RN_FACTORS_SHARED) {
+        // no per-node matrix: read Hx, w, z, y_{k-1} + write y_k, w + read the diagonals (ny) + write c, G c, L' g; the two
+        // shared matrices G, L' once per CTA from L2 (counted once)
+        const double vec = 6.0 * ny + ny + d.nx + 2.0 * d.nv;
+        return 4.0 * (d.nodes * vec + (double)d.nv * (d.nx + d.nu));
+    }
+    const double per_node_mats = (double)d.nv * (2.0 * d.nx + d.nu) * (h->factor_mode == RN_FACTORS_FULL ? 2.0 : 1.0);
     // matrices once + read y_k, y_{k-1} + write w + read diag(2nx) + write a,(b),c
     const double vec = 3.0 * ny + 2.0 * d.nx + d.nx + d.nv * (h->factor_mode == RN_FACTORS_FULL ? 2.0 : 1.0);
     return 4.0 * d.nodes * (per_node_mats + vec);
@@ -656,10 +662,11 @@ double stream_bytes_per_iteration(const Handle *h) {
 
 double apg_bytes_per_iteration(const Handle *h) {
     // SURVEY 8(d) "Tier A": bytes_iter = 4 [ nodes (nv(4nx+2nu) + (2nx+nu) + V) + fb (nv^2 + nv nx) + nv nx + nu nv + nx nu ]
+    // "Tier B" (RN_FACTORS_SHARED): the per-node matrix term vanishes (vectors + diagonals + the shared matrices)
     const rn_dims &d = h->d;
     const double nx = d.nx, nu = d.nu, nv = d.nv, ny = 2 * nx + nu;
     const double V = 4 * ny + ny + 2 * nv + 2 * (nx + nv) + 2 * nu + 2 * nx + ny + 2 * ny + 3 * nx + 2 * nu + 2 * ny;
-    const double mats = nv * (4 * nx + 2 * nu) * (h->factor_mode == RN_FACTORS_FULL ? 1.0 : 0.5);
+    const double mats = h->factor_mode == RN_FACTORS_SHARED ? 0.0 : nv * (4 * nx + 2 * nu) * (h->factor_mode == RN_FACTORS_FULL ? 1.0 : 0.5);
     return 4.0 * (d.nodes * (mats + ny + V) + (double)h->n_omega * (nv * nv + nv * nx) + nv * nx + nu * nv + nx * nu);
 }
 
@@ -689,6 +696,8 @@ static SweepArgs make_sweep_args(Handle *h, bool fuse_prox) {
 static rn_status launch_stream(Handle *h, cudaStream_t st, bool extrapolate, bool dry, const float *yA_xi, const float *yA_psi,
                                const float *yB_xi, const float *yB_psi) {
     const rn_dims &d = h->d;
+    if (h->factor_mode == RN_FACTORS_SHARED)
+        return fail(h, RN_ERR_INVALID, "the stand-alone factor stream does not exist in RN_FACTORS_SHARED mode (persistent sweep only)");
     StreamArgs A{};
     A.mat[0] = h->D; A.mat[1] = h->F; A.mat[2] = h->Phi; A.mat[3] = h->Psi;
     A.yA_xi = yA_xi; A.yA_psi = yA_psi; A.yB_xi = yB_xi; A.yB_psi = yB_psi;
@@ -910,6 +919,8 @@ rn_status apg_enqueue(Handle *h, int iterations) {
     RN_CHECK(ensure_lambda(h, iterations));
     RN_CHECK(apg_init(h));
     if (use_persistent(h)) return enqueue_persistent(h, iterations);
+    if (h->factor_mode == RN_FACTORS_SHARED)
+        return fail(h, RN_ERR_INVALID, "RN_FACTORS_SHARED needs the persistent sweep (RN_SWEEP_PERSISTENT on a tree it supports)");
     static const bool no_graph = getenv("RN_NO_GRAPH") != nullptr;
     long long per_iter = 0;
     if (no_graph) {

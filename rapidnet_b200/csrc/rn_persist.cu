@@ -63,6 +63,8 @@ struct PArgs {
     const int *crown_path;                      // [n_crown][kMaxCs]: path root -> node of every crown node (entry k = its stage-k ancestor)
     unsigned int branch_mask;                   // bit s: stage s has more nodes than stage s-1 (the reference's branching stages, :699-719)
     int N, cs, K, nodes, n_crown, n_mats, df_mode, iters, nx, nu, nv, cols_per_chunk, clock_cta;
+    int sh_mode, sh_tile;                       // RN_FACTORS_SHARED: no per-node matrix is read; nodes per tile of its phase S
+    int sh_oLt, sh_oC, sh_oGc, sh_oY, sh_oScr2, sh_oVec;   // its shared-memory layout (float offsets; G sits at kOffSweep)
     int n_stages, stage_stride;                 // matrix ring: stages and floats per stage (payload + 32 floats of slack)
     const float *mat[4];                        // D, F, Phi, Psi (packed per node, Engine.cu:201-207)
     const float *pack;                          // G | OmegaBar | L | B, each padded to 16 B (sweeps)
@@ -96,8 +98,8 @@ struct PArgs {
     float step, inv_step, pen_x, pen_xs;
     // sweep shared-memory layout (float offsets from the dynamic shared-memory base) and the pack's pieces
     int oG, oOm, oL, oX1, oY, oV, oScr2, oStg, oXb;
-    unsigned int bG, bOm, bL, bB;               // bytes of the four bulk copies
-    int pG, pOm, pL, pB;                        // float offsets inside the pack
+    unsigned int bG, bOm, bL, bB, bLt;          // bytes of the bulk copies
+    int pG, pOm, pL, pB, pLt;                   // float offsets inside the pack
 };
 
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kPC) : "memory"); }
@@ -1299,6 +1301,170 @@ __device__ __noinline__ void ew_role(const PArgs &P, const Slice &R, EwState &E,
     if (blockIdx.x == P.clock_cta && et == 0) { unsigned long long *c = clk_smem(); c[30] += cyc_rf; c[31] += cyc_pro; }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// phase S of the shared-factor formulation (RN_FACTORS_SHARED, "Tier B" of SURVEY.md 8d).  D_i = G sysF_i' and
+// F_i = L' sysG_i' (Engine.cu:720-728) with sysF_i = [diag(s_x); diag(s_xs)], sysG_i = diag(s_u), so
+//   D_i xi_w = G c_i,  c_i = sysF_i' xi_w      and      F_i psi_w = L' g_i,  g_i = s_u o psi_w
+// and no per-node matrix is read at all: the phase is the fused element-wise pass plus two small GEMMs per tile of
+// nodes against the SHARED matrices G (nv x nx) and L' (nv x nu), both in shared memory.  A CTA owns a contiguous node
+// range and walks it in tiles of up to sh_tile nodes:
+//   1. the tile's vectors (Hx, w, z, y of both dual blocks, the diagonals) arrive by nine 1-D bulk TMA copies -- each
+//      array's slice of a contiguous node range is contiguous, copied as the enclosing 16-byte window;
+//   2. warp = node, lane = element pair: finalisation of the previous prox, residual, dual update, extrapolation
+//      (the same arithmetic as ew_role), y and w to global memory, c and g as columns [element][kTP];
+//   3. G x [c columns] -> part[0] rows, L' x [g columns] -> part[1] rows (tile_gemm, the sweeps' GEMM).
+// The sweeps then run exactly as in RN_FACTORS_DF (v = -1/2 Omega r).
+// ---------------------------------------------------------------------------------------------------------------
+struct ShState { uint32_t vph; };
+struct ShRange { int n0, n1; };
+__device__ __forceinline__ ShRange sh_range(const PArgs &P) {
+    ShRange R;
+    R.n0 = (int)((long long)P.nodes * blockIdx.x / gridDim.x);
+    R.n1 = (int)((long long)P.nodes * (blockIdx.x + 1) / gridDim.x);
+    return R;
+}
+__device__ __forceinline__ uint64_t *sh_bar(int k) { return reinterpret_cast<uint64_t *>(smem_f(kOffBar)) + k; }   // Pipe::full[k]: idle in this mode
+// one thread: G and L' of iteration `it` -> shared memory (barrier 0, parity it & 1).  Issued while the closing grid
+// barrier of the previous iteration is pending (the sweep region is dead by then; the matrices are constants).
+__device__ __noinline__ void sh_issue_matrices(const PArgs &P) {
+    fence_proxy_async_all();
+    mbar_expect_tx(sh_bar(0), P.bG + P.bLt);
+    bulk_g2s(smem_f(kOffSweep), P.pack + P.pG, P.bG, sh_bar(0));
+    bulk_g2s(smem_f(P.sh_oLt), P.pack + P.pLt, P.bLt, sh_bar(0));
+}
+struct ShVecPtrs { const float *g[9]; };
+// global sources of the nine vector arrays of iteration `it` (same roles as loader_role's g0..g8)
+__device__ __forceinline__ ShVecPtrs sh_vec_ptrs(const PArgs &P, int it) {
+    const int prev_ = (it + 1) & 1;   // W[(it-1)&1] and Y[(it&1)^1]
+    ShVecPtrs V;
+    V.g[0] = P.pri_xi; V.g[1] = P.Wxi[prev_]; V.g[2] = P.dual_xi; V.g[3] = P.Yxi[prev_];
+    V.g[4] = P.pri_psi; V.g[5] = P.Wpsi[prev_]; V.g[6] = P.dual_psi; V.g[7] = P.Ypsi[prev_]; V.g[8] = P.diag;
+    return V;
+}
+// float offset of array a's buffer inside the vector buffer / its row length
+__device__ __forceinline__ int sh_vec_off(const PArgs &P, int a) {
+    const int tile = P.sh_tile, bx = ((tile * 2 * P.nx + 3) & ~3) + 8, bp = ((tile * P.nu + 3) & ~3) + 8;
+    return a < 4 ? a * bx : (4 * bx + (a - 4) * bp);
+}
+__device__ __forceinline__ int sh_vec_dim(const PArgs &P, int a) { return a < 4 ? 2 * P.nx : (a < 8 ? P.nu : 2 * P.nx + P.nu); }
+// one thread: the vectors of nodes [t0, t0 + nt) -> the vector buffer (barrier 1)
+__device__ __noinline__ void sh_issue_vectors(const PArgs &P, int it, int t0, int nt) {
+    const ShVecPtrs V = sh_vec_ptrs(P, it);
+    fence_proxy_async_all();
+    uint32_t total = 0;
+    uintptr_t src[9]; uint32_t bytes[9];
+#pragma unroll
+    for (int a = 0; a < 9; a++) {
+        const int dim = sh_vec_dim(P, a);
+        const uintptr_t p0 = reinterpret_cast<uintptr_t>(V.g[a] + (size_t)t0 * dim), p1 = p0 + (size_t)nt * dim * sizeof(float);
+        src[a] = p0 & ~uintptr_t(15);
+        bytes[a] = (uint32_t)(((p1 + 15) & ~uintptr_t(15)) - src[a]);
+        total += bytes[a];
+    }
+    mbar_expect_tx(sh_bar(1), total);
+#pragma unroll
+    for (int a = 0; a < 9; a++) bulk_g2s(smem_f(P.sh_oVec + sh_vec_off(P, a)), reinterpret_cast<const void *>(src[a]), bytes[a], sh_bar(1));
+}
+
+__device__ __noinline__ void sh_elementwise(const PArgs &P, const EwIter &I, int it, int t0, int nt, Cand &bx, Cand &bp) {
+    const int nx = P.nx, nu = P.nu, ny = 2 * nx + nu, nxp = P.nxp, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float inv_step = P.inv_step, step = P.step, a1 = I.a1, a2 = I.a2, sc1 = I.sc1, sc2 = I.sc2;
+    const bool br1 = I.br1 != 0, br2 = I.br2 != 0;
+    float *__restrict__ Yxi = P.Yxi[I.cur], *__restrict__ Wxi = P.Wxi[I.cur], *__restrict__ Ypsi = P.Ypsi[I.cur],
+          *__restrict__ Wpsi = P.Wpsi[I.cur], *__restrict__ cg = P.cm_c;
+    float *ccol = smem_f(P.sh_oC), *gcol = smem_f(P.sh_oGc);
+    const int *colnode = reinterpret_cast<const int *>(smem_f(kOffMisc));
+    // every array's slice starts `skip` floats into its 16-byte window
+    const ShVecPtrs V = sh_vec_ptrs(P, it);
+    const float *b[9];
+#pragma unroll
+    for (int a = 0; a < 9; a++) {
+        const uintptr_t p0 = reinterpret_cast<uintptr_t>(V.g[a] + (size_t)t0 * sh_vec_dim(P, a));
+        b[a] = smem_f(P.sh_oVec + sh_vec_off(P, a)) + (int)((p0 & 15) >> 2);
+    }
+    Cand lbx = bx, lbp = bp;
+#pragma unroll 1
+    for (int nl = warp; nl < kTP; nl += kPC / 32) {
+        if (nl >= nt) {   // unused columns of the tile: zeros
+            for (int t = lane; t < nx; t += 32) ccol[t * kTP + nl] = 0.f;
+            for (int t = lane; t < nu; t += 32) gcol[t * kTP + nl] = 0.f;
+            continue;
+        }
+        const int node = t0 + nl;
+        const size_t crow = (size_t)colnode[nl] * nxp;
+        const float *hx = b[0] + nl * 2 * nx, *wp = b[1] + nl * 2 * nx, *zz = b[2] + nl * 2 * nx, *yp = b[3] + nl * 2 * nx;
+        const float *dg = b[8] + nl * ny;
+        // state-box element t and safety element nx + t of the node: together they give c[t] = (sysF' xi_w)[t]  (:651-658)
+        for (int t = lane; t < nx; t += 32) {
+            float wv[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int el = t + h * nx;
+                const float hxv = hx[el], wpv = wp[el], ypv = yp[el];
+                float z = zz[el];
+                if (br1 || br2) {   // distance branch of the previous prox (:792-815; quirk SURVEY A.4-1)
+                    const float tt = hxv + inv_step * wpv;
+                    const float df = tt + -1.f * z;
+                    if (h == 0) { if (br1) z = z + sc1 * df; }
+                    else if (br2) { const float d2v = br1 ? (node == 0 ? 0.f : df + -1.f * z) : df; z = z + sc2 * d2v; }
+                }
+                const float res = hxv + -1.f * z;           // computeFixedPointResidual (:839-850)
+                const float yn = wpv + step * res;          // dualUpdate (:854-864)
+                float w = yn * a1;                          // dualExtrapolationStep (:548-552)
+                w += a2 * ypv;
+                const size_t k = (size_t)node * 2 * nx + el;
+                Yxi[k] = yn; Wxi[k] = w;
+                cand_merge(lbx, Cand{fabsf(res), res, (int)k});
+                wv[h] = w;
+            }
+            const float cv = dg[t] * wv[0] + dg[nx + t] * wv[1];
+            cg[crow + t] = cv;
+            ccol[t * kTP + nl] = cv;
+        }
+        const float *hp = b[4] + nl * nu, *wpp = b[5] + nl * nu, *zp = b[6] + nl * nu, *ypp = b[7] + nl * nu;
+        for (int t = lane; t < nu; t += 32) {
+            const float hxv = hp[t], wpv = wpp[t], ypv = ypp[t], z = zp[t];
+            const float res = hxv + -1.f * z;
+            const float yn = wpv + step * res;
+            float w = yn * a1;
+            w += a2 * ypv;
+            const size_t k = (size_t)node * nu + t;
+            Ypsi[k] = yn; Wpsi[k] = w;
+            cand_merge(lbp, Cand{fabsf(res), res, (int)k});
+            gcol[t * kTP + nl] = dg[2 * nx + t] * w;       // g = sysG' psi_w
+        }
+    }
+    bx = lbx; bp = lbp;
+}
+
+__device__ __noinline__ void sh_stream(const PArgs &P, ShState &S, const EwIter &I, int it, Cand &bx, Cand &bp) {
+    const ShRange R = sh_range(P);
+    const int tile = P.sh_tile, nv = P.nv, nvp = P.nvp;
+    int *colnode = reinterpret_cast<int *>(smem_f(kOffMisc));
+    float *Ysm = smem_f(P.sh_oY), *scr2 = smem_f(P.sh_oScr2);
+    if (threadIdx.x == 0 && R.n0 < R.n1) sh_issue_vectors(P, it, R.n0, min(tile, R.n1 - R.n0));
+    bool mats = false;
+#pragma unroll 1
+    for (int t0 = R.n0; t0 < R.n1; t0 += tile) {
+        const int nt = min(tile, R.n1 - t0);
+        if (threadIdx.x < kTP) colnode[threadIdx.x] = threadIdx.x < nt ? __ldg(P.pos + t0 + threadIdx.x) : 0;
+        mbar_wait(sh_bar(1), S.vph); S.vph ^= 1;
+        cbar();
+        sh_elementwise(P, I, it, t0, nt, bx, bp);
+        cbar();
+        // the vector buffer is free: the next tile's vectors land while this tile's products are formed
+        if (threadIdx.x == 0 && t0 + tile < R.n1) sh_issue_vectors(P, it, t0 + tile, min(tile, R.n1 - t0 - tile));
+        if (!mats) { mbar_wait(sh_bar(0), (uint32_t)(it & 1)); mats = true; }
+        tile_gemm(smem_f(kOffSweep), nv, P.nx, smem_f(P.sh_oC), Ysm, scr2);          // G c = D xi_w
+        cols_to_global(Ysm, colnode, nt, nv, nvp, P.part[0]);
+        tile_gemm(smem_f(P.sh_oLt), nv, P.nu, smem_f(P.sh_oGc), Ysm, scr2);          // L' g = F psi_w
+        cols_to_global(Ysm, colnode, nt, nv, nvp, P.part[1]);
+        cbar();
+    }
+    if (!mats) mbar_wait(sh_bar(0), (uint32_t)(it & 1));   // keep the barrier's phase in step on a CTA without nodes
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
@@ -1312,6 +1478,7 @@ struct KState {
     GemvState GS;
     EwState ES;
     LoaderState LS;
+    ShState SH;
     double s1, s2;
 };
 
@@ -1361,7 +1528,16 @@ __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
     Cand bx{-1.f, 0.f, 0x7fffffff}, bp{-1.f, 0.f, 0x7fffffff};
 
     // ---- phase S: three-role pipeline.  loader -> [ring] -> GEMV warps -> [red] -> element-wise warps -> [wbuf] -> GEMV
-    if (warp < kGemvWarps) {
+    if (P.sh_mode) {   // shared-factor formulation: no matrix stream, every warp runs the element-wise pass
+        const float lam = __ldg(P.lambda_tab + it);
+        const float d1 = sd[0], d2 = sd[1];
+        const float thr1 = P.inv_step * P.pen_x, thr2 = P.inv_step * P.pen_xs;
+        EwIter I;
+        I.a1 = 1.f + lam; I.a2 = -lam; I.cur = it & 1;
+        I.br1 = d1 > thr1; I.br2 = d2 > thr2;
+        I.sc1 = I.br1 ? 1.f - thr1 / d1 : 0.f; I.sc2 = I.br2 ? 1.f - thr2 / d2 : 0.f;
+        sh_stream(P, K.SH, I, it, bx, bp);
+    } else if (warp < kGemvWarps) {
         gemv_dispatch(P, K.R, K.GS);
     } else if (warp == kLoaderWarp) {
         loader_role(P, K.R, K.LS, it, 0);
@@ -1502,7 +1678,10 @@ __device__ __noinline__ void iter_close(const PArgs &P, KState &K, int it) {
     dstamp(P, 28);
     if (P.n_ranks > 1) {
         // the sweep region is dead (every warp passed the barrier above): start refilling the stream ring for iteration it+1
-        if (warp == kLoaderWarp && it + 1 < P.iters) loader_role(P, K.R, K.LS, it + 1, 1);
+        if (warp == kLoaderWarp && it + 1 < P.iters) {
+            if (!P.sh_mode) loader_role(P, K.R, K.LS, it + 1, 1);
+            else if (lane == 0) sh_issue_matrices(P);
+        }
         grid_sync_cross(P, target, P.epoch0 + 2u * (unsigned)it + 2u, it);
     } else {
         // closing grid barrier, run by the loader warp: arrive first (the fence would otherwise also wait for the bulk
@@ -1512,7 +1691,11 @@ __device__ __noinline__ void iter_close(const PArgs &P, KState &K, int it) {
         if (warp == kLoaderWarp) {
             if (lane == 0) { __threadfence(); atomicAdd(P.bar, 1u); }
             __syncwarp();
-            if (it + 1 < P.iters) loader_role(P, K.R, K.LS, it + 1, 1);
+            if (it + 1 < P.iters) {
+                if (!P.sh_mode) loader_role(P, K.R, K.LS, it + 1, 1);
+                else if (lane == 0) sh_issue_matrices(P);   // shared-factor mode: G, L' of the next iteration
+                __syncwarp();
+            }
             if (lane == 0) while (ld_acquire_u32(P.bar) < target) {}   // acquire + the CTA barrier below order the other threads' reads
             __syncwarp();
             // the global distances of this iteration's prox (cublasSnrm2, :792, :810) for the next iteration's element-wise
@@ -1573,9 +1756,11 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
     K.GS = GemvState{0, 0u, 0, 0u, 0, 0u};
     K.ES = EwState{0, 0u, 0, 0u, 0, 0u};
     K.LS = LoaderState{0, 0u, 0, 0u, 0};
+    K.SH = ShState{0u};
     K.s1 = 0; K.s2 = 0;
 
     const int iters = P.iters;
+    if (P.sh_mode && tid == 0 && iters > 0) sh_issue_matrices(PS);   // later iterations: at the closing barrier of the one before
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
         iter_stream(PS, K, it);
@@ -1602,7 +1787,7 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
 // ---------------------------------------------------------------------------------------------------------------
 struct SweepLayout {
     int oG, oOm, oL, oX1, oY, oV, oScr2, oStg, oXb, end;   // shared-memory float offsets
-    int pG, pOm, pL, pB, pack_floats;                 // float offsets inside the pack
+    int pG, pOm, pL, pB, pLt, pack_floats, sB, sLt;   // float offsets inside the pack (G | OmegaBar | L | B | L'), sizes of B and L'
     int nxp, nup, nvp;
 };
 static int pad4(long long n) { return (int)((n + 3) & ~3LL); }
@@ -1611,7 +1796,8 @@ static SweepLayout sweep_layout(const Handle *h) {
     SweepLayout Y{};
     Y.nxp = pad4(nx); Y.nup = pad4(nu); Y.nvp = pad4(nv);
     const int sG = pad4((long long)nv * nx), sOm = pad4((long long)nv * nv), sL = pad4((long long)nu * nv), sB = pad4((long long)nx * nu);
-    Y.pG = 0; Y.pOm = sG; Y.pL = sG + sOm; Y.pB = sG + sOm + sL; Y.pack_floats = sG + sOm + sL + sB;
+    Y.pG = 0; Y.pOm = sG; Y.pL = sG + sOm; Y.pB = sG + sOm + sL; Y.pLt = Y.pB + sB; Y.pack_floats = Y.pLt + sL;
+    Y.sB = sB; Y.sLt = sL;
     Y.oG = kOffSweep; Y.oOm = Y.oG + std::max(sG, sB); Y.oL = Y.oOm + sOm;     // B overlays G
     Y.oX1 = Y.oL + sL;
     Y.oY = Y.oX1 + std::max(nv + nx, nu) * kTP;
@@ -1644,7 +1830,31 @@ static RingLayout ring_layout(const Handle *h) {
     R.end = kOffRing + R.n_stages * R.stage_stride;
     return R;
 }
-static size_t persist_smem_bytes(const Handle *h) { return (size_t)std::max(ring_layout(h).end, sweep_layout(h).end) * 4 + 128; }
+// RN_FACTORS_SHARED, phase S: G | L' | c columns [nx][kTP] | g columns [nu][kTP] | products [nv][kTP] | split-K scratch |
+// vector buffer of one tile of `tile` nodes (Hx, w, z, y of both dual blocks + the diagonals, each with 8 floats of slack
+// for the 16-byte window of its bulk copy).  It overlays the sweep region like the stream ring does.
+struct SharedLayout { int oLt, oC, oGc, oY, oScr2, oVec, tile, end; };
+static int shared_vec_floats(const rn_dims &d, int tile) {
+    return 4 * (pad4((long long)tile * 2 * d.nx) + 8) + 4 * (pad4((long long)tile * d.nu) + 8) + pad4((long long)tile * (2 * d.nx + d.nu)) + 8;
+}
+static SharedLayout shared_layout(const Handle *h) {
+    const rn_dims &d = h->d;
+    SharedLayout S{};
+    S.oLt = kOffSweep + ((pad4((long long)d.nv * d.nx) + 31) & ~31);
+    S.oC = S.oLt + ((pad4((long long)d.nu * d.nv) + 31) & ~31);
+    S.oGc = S.oC + d.nx * kTP; S.oY = S.oGc + d.nu * kTP; S.oScr2 = S.oY + d.nv * kTP;
+    S.oVec = (S.oScr2 + 128 * kTP + 31) & ~31;
+    const int cap = 227 * 1024 / 4 - 32;
+    S.tile = kTP;
+    while (S.tile > 1 && S.oVec + shared_vec_floats(d, S.tile) > cap) S.tile--;
+    S.end = S.oVec + shared_vec_floats(d, S.tile);
+    return S;
+}
+static size_t persist_smem_bytes(const Handle *h) {
+    int end = std::max(ring_layout(h).end, sweep_layout(h).end);
+    if (h->factor_mode == RN_FACTORS_SHARED) end = std::max(end, shared_layout(h).end);
+    return (size_t)end * 4 + 128;
+}
 
 bool persistent_supported(const Handle *h) {
     const rn_dims &d = h->d;
@@ -1703,13 +1913,14 @@ rn_status persistent_prepare(Handle *h) {
     RN_CHECK(dev_alloc(h, &h->grid_bar, 64));   // [0] grid barrier, [32] heads counter (its own 128-byte line)
     RN_CHECK(dev_alloc(h, &h->phase_ns, 32));
     RN_CHECK(dev_alloc(h, &h->cta_ns, 2 * 1024));
-    // G | OmegaBar | L | B, each padded to 16 bytes: the four bulk copies of the sweeps
+    // G | OmegaBar | L | B | L', each padded to 16 bytes: the bulk copies of the sweeps (and of phase S in shared-factor mode)
     RN_CHECK(dev_alloc(h, &h->sweep_pack, (size_t)Y.pack_floats));
     const size_t f = sizeof(float);
     RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pG, h->G, (size_t)d.nv * d.nx * f, cudaMemcpyDeviceToDevice, h->stream));
     RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pOm, h->OmegaBar, (size_t)d.nv * d.nv * f, cudaMemcpyDeviceToDevice, h->stream));
     RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pL, h->L, (size_t)d.nu * d.nv * f, cudaMemcpyDeviceToDevice, h->stream));
     RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pB, h->B, (size_t)d.nx * d.nu * f, cudaMemcpyDeviceToDevice, h->stream));
+    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pLt, h->Lt, (size_t)d.nv * d.nu * f, cudaMemcpyDeviceToDevice, h->stream));
     // chain-major row of every node: crown nodes keep their id, chain j / stage cs+s sits at n_crown + j T + s
     std::vector<int> pos(n);
     for (int i = 0; i < d.nodes; i++) {
@@ -1745,7 +1956,9 @@ rn_status persistent_prepare(Handle *h) {
     RN_CHECK(dev_alloc(h, &h->crown_rng, rng.size()));
     RN_CUDA(h, cudaMemcpyAsync(h->crown_rng, rng.data(), rng.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     RN_CUDA(h, cudaStreamSynchronize(h->stream));
-    const size_t smem = persist_smem_bytes(h);
+    // the attribute is set once: cover the shared-factor layout too when it fits (rn_set_modes may switch later)
+    size_t smem = persist_smem_bytes(h);
+    if ((size_t)shared_layout(h).end * 4 + 128 <= 227 * 1024) smem = std::max(smem, (size_t)shared_layout(h).end * 4 + 128);
     RN_CUDA(h, cudaFuncSetAttribute(k_apg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     RN_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_apg_persistent, kPT, smem));
@@ -1769,7 +1982,12 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
         if (h->h_cum[st_ + 1] - h->h_cum[st_] > h->h_cum[st_] - h->h_cum[st_ - 1]) P.branch_mask |= 1u << st_;
     P.N = d.N; P.cs = h->chain_stage; P.K = d.K; P.nodes = d.nodes; P.n_crown = h->h_cum[h->chain_stage];
     P.n_mats = h->factor_mode == RN_FACTORS_FULL ? 4 : 2;
-    P.df_mode = h->factor_mode == RN_FACTORS_DF ? 1 : 0;
+    P.df_mode = h->factor_mode != RN_FACTORS_FULL ? 1 : 0;           // v = -1/2 Omega r
+    P.sh_mode = h->factor_mode == RN_FACTORS_SHARED ? 1 : 0;          // D xi = G c, F psi = L' g: no per-node matrix
+    {
+        const SharedLayout SL = shared_layout(h);
+        P.sh_tile = SL.tile; P.sh_oLt = SL.oLt; P.sh_oC = SL.oC; P.sh_oGc = SL.oGc; P.sh_oY = SL.oY; P.sh_oScr2 = SL.oScr2; P.sh_oVec = SL.oVec;
+    }
     P.iters = iters; P.nx = d.nx; P.nu = d.nu; P.nv = d.nv;
     const RingLayout RL = ring_layout(h);
     P.cols_per_chunk = RL.cols_per_chunk; P.n_stages = RL.n_stages; P.stage_stride = RL.stage_stride;
@@ -1812,9 +2030,9 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     P.step = h->step; P.inv_step = 1 / h->step; P.pen_x = h->pen_x; P.pen_xs = h->pen_xs;
     const SweepLayout Y = sweep_layout(h);
     P.oG = Y.oG; P.oOm = Y.oOm; P.oL = Y.oL; P.oX1 = Y.oX1; P.oY = Y.oY; P.oV = Y.oV; P.oScr2 = Y.oScr2; P.oStg = Y.oStg; P.oXb = Y.oXb;
-    P.pG = Y.pG; P.pOm = Y.pOm; P.pL = Y.pL; P.pB = Y.pB;
+    P.pG = Y.pG; P.pOm = Y.pOm; P.pL = Y.pL; P.pB = Y.pB; P.pLt = Y.pLt;
     P.bG = (unsigned)(Y.pOm - Y.pG) * 4u; P.bOm = (unsigned)(Y.pL - Y.pOm) * 4u; P.bL = (unsigned)(Y.pB - Y.pL) * 4u;
-    P.bB = (unsigned)(Y.pack_floats - Y.pB) * 4u;
+    P.bB = (unsigned)Y.sB * 4u; P.bLt = (unsigned)Y.sLt * 4u;
     P.nxp = Y.nxp; P.nup = Y.nup; P.nvp = Y.nvp;
     // chain-major copies of the per-solve vectors the sweeps stage with bulk copies
     k_to_chain_major<<<d.nodes, 128, 0, st>>>(d.nodes, d.nv, Y.nvp, h->pos_dev, h->beta, h->cm_beta);
