@@ -235,11 +235,47 @@ def bench_closed_loop(args, rank, world, local, stream, barrier):
     sec = float(t[0])
     solves = total * args.closed_loop_steps
     finite = all(np.isfinite(u).all() and np.isfinite(x).all() for u, x in res.values())
+    out = {"workload": describe(args.closed_loop_workload, prob), "instances": total, "steps_per_instance": args.closed_loop_steps,
+           "iterations_per_solve": args.iters, "scaling": "weak", "solves_per_s": solves / sec, "ms_per_closed_loop_step": sec / max(1, len(res) * args.closed_loop_steps) * 1e3,
+           "apg_iterations_per_s": solves * args.iters / sec, "finite": bool(finite),
+           "note": "instances shard with no data-path collective; one factored handle per GPU is reused by all of its instances"}
     s.close()
-    return {"workload": describe(args.closed_loop_workload, prob), "instances": total, "steps_per_instance": args.closed_loop_steps,
-            "iterations_per_solve": args.iters, "scaling": "weak", "solves_per_s": solves / sec, "ms_per_closed_loop_step": sec / max(1, len(res) * args.closed_loop_steps) * 1e3,
-            "apg_iterations_per_s": solves * args.iters / sec, "finite": bool(finite),
-            "note": "instances shard with no data-path collective; one factored handle per GPU is reused by all of its instances"}
+    # the same study with several handles of this GPU solving side by side (rn_set_grid_limit): a K-scenario tree keeps K
+    # CTAs busy in its sweeps, the lanes fill the SMs one solve leaves idle.  Streamed and shared-factor formulations.
+    lanes = args.closed_loop_lanes
+    if lanes > 1:
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        cap = max(1, sms // lanes)
+        per_rank = max(args.closed_loop_instances, 2 * lanes)
+        handles = []
+        for _ in range(lanes):
+            h = cabi.Solver(prob, device=local)
+            h.set_stream(torch.cuda.Stream().cuda_stream)
+            h.set_grid_limit(cap)
+            h.factor_step()
+            handles.append(h)
+        for key, mode in (("lanes", cabi.FACTORS_FULL), ("lanes_shared", cabi.FACTORS_SHARED)):
+            for h in handles:
+                h.set_modes(cabi.SWEEP_PERSISTENT, mode)
+            closed_loop.simulate_lanes(handles, prob, lanes, 1, args.iters)   # warm-up: one solve per lane
+            barrier()
+            t0 = time.perf_counter()
+            r2 = closed_loop.simulate_lanes(handles, prob, per_rank * world, args.closed_loop_steps, args.iters, rank=rank, world=world)
+            barrier()
+            sec2 = time.perf_counter() - t0
+            t2 = torch.tensor([sec2], dtype=torch.float64, device="cuda")
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            sec2 = float(t2[0])
+            n2 = per_rank * world * args.closed_loop_steps
+            out[key] = {"lanes_per_gpu": lanes, "ctas_per_lane": cap, "factors": "full" if mode == cabi.FACTORS_FULL else "shared",
+                        "instances": per_rank * world, "solves_per_s": n2 / sec2, "apg_iterations_per_s": n2 * args.iters / sec2,
+                        "speedup_vs_one_handle": (n2 / sec2) / (solves / sec),
+                        "finite": bool(all(np.isfinite(u).all() and np.isfinite(x).all() for u, x in r2.values()))}
+        for h in handles:
+            h.close()
+    return out
 
 
 def describe(workload, prob):
@@ -261,6 +297,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the legs of the two reformulations (D, F only; shared factors)")
     ap.add_argument("--closed-loop-instances", type=int, default=4, help="closed-loop Monte-Carlo leg: instances PER RANK (0 = skip)")
+    ap.add_argument("--closed-loop-lanes", type=int, default=4, help="that leg again with this many handles per GPU side by side (1 = skip)")
     ap.add_argument("--closed-loop-steps", type=int, default=2, help="receding-horizon steps per instance in that leg")
     ap.add_argument("--closed-loop-workload", default="C1r30", help="tree of that leg (SURVEY C4: the shipped K=30 tree)")
     ap.add_argument("--sweep", default="persistent", choices=["persistent", "chain", "per_stage"])

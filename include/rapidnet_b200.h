@@ -301,6 +301,11 @@ rn_status rn_phase_times(rn_handle *h, double *ns_per_iteration /*[32]*/);
 /* Load balance of the factor stream in the last rn_profile_kernels run: out[2k] = ns per iteration CTA k spent in phase S,
  * out[2k+1] = the SM it ran on.  n_ctas = size of the persistent grid. */
 rn_status rn_cta_times(rn_handle *h, double *out /*[2*cap_ctas]*/, int cap_ctas, int *n_ctas);
+/* Caps the grid of the persistent kernel at max_ctas CTAs (0 = one per SM, the default).  Independent SMPC instances
+ * (closed-loop Monte-Carlo, BASELINE config[3]) shard with no collective; on ONE GPU several handles, each on its own
+ * stream with a share of the SMs, solve side by side: a tree with K scenarios keeps only K CTAs busy in its sweeps.
+ * The reference runs one controller at a time (src/main.cu:27-63). */
+rn_status rn_set_grid_limit(rn_handle *h, int max_ctas);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,7 @@ EXPORTS = [
     "rn_set_uncertainty", "rn_apg_init", "rn_step", "rn_apg_solve", "rn_control_action", "rn_move_forward",
     "rn_buffer", "rn_read_buffer", "rn_write_buffer", "rn_profile_stream", "rn_profile_kernels", "rn_phase_times", "rn_cta_times",
     "rn_dist_prepare", "rn_dist_connect", "rn_dist_fix_crown_beta", "rn_read_pinf_parts", "rn_dist_error",
+    "rn_set_grid_limit",
 ]
 
 
@@ -197,6 +198,10 @@ class Solver:
 
     def set_modes(self, sweep=SWEEP_PERSISTENT, factors=FACTORS_FULL):
         self._check(load().rn_set_modes(self.h, sweep, factors), "rn_set_modes")
+
+    def set_grid_limit(self, max_ctas: int):
+        """Cap the persistent kernel's grid (0 = one CTA per SM) so that several handles can solve side by side."""
+        self._check(load().rn_set_grid_limit(self.h, int(max_ctas)), "rn_set_grid_limit")
 
     def info(self) -> RnInfo:
         info = RnInfo()

@@ -70,3 +70,23 @@ def simulate(solver, prob: Problem, instances: int, steps: int, iterations: int,
     for idx in shard(instances, world, rank):
         out[idx] = run_instance(solver, prob, make_instance(prob, idx, steps), iterations)
     return out
+
+
+def simulate_lanes(solvers, prob: Problem, instances: int, steps: int, iterations: int, rank: int = 0, world: int = 1):
+    """The same study with several handles ("lanes") of ONE GPU solving side by side: lane l runs every len(solvers)-th
+    instance of this rank's share on its own handle and CUDA stream, each handle's persistent kernel capped at a share
+    of the SMs (`Solver.set_grid_limit`).  A tree with K scenarios keeps K CTAs busy in its sweeps, so the lanes fill SMs
+    that one solve leaves idle.  One host thread per lane (the C-ABI calls block, ctypes releases the GIL).  Same
+    result as `simulate`: instances are independent and every solve is deterministic for a given grid size."""
+    from concurrent.futures import ThreadPoolExecutor
+    mine = list(shard(instances, world, rank))
+    lanes = len(solvers)
+
+    def run_lane(l):
+        return {idx: run_instance(solvers[l], prob, make_instance(prob, idx, steps), iterations) for idx in mine[l::lanes]}
+
+    out = {}
+    with ThreadPoolExecutor(max_workers=lanes) as ex:
+        for part in ex.map(run_lane, range(lanes)):
+            out.update(part)
+    return out

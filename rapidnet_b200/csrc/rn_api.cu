@@ -257,6 +257,15 @@ rn_status rn_set_modes(rn_handle *hh, rn_sweep_mode sweep, rn_factor_mode factor
     return RN_OK;
 }
 
+rn_status rn_set_grid_limit(rn_handle *hh, int max_ctas) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return RN_ERR_INVALID;
+    if (max_ctas < 0) return rn::fail(h, RN_ERR_INVALID, "rn_set_grid_limit: max_ctas = %d", max_ctas);
+    if (h->dist_world > 1 && max_ctas > 0) return rn::fail(h, RN_ERR_STATE, "rn_set_grid_limit: the tree partition uses the whole GPU");
+    h->grid_limit = max_ctas;
+    return RN_OK;
+}
+
 rn_status rn_get_info(rn_handle *hh, rn_info *info) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (!h || !info) return RN_ERR_INVALID;

@@ -116,6 +116,7 @@ struct Handle {
     unsigned long long last_phase_ns[32] = {0};
     int last_phase_iters = 0;
     int persist_grid = 0;
+    int grid_limit = 0;              // rn_set_grid_limit: most CTAs of the persistent kernel (0 = one per SM)
 
     cudaGraphExec_t iter_graph = nullptr;
     int graph_sweep = -1, graph_factor = -1;

@@ -1966,7 +1966,6 @@ rn_status persistent_prepare(Handle *h) {
     int coop = 0;
     RN_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     if (!coop) return fail(h, RN_ERR_CUDA, "device does not support cooperative launch");
-    h->persist_grid = std::min(h->sm_count, std::min(h->dist_slots, h->pinf_slots));
     h->persist_ready = true;
     return RN_OK;
 }
@@ -1974,6 +1973,8 @@ rn_status persistent_prepare(Handle *h) {
 // iterations 0 .. iters-1 up to (and excluding) the last finalisation; the caller runs k_finalize afterwards
 rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     const rn_dims &d = h->d;
+    h->persist_grid = std::min(h->sm_count, std::min(h->dist_slots, h->pinf_slots));
+    if (h->grid_limit > 0) h->persist_grid = std::min(h->persist_grid, h->grid_limit);   // rn_set_grid_limit
     PArgs P{};
     P.parent = h->t.parent; P.child_first = h->t.child_first; P.child_count = h->t.child_count; P.omega_idx = h->t.omega_idx;
     P.cum = h->cum_dev; P.stages = h->t.stages; P.crown_rng = h->crown_rng; P.pos = h->pos_dev; P.crown_path = h->crown_path;

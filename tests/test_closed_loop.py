@@ -55,3 +55,33 @@ def test_closed_loop_two_ranks_equal_one_rank():
     B = prob.network.B.reshape(prob.network.nu, prob.network.nx).T.astype(np.float64)   # column-major nx x nu
     assert np.allclose(whole[1][1][1], whole[1][1][0] + B @ whole[1][0][0], rtol=1e-5, atol=1e-2)
     s.close()
+
+
+@pytest.mark.gpu
+def test_lanes_equal_single_handle():
+    """Four handles of one GPU, each capped at a quarter of the SMs, solving side by side: same closed-loop trajectories
+    as one handle with the same cap (bit-exact: a solve is deterministic for a given grid size) and, within the parity
+    tolerance, as the uncapped handle."""
+    import torch
+    from rapidnet_b200 import cabi
+    prob = named_problem("C1r6", max_iter=40)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    cap = max(8, sms // 4)
+    lanes = []
+    for _ in range(4):
+        s = cabi.Solver(prob)
+        s.set_stream(torch.cuda.Stream().cuda_stream)
+        s.set_grid_limit(cap)
+        s.factor_step()
+        lanes.append(s)
+    got = closed_loop.simulate_lanes(lanes, prob, 8, 2, 40)
+    want = closed_loop.simulate(lanes[0], prob, 8, 2, 40)
+    assert sorted(got) == sorted(want) == list(range(8))
+    for k in want:
+        assert np.array_equal(got[k][0], want[k][0]) and np.array_equal(got[k][1], want[k][1]), k
+    lanes[0].set_grid_limit(0)
+    full = closed_loop.simulate(lanes[0], prob, 2, 2, 40)
+    for k in full:
+        assert np.linalg.norm(full[k][0] - want[k][0]) <= 1e-4 * np.linalg.norm(want[k][0]), k
+    for s in lanes:
+        s.close()
