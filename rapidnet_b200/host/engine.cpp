@@ -56,6 +56,24 @@ Engine::Engine(SmpcConfiguration *smpcConfig) {
         std::cerr << "rapidnet_b200: rn_create failed (" << rc << "): " << rn_last_error(nullptr) << std::endl;
         std::exit(EXIT_FAILURE);
     }
+    // The reference has one formulation; the library's alternatives (include/rapidnet_b200.h: rn_sweep_mode,
+    // rn_factor_mode -- same iterates up to fp32 rounding) are chosen from the environment so that the class API stays
+    // the reference's: RAPIDNET_FACTORS = full | df | shared, RAPIDNET_SWEEP = persistent | chain | per_stage.
+    rn_factor_mode fm = RN_FACTORS_FULL;
+    rn_sweep_mode sm = RN_SWEEP_PERSISTENT;
+    if (const char *e = std::getenv("RAPIDNET_FACTORS")) {
+        const std::string v(e);
+        if (v == "df") fm = RN_FACTORS_DF;
+        else if (v == "shared") fm = RN_FACTORS_SHARED;
+        else if (v != "full") { std::cerr << "rapidnet_b200: RAPIDNET_FACTORS=" << v << " is not full|df|shared" << std::endl; std::exit(EXIT_FAILURE); }
+    }
+    if (const char *e = std::getenv("RAPIDNET_SWEEP")) {
+        const std::string v(e);
+        if (v == "chain") sm = RN_SWEEP_CHAIN;
+        else if (v == "per_stage") sm = RN_SWEEP_PER_STAGE;
+        else if (v != "persistent") { std::cerr << "rapidnet_b200: RAPIDNET_SWEEP=" << v << " is not persistent|chain|per_stage" << std::endl; std::exit(EXIT_FAILURE); }
+    }
+    check(rn_set_modes(h, sm, fm), "rn_set_modes");
 }
 
 Engine::~Engine() {

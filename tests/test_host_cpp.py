@@ -29,8 +29,9 @@ def _golden_json(path, d):
     return str(path)
 
 
-def _run(*args, timeout=600):
-    out = subprocess.run([_build(), *map(str, args)], capture_output=True, text=True, timeout=timeout)
+def _run(*args, timeout=600, env=None):
+    out = subprocess.run([_build(), *map(str, args)], capture_output=True, text=True, timeout=timeout,
+                         env=None if env is None else dict(os.environ, **env))
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     return out.stdout
 
@@ -79,18 +80,21 @@ def test_apg_steps_golden_gpu(toy, tmp_path):
 
 
 @pytest.mark.gpu
-def test_closed_loop_matches_ctypes_path(tmp_path):
+@pytest.mark.parametrize("factors", ["full", "shared"])
+def test_closed_loop_matches_ctypes_path(tmp_path, factors):
     """main.cu's closed loop through the C++ classes == the same calls through the ctypes binding (bit-identical: both
-    sit on the same C ABI), and the plant update is x+ = x + B u0_clamped."""
+    sit on the same C ABI), and the plant update is x+ = x + B u0_clamped.  The facade takes the
+    formulation from RAPIDNET_FACTORS."""
     from rapidnet_b200 import cabi
     from rapidnet_b200.datagen import named_problem
     prob = named_problem("C1", max_iter=40)
     cfg = write_problem(prob, str(tmp_path))
     out = tmp_path / "loop.json"
-    _run("closedloop", cfg, 2, out)
+    _run("closedloop", cfg, 2, out, env={"RAPIDNET_FACTORS": factors})
     res = json.load(open(out))
     c, fc = prob.config, prob.forecast
     s = cabi.Solver(prob)
+    s.set_modes(cabi.SWEEP_PERSISTENT, {"full": cabi.FACTORS_FULL, "shared": cabi.FACTORS_SHARED}[factors])
     s.factor_step()
     x, up, dp = c.current_x.copy(), c.prev_u.copy(), c.prev_demand.copy()
     for t in range(2):
