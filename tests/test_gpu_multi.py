@@ -17,11 +17,12 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("workload,world", [("C1", 2), ("C1r30", 2), ("C2", 2)])
-def test_partitioned_tree_matches_single_gpu(workload, world):
+@pytest.mark.parametrize("workload,world,factors", [("C1", 2, "full"), ("C1r30", 2, "full"), ("C2", 2, "full"), ("C2", 2, "shared")])
+def test_partitioned_tree_matches_single_gpu(workload, world, factors):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tools", "dist_check.py"), "--workload", workload, "--iters", "1,10,100"]
+           "--master-port", "29533", os.path.join(ROOT, "tools", "dist_check.py"), "--workload", workload, "--iters", "1,10,100",
+           "--factors", factors]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert "DIST_CHECK OK" in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])

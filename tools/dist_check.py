@@ -33,12 +33,12 @@ def main():
     dist.init_process_group("gloo")           # carries only the IPC handles and the host-side gathers
     prob = named_problem(args.workload)
     ds = DistributedSolver(prob, rank, world, device=local)
-    ds.solver.set_modes(cabi.SWEEP_PERSISTENT, cabi.FACTORS_FULL if args.factors == "full" else cabi.FACTORS_DF)
+    ds.solver.set_modes(cabi.SWEEP_PERSISTENT, {"full": cabi.FACTORS_FULL, "df": cabi.FACTORS_DF, "shared": cabi.FACTORS_SHARED}[args.factors])
     ds.setup(slot=0)
     ref = None
     if rank == 0:
         ref = cabi.Solver(prob, device=local)
-        ref.set_modes(cabi.SWEEP_PERSISTENT, cabi.FACTORS_FULL if args.factors == "full" else cabi.FACTORS_DF)
+        ref.set_modes(cabi.SWEEP_PERSISTENT, {"full": cabi.FACTORS_FULL, "df": cabi.FACTORS_DF, "shared": cabi.FACTORS_SHARED}[args.factors])
         ref.factor_step(); ref.update_state(); ref.eliminate_coupling(prob.forecast.demand[0], prob.forecast.prices[0])
     n = prob.network
     ok = True
