@@ -86,8 +86,13 @@ static rn_status allocate(Handle *h) {
     RN_CHECK(dev_alloc(h, &h->precond, (size_t)d.N * ny)); RN_CHECK(dev_alloc(h, &h->alpha1, nu));
     RN_CHECK(dev_alloc(h, &h->xmin, nx)); RN_CHECK(dev_alloc(h, &h->xmax, nx)); RN_CHECK(dev_alloc(h, &h->xsafe, nx));
     RN_CHECK(dev_alloc(h, &h->umin, nu)); RN_CHECK(dev_alloc(h, &h->umax, nu));
-    RN_CHECK(dev_alloc(h, &h->Phi, n * nv * 2 * nx, false)); RN_CHECK(dev_alloc(h, &h->Psi, n * nv * nu, false));
-    RN_CHECK(dev_alloc(h, &h->D, n * nv * 2 * nx, false)); RN_CHECK(dev_alloc(h, &h->F, n * nv * nu, false));
+    {   // the four per-node factor arrays in one slab, D | F | Phi | Psi (256-byte aligned pieces); D, F first --
+        // RN_FACTORS_DF streams only those
+        const size_t cxi = (n * nv * 2 * nx + 63) & ~size_t(63), cpsi = (n * nv * nu + 63) & ~size_t(63);
+        RN_CHECK(dev_alloc(h, &h->factor_slab, 2 * (cxi + cpsi), false));
+        h->D = h->factor_slab; h->F = h->D + cxi; h->Phi = h->F + cpsi; h->Psi = h->Phi + cxi;
+        h->factor_df_bytes = (cxi + cpsi) * sizeof(float); h->factor_full_bytes = 2 * (cxi + cpsi) * sizeof(float);
+    }
     RN_CHECK(dev_alloc(h, &h->Omega, (size_t)h->n_omega * nv * nv)); RN_CHECK(dev_alloc(h, &h->Theta, (size_t)h->n_omega * nv * nx));
     RN_CHECK(dev_alloc(h, &h->diag, n * ny));
     RN_CHECK(dev_alloc(h, &h->sxmin, n * nx)); RN_CHECK(dev_alloc(h, &h->sxmax, n * nx)); RN_CHECK(dev_alloc(h, &h->sxs, n * nx));

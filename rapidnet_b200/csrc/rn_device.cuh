@@ -42,6 +42,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// the same with an L2 eviction-priority hint (the 64-bit policy encodings of createpolicy: evict_first / evict_last)
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
 __device__ __forceinline__ float clampf(float v, float lo, float hi) {   // projectionBox (Utilities.cu:237-254)
     if (v < lo) return lo; else if (v > hi) return hi; return v;
 }

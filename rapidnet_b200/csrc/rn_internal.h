@@ -58,6 +58,8 @@ struct Handle {
     float *xmin = nullptr, *xmax = nullptr, *xsafe = nullptr, *umin = nullptr, *umax = nullptr;  // unscaled
     // factor-step outputs (reference layouts, + 16 B slack at the end of each streamed array)
     float *Phi = nullptr, *Psi = nullptr, *D = nullptr, *F = nullptr, *Omega = nullptr, *Theta = nullptr;
+    float *factor_slab = nullptr;    // D | F | Phi | Psi live in one allocation
+    size_t factor_df_bytes = 0, factor_full_bytes = 0;
     float *diag = nullptr;           // [nodes][2nx+nu] : s_x | s_xs | s_u
     float *sxmin = nullptr, *sxmax = nullptr, *sxs = nullptr, *sxs_upper = nullptr, *sumin = nullptr, *sumax = nullptr;
     float *sysF_dense = nullptr, *sysG_dense = nullptr;   // lazily materialised for the getters

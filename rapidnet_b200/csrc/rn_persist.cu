@@ -55,6 +55,7 @@ constexpr int kTP = 24;                         // columns of a sweep tile (a ch
 constexpr int kMaxCs = 8;                       // deepest crown supported (stages above the chains)
 constexpr int kDimMax = 128;                    // max(2nx, nu, nv) supported by this kernel
 constexpr int kMaxRanks = 8;                    // GPUs of one node
+constexpr double kL2KeepDefault = 0.1;          // RN_L2_KEEP default: share of the L2 given to evict_last factor matrices
 
 struct PArgs {
     const int *parent, *child_first, *child_count, *omega_idx, *cum, *stages;
@@ -63,6 +64,7 @@ struct PArgs {
     const int *crown_path;                      // [n_crown][kMaxCs]: path root -> node of every crown node (entry k = its stage-k ancestor)
     unsigned int branch_mask;                   // bit s: stage s has more nodes than stage s-1 (the reference's branching stages, :699-719)
     int N, cs, K, nodes, n_crown, n_mats, df_mode, iters, nx, nu, nv, cols_per_chunk, clock_cta;
+    float l2_keep;                              // share of every CTA's stream units whose matrices are loaded with L2 evict_last (0 = plain loads)
     int sh_mode, sh_tile;                       // RN_FACTORS_SHARED: no per-node matrix is read; nodes per tile of its phase S
     int sh_oLt, sh_oC, sh_oGc, sh_oY, sh_oScr2, sh_oVec;   // its shared-memory layout (float offsets; G sits at kOffSweep)
     int n_stages, stage_stride;                 // matrix ring: stages and floats per stage (payload + 32 floats of slack)
@@ -989,6 +991,10 @@ __device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderS
     const float *m0 = P.mat[0], *m1 = P.mat[1], *m2 = P.mat[2], *m3 = P.mat[3];
     const int n_mats = P.n_mats, cols_per_chunk = P.cols_per_chunk, n_stages = P.n_stages, stage_stride = P.stage_stride;
     const int u_begin = R.u_begin, u_end = R.u_end, node_first = R.node_first, node_last = R.node_last;
+    // L2 residency across iterations: the stream reads the same bytes every iteration, and when they exceed the L2 a plain
+    // LRU keeps none of them (cyclic access).  The first u_keep units of the slice are loaded evict_last and the others
+    // evict_first, so that share stays in L2 from one iteration to the next and only the rest comes from HBM.
+    const int u_keep = P.l2_keep > 0.f ? u_begin + (int)(P.l2_keep * (float)(u_end - u_begin)) : -1;
     auto load_vec = [&](int node, int) {
         const size_t ox = (size_t)node * 2 * nx, op = (size_t)node * nu;
         const long long cv_ = clock64();
@@ -1040,7 +1046,9 @@ __device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderS
                 { const long long c_ = clock64(); mbar_wait(&M.empty[st], ph ^ 1); cyc_empty += clock64() - c_; }
                 if (lane == 0) {
                     mbar_expect_tx(&M.full[st], bytes);
-                    bulk_g2s(M.ring + st * stage_stride, reinterpret_cast<const void *>(b0), bytes, &M.full[st]);
+                    if (u_keep < 0) bulk_g2s(M.ring + st * stage_stride, reinterpret_cast<const void *>(b0), bytes, &M.full[st]);
+                    else bulk_g2s_hint(M.ring + st * stage_stride, reinterpret_cast<const void *>(b0), bytes, &M.full[st],
+                                       u < u_keep ? kL2EvictLast : kL2EvictFirst);
                 }
                 __syncwarp();
                 if (++st == n_stages) { st = 0; ph ^= 1; }
@@ -1985,6 +1993,16 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     P.n_mats = h->factor_mode == RN_FACTORS_FULL ? 4 : 2;
     P.df_mode = h->factor_mode != RN_FACTORS_FULL ? 1 : 0;           // v = -1/2 Omega r
     P.sh_mode = h->factor_mode == RN_FACTORS_SHARED ? 1 : 0;          // D xi = G c, F psi = L' g: no per-node matrix
+    {
+        // share of the streamed matrices kept L2-resident across iterations: RN_L2_KEEP x L2 size (x this handle's share of
+        // the SMs, rn_set_grid_limit: lanes share the L2) over the bytes one iteration streams
+        static const char *env = getenv("RN_L2_KEEP");
+        static const double keep_l2 = env ? atof(env) : kL2KeepDefault;
+        const double bytes = h->factor_mode == RN_FACTORS_FULL ? (double)h->factor_full_bytes : (double)h->factor_df_bytes;
+        P.l2_keep = 0.f;
+        if (keep_l2 > 0 && !P.sh_mode && bytes > 0)
+            P.l2_keep = (float)std::min(1.0, keep_l2 * (double)h->l2_bytes * h->persist_grid / h->sm_count / bytes);
+    }
     {
         const SharedLayout SL = shared_layout(h);
         P.sh_tile = SL.tile; P.sh_oLt = SL.oLt; P.sh_oC = SL.oC; P.sh_oGc = SL.oGc; P.sh_oY = SL.oY; P.sh_oScr2 = SL.oScr2; P.sh_oVec = SL.oVec;
