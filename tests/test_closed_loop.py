@@ -57,6 +57,43 @@ def test_closed_loop_two_ranks_equal_one_rank():
     s.close()
 
 
+class _FakeSolver:
+    """Stands in for cabi.Solver on the CPU: a deterministic 'controller' (u0 = a fixed linear map of its inputs) and the
+    reference's plant update x+ = x + B u0, so that the host logic of the drivers can be compared without a GPU."""
+    def __init__(self, prob):
+        n = prob.network
+        self.B = n.B.reshape(n.nu, n.nx).T.astype(np.float64)
+        self.nu, self.calls = n.nu, 0
+
+    def control_action(self, x, up, dp, d_hat, a_hat, iterations, clamp=False):
+        self.calls += 1
+        self.x = np.asarray(x, dtype=np.float64)
+        self.u0 = (1e-3 * np.resize(self.x, self.nu) + 1e-2 * np.resize(d_hat, self.nu) + 0.5 * up + 1e-1 * np.resize(a_hat, self.nu)).astype(np.float32)
+        return self.u0
+
+    def move_forward(self):
+        return (self.x + self.B @ self.u0.astype(np.float64)).astype(np.float32), self.u0.copy()
+
+
+@pytest.mark.parametrize("lanes,world", [(1, 1), (3, 1), (4, 2)])
+def test_lanes_driver_equals_sequential_driver_cpu(lanes, world):
+    """simulate_lanes (one host thread per handle, every lanes-th instance of the rank's share) returns what simulate
+    returns, for every rank, and every instance is solved exactly once."""
+    prob = named_problem("C1", max_iter=5)
+    instances, steps = 11, 2
+    seen = []
+    for rank in range(world):
+        solvers = [_FakeSolver(prob) for _ in range(lanes)]
+        got = closed_loop.simulate_lanes(solvers, prob, instances, steps, 5, rank=rank, world=world)
+        want = closed_loop.simulate(_FakeSolver(prob), prob, instances, steps, 5, rank=rank, world=world)
+        assert sorted(got) == sorted(want) == list(closed_loop.shard(instances, world, rank))
+        for k in want:
+            assert np.array_equal(got[k][0], want[k][0]) and np.array_equal(got[k][1], want[k][1])
+        assert sum(s.calls for s in solvers) == len(got) * steps
+        seen += list(got)
+    assert sorted(seen) == list(range(instances))
+
+
 @pytest.mark.gpu
 def test_lanes_equal_single_handle():
     """Four handles of one GPU, each capped at a quarter of the SMs, solving side by side: same closed-loop trajectories
