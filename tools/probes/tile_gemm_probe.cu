@@ -1,0 +1,203 @@
+// tile_gemm_probe.cu -- micro-benchmark for the sweeps' building block: the product
+// Y[m x 24] = M[m x K] X[K x 24] with everything in shared memory, one CTA of 512 threads per SM, as the persistent kernel
+// runs it six times per chain and iteration (G q, OmegaBar s, L v, B u, and G c, L' g of the shared-factor phase S).
+//   variant 0: the product as rn_persist.cu::tile_gemm does it today -- fp32 FFMA, 256 threads, 2 rows x 12 columns x half of k
+//   variant 1: tensor cores, mma.sync.m16n8k8 TF32 with the 3xTF32 split (hi*hi + lo*hi + hi*lo: fp32-level accuracy),
+//              16 warps = 8 row tiles x 2 halves of k, the halves added through the same scratch area
+//   variant 2: variant 1 with the matrix stored with a padded leading dimension (ld = 8 mod 32: conflict-free fragment loads)
+// Prints ns per product (device clock, mean over the repetitions of the slowest CTA) and the largest error against a
+// double-precision product, relative to max|Y|.
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tile_gemm_probe tile_gemm_probe.cu
+// Run:   ./tile_gemm_probe [reps]
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
+
+constexpr int kPC = 512, kTP = 24;
+
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kPC) : "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+// ---- variant 0: today's FFMA product (copy of the arithmetic; ld = m) ------------------------------------------------------
+__device__ __noinline__ void gemm_ffma(const float *M, int m, int K, const float *X, float *Y, float *scr2) {
+    const int t = threadIdx.x, ks = t >> 7, u = t & 127, rp = u & 63, cg = u >> 6;
+    const bool work = ks < 2 && rp < m;
+    const bool two = rp + 64 < m;
+    float a0[12], a1[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { a0[i] = 0.f; a1[i] = 0.f; }
+    if (work) {
+        const int kh = (K + 1) >> 1, k0 = ks ? kh : 0, k1 = ks ? K : kh;
+        const float *mp = M + (size_t)k0 * m + rp;
+        const int d1 = two ? 64 : 0;
+        const float *xp = X + k0 * kTP + cg * 12;
+#pragma unroll 2
+        for (int k = k0; k < k1; k++, mp += m, xp += kTP) {
+            const float m0 = mp[0], m1 = mp[d1];
+            const float4 x0 = *reinterpret_cast<const float4 *>(xp), x1 = *reinterpret_cast<const float4 *>(xp + 4),
+                         x2 = *reinterpret_cast<const float4 *>(xp + 8);
+            const float xv[12] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w};
+#pragma unroll
+            for (int i = 0; i < 12; i++) { a0[i] = fmaf(m0, xv[i], a0[i]); a1[i] = fmaf(m1, xv[i], a1[i]); }
+        }
+        if (ks == 1) {
+            float *d = scr2 + u * kTP;
+#pragma unroll
+            for (int i = 0; i < 12; i++) { d[i] = a0[i]; d[12 + i] = a1[i]; }
+        }
+    }
+    cbar();
+    if (work && ks == 0) {
+        const float *sp = scr2 + u * kTP;
+#pragma unroll
+        for (int i = 0; i < 12; i++) Y[rp * kTP + cg * 12 + i] = a0[i] + sp[i];
+        if (two) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) Y[(rp + 64) * kTP + cg * 12 + i] = a1[i] + sp[12 + i];
+        }
+    }
+    cbar();
+}
+
+// ---- variants 1, 2: 3xTF32 on mma.sync.m16n8k8 -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tf32_hi(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+    hi = tf32_hi(x);
+    lo = tf32_hi(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// M column-major with leading dimension ldm >= m.  Warp w: row tile w & 7 (rows 16 (w & 7) ..), half w >> 3 of k.
+__device__ __noinline__ void gemm_mma(const float *M, int m, int ldm, int K, const float *X, float *Y, float *scr2) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int mt = warp & 7, kh = warp >> 3;
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    const bool work = mt * 16 < m;
+    float acc[3][4];
+#pragma unroll
+    for (int n = 0; n < 3; n++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[n][i] = 0.f;
+    if (work) {
+        const int ksteps = (K + 7) >> 3, khalf = (ksteps + 1) >> 1;
+        const int s0 = kh ? khalf : 0, s1 = kh ? ksteps : khalf;
+        const int rr0 = min(r0, m - 1), rr1 = min(r1, m - 1);   // rows past m repeat the last row (never stored)
+#pragma unroll 1
+        for (int s = s0; s < s1; s++) {
+            const int ka = s * 8 + t, kb = ka + 4;
+            const bool va = ka < K, vb = kb < K;
+            const int kaa = va ? ka : 0, kbb = vb ? kb : 0;
+            // A fragment: (r0, ka), (r1, ka), (r0, kb), (r1, kb)
+            const float af[4] = {va ? M[rr0 + kaa * ldm] : 0.f, va ? M[rr1 + kaa * ldm] : 0.f, vb ? M[rr0 + kbb * ldm] : 0.f,
+                                 vb ? M[rr1 + kbb * ldm] : 0.f};
+            uint32_t ahi[4], alo[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) split_tf32(af[i], ahi[i], alo[i]);
+#pragma unroll
+            for (int n = 0; n < 3; n++) {
+                // B fragment: (k = ka, col = 8 n + g), (k = kb, col = 8 n + g)
+                const float bf[2] = {va ? X[kaa * kTP + n * 8 + g] : 0.f, vb ? X[kbb * kTP + n * 8 + g] : 0.f};
+                uint32_t bhi[2], blo[2];
+                split_tf32(bf[0], bhi[0], blo[0]); split_tf32(bf[1], bhi[1], blo[1]);
+                mma_tf32(acc[n], alo, bhi);      // small terms first
+                mma_tf32(acc[n], ahi, blo);
+                mma_tf32(acc[n], ahi, bhi);
+            }
+        }
+        if (kh == 1) {
+            float *d = scr2 + ((warp & 7) * 32 + lane) * 12;
+#pragma unroll
+            for (int n = 0; n < 3; n++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) d[n * 4 + i] = acc[n][i];
+        }
+    }
+    cbar();
+    if (work && kh == 0) {
+        const float *sp = scr2 + (warp * 32 + lane) * 12;
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+            const int c = n * 8 + 2 * t;
+            if (r0 < m) *reinterpret_cast<float2 *>(Y + r0 * kTP + c) = make_float2(acc[n][0] + sp[n * 4], acc[n][1] + sp[n * 4 + 1]);
+            if (r1 < m) *reinterpret_cast<float2 *>(Y + r1 * kTP + c) = make_float2(acc[n][2] + sp[n * 4 + 2], acc[n][3] + sp[n * 4 + 3]);
+        }
+    }
+    cbar();
+}
+
+__global__ void __launch_bounds__(kPC, 1) k_probe(int variant, int m, int ldm, int K, const float *Mg, const float *Xg, float *Yg, int reps,
+                                                  unsigned long long *ns_out) {
+    extern __shared__ __align__(128) float smem[];
+    float *M = smem, *X = M + ((ldm * K + 31) & ~31), *Y = X + ((K + 8) * kTP), *scr2 = Y + 128 * kTP;
+    for (int i = threadIdx.x; i < ldm * K; i += kPC) { const int r = i % ldm, k = i / ldm; M[i] = r < m ? Mg[r + (size_t)k * m] : 0.f; }
+    for (int i = threadIdx.x; i < (K + 8) * kTP; i += kPC) X[i] = i < K * kTP ? Xg[i] : 0.f;
+    __syncthreads();
+    const unsigned long long t0 = globaltimer();
+    for (int r = 0; r < reps; r++) {
+        if (variant == 0) gemm_ffma(M, m, K, X, Y, scr2);
+        else gemm_mma(M, m, ldm, K, X, Y, scr2);
+    }
+    const unsigned long long t1 = globaltimer();
+    if (threadIdx.x == 0) ns_out[blockIdx.x] = t1 - t0;
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < m * kTP; i += kPC) Yg[i] = Y[i];
+}
+
+int main(int argc, char **argv) {
+    const int reps = argc > 1 ? atoi(argv[1]) : 200;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int grid = prop.multiProcessorCount;
+    const int shapes[5][2] = {{97, 63}, {97, 97}, {114, 97}, {63, 114}, {97, 114}};   // G, OmegaBar, L, B, L'
+    const char *names[5] = {"G  (nv x nx)", "Om (nv x nv)", "L  (nu x nv)", "B  (nx x nu)", "L' (nv x nu)"};
+    CK(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    unsigned long long *ns_dev;
+    CK(cudaMalloc(&ns_dev, grid * sizeof(unsigned long long)));
+    for (int sidx = 0; sidx < 5; sidx++) {
+        const int m = shapes[sidx][0], K = shapes[sidx][1];
+        std::vector<float> M((size_t)m * K), X((size_t)K * kTP);
+        srand(1234 + sidx);
+        for (auto &v : M) v = (float)rand() / RAND_MAX - 0.5f;
+        for (auto &v : X) v = 1e3f * ((float)rand() / RAND_MAX - 0.5f);
+        std::vector<double> ref((size_t)m * kTP, 0.0);
+        double ymax = 0;
+        for (int r = 0; r < m; r++)
+            for (int c = 0; c < kTP; c++) {
+                double s = 0;
+                for (int k = 0; k < K; k++) s += (double)M[r + (size_t)k * m] * X[(size_t)k * kTP + c];
+                ref[(size_t)r * kTP + c] = s; ymax = fmax(ymax, fabs(s));
+            }
+        float *Md, *Xd, *Yd;
+        CK(cudaMalloc(&Md, M.size() * 4)); CK(cudaMalloc(&Xd, X.size() * 4)); CK(cudaMalloc(&Yd, (size_t)m * kTP * 4));
+        CK(cudaMemcpy(Md, M.data(), M.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(Xd, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
+        for (int variant = 0; variant < 3; variant++) {
+            int ldm = m;
+            if (variant == 2) { ldm = m; while ((ldm & 31) != 8) ldm++; }
+            const size_t smem = ((size_t)((ldm * K + 31) & ~31) + (size_t)(K + 8) * kTP + 128 * kTP + 128 * kTP) * 4;
+            for (int pass = 0; pass < 2; pass++) {   // the first pass warms the instruction cache and the clocks
+                k_probe<<<grid, kPC, smem>>>(variant, m, ldm, K, Md, Xd, Yd, reps, ns_dev);
+                CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+            }
+            std::vector<unsigned long long> ns(grid);
+            std::vector<float> Y((size_t)m * kTP);
+            CK(cudaMemcpy(ns.data(), ns_dev, grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(Y.data(), Yd, Y.size() * 4, cudaMemcpyDeviceToHost));
+            unsigned long long worst = 0;
+            for (auto v : ns) worst = v > worst ? v : worst;
+            double err = 0;
+            for (size_t i = 0; i < Y.size(); i++) err = fmax(err, fabs((double)Y[i] - ref[i]));
+            printf("%s  variant %d (ld %3d): %7.1f ns per product, max err / max|Y| = %.2e\n", names[sidx], variant, ldm,
+                   (double)worst / reps, err / ymax);
+        }
+        cudaFree(Md); cudaFree(Xd); cudaFree(Yd);
+    }
+    return 0;
+}
