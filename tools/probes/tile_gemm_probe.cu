@@ -5,6 +5,9 @@
 //   variant 1: tensor cores, mma.sync.m16n8k8 TF32 with the 3xTF32 split (hi*hi + lo*hi + hi*lo: fp32-level accuracy),
 //              16 warps = 8 row tiles x 2 halves of k, the halves added through the same scratch area
 //   variant 2: variant 1 with the matrix stored with a padded leading dimension (ld = 8 mod 32: conflict-free fragment loads)
+//   variant 3: variant 1 with half the conversions (hi = cvt.rna.tf32, lo = x - hi passed as raw fp32 bits: the tensor core
+//              truncates it, an error of 2^-21 of x) and the operands of step s+1 loaded before the MMAs of step s
+//   variant 4: FFMA on all 512 threads: 1 row x 12 columns x half of k per thread (twice the right-hand-side loads)
 // Prints ns per product (device clock, mean over the repetitions of the slowest CTA) and the largest error against a
 // double-precision product, relative to max|Y|.
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tile_gemm_probe tile_gemm_probe.cu
@@ -134,6 +137,110 @@ __device__ __noinline__ void gemm_mma(const float *M, int m, int ldm, int K, con
     cbar();
 }
 
+
+// ---- variant 3: fewer conversions, software-pipelined k loop -----------------------------------------------------------------
+struct Frag { float a[4]; float b[3][2]; };
+__device__ __forceinline__ void load_frag(Frag &f, const float *M, int ldm, int K, const float *X, int rr0, int rr1, int s, int t, int g) {
+    const int ka = s * 8 + t, kb = ka + 4;
+    const bool va = ka < K, vb = kb < K;
+    const int kaa = va ? ka : 0, kbb = vb ? kb : 0;
+    f.a[0] = va ? M[rr0 + kaa * ldm] : 0.f; f.a[1] = va ? M[rr1 + kaa * ldm] : 0.f;
+    f.a[2] = vb ? M[rr0 + kbb * ldm] : 0.f; f.a[3] = vb ? M[rr1 + kbb * ldm] : 0.f;
+#pragma unroll
+    for (int n = 0; n < 3; n++) { f.b[n][0] = va ? X[kaa * kTP + n * 8 + g] : 0.f; f.b[n][1] = vb ? X[kbb * kTP + n * 8 + g] : 0.f; }
+}
+__device__ __forceinline__ void mma_frag(float (&acc)[3][4], const Frag &f) {
+    uint32_t ahi[4], alo[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { ahi[i] = tf32_hi(f.a[i]); alo[i] = __float_as_uint(f.a[i] - __uint_as_float(ahi[i])); }
+#pragma unroll
+    for (int n = 0; n < 3; n++) {
+        uint32_t bhi[2], blo[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) { bhi[i] = tf32_hi(f.b[n][i]); blo[i] = __float_as_uint(f.b[n][i] - __uint_as_float(bhi[i])); }
+        mma_tf32(acc[n], alo, bhi);
+        mma_tf32(acc[n], ahi, blo);
+        mma_tf32(acc[n], ahi, bhi);
+    }
+}
+__device__ __noinline__ void gemm_mma_pipe(const float *M, int m, int ldm, int K, const float *X, float *Y, float *scr2) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int mt = warp & 7, kh = warp >> 3;
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    const bool work = mt * 16 < m;
+    float acc[3][4];
+#pragma unroll
+    for (int n = 0; n < 3; n++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[n][i] = 0.f;
+    if (work) {
+        const int ksteps = (K + 7) >> 3, khalf = (ksteps + 1) >> 1;
+        const int s0 = kh ? khalf : 0, s1 = kh ? ksteps : khalf;
+        const int rr0 = min(r0, m - 1), rr1 = min(r1, m - 1);
+        Frag cur, nxt;
+        if (s0 < s1) load_frag(cur, M, ldm, K, X, rr0, rr1, s0, t, g);
+#pragma unroll 1
+        for (int s = s0; s < s1; s++) {
+            if (s + 1 < s1) load_frag(nxt, M, ldm, K, X, rr0, rr1, s + 1, t, g);
+            mma_frag(acc, cur);
+            cur = nxt;
+        }
+        if (kh == 1) {
+            float *d = scr2 + ((warp & 7) * 32 + lane) * 12;
+#pragma unroll
+            for (int n = 0; n < 3; n++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) d[n * 4 + i] = acc[n][i];
+        }
+    }
+    cbar();
+    if (work && kh == 0) {
+        const float *sp = scr2 + (warp * 32 + lane) * 12;
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+            const int c = n * 8 + 2 * t;
+            if (r0 < m) *reinterpret_cast<float2 *>(Y + r0 * kTP + c) = make_float2(acc[n][0] + sp[n * 4], acc[n][1] + sp[n * 4 + 1]);
+            if (r1 < m) *reinterpret_cast<float2 *>(Y + r1 * kTP + c) = make_float2(acc[n][2] + sp[n * 4 + 2], acc[n][3] + sp[n * 4 + 3]);
+        }
+    }
+    cbar();
+}
+
+// ---- variant 4: FFMA on all 512 threads, 1 row x 12 columns x half of k ------------------------------------------------------
+__device__ __noinline__ void gemm_ffma512(const float *M, int m, int K, const float *X, float *Y, float *scr2) {
+    const int t = threadIdx.x, ks = t >> 8, u = t & 255, rp = u & 127, cg = u >> 7;
+    const bool work = rp < m;
+    float a0[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) a0[i] = 0.f;
+    if (work) {
+        const int kh = (K + 1) >> 1, k0 = ks ? kh : 0, k1 = ks ? K : kh;
+        const float *mp = M + (size_t)k0 * m + rp;
+        const float *xp = X + k0 * kTP + cg * 12;
+#pragma unroll 4
+        for (int k = k0; k < k1; k++, mp += m, xp += kTP) {
+            const float m0 = mp[0];
+            const float4 x0 = *reinterpret_cast<const float4 *>(xp), x1 = *reinterpret_cast<const float4 *>(xp + 4),
+                         x2 = *reinterpret_cast<const float4 *>(xp + 8);
+            const float xv[12] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w};
+#pragma unroll
+            for (int i = 0; i < 12; i++) a0[i] = fmaf(m0, xv[i], a0[i]);
+        }
+        if (ks == 1) {
+            float *d = scr2 + u * 12;
+#pragma unroll
+            for (int i = 0; i < 12; i++) d[i] = a0[i];
+        }
+    }
+    cbar();
+    if (work && ks == 0) {
+        const float *sp = scr2 + u * 12;
+#pragma unroll
+        for (int i = 0; i < 12; i++) Y[rp * kTP + cg * 12 + i] = a0[i] + sp[i];
+    }
+    cbar();
+}
+
 __global__ void __launch_bounds__(kPC, 1) k_probe(int variant, int m, int ldm, int K, const float *Mg, const float *Xg, float *Yg, int reps,
                                                   unsigned long long *ns_out) {
     extern __shared__ __align__(128) float smem[];
@@ -144,6 +251,8 @@ __global__ void __launch_bounds__(kPC, 1) k_probe(int variant, int m, int ldm, i
     const unsigned long long t0 = globaltimer();
     for (int r = 0; r < reps; r++) {
         if (variant == 0) gemm_ffma(M, m, K, X, Y, scr2);
+        else if (variant == 3) gemm_mma_pipe(M, m, ldm, K, X, Y, scr2);
+        else if (variant == 4) gemm_ffma512(M, m, K, X, Y, scr2);
         else gemm_mma(M, m, ldm, K, X, Y, scr2);
     }
     const unsigned long long t1 = globaltimer();
@@ -156,12 +265,12 @@ int main(int argc, char **argv) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     const int grid = prop.multiProcessorCount;
-    const int shapes[5][2] = {{97, 63}, {97, 97}, {114, 97}, {63, 114}, {97, 114}};   // G, OmegaBar, L, B, L'
-    const char *names[5] = {"G  (nv x nx)", "Om (nv x nv)", "L  (nu x nv)", "B  (nx x nu)", "L' (nv x nu)"};
+    const int shapes[6][2] = {{97, 63}, {97, 97}, {114, 97}, {63, 114}, {97, 114}, {97, 8}};   // G, OmegaBar, L, B, L', and k = 8: the fixed cost
+    const char *names[6] = {"G  (nv x nx)", "Om (nv x nv)", "L  (nu x nv)", "B  (nx x nu)", "L' (nv x nu)", "fixed (k = 8)"};
     CK(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     unsigned long long *ns_dev;
     CK(cudaMalloc(&ns_dev, grid * sizeof(unsigned long long)));
-    for (int sidx = 0; sidx < 5; sidx++) {
+    for (int sidx = 0; sidx < 6; sidx++) {
         const int m = shapes[sidx][0], K = shapes[sidx][1];
         std::vector<float> M((size_t)m * K), X((size_t)K * kTP);
         srand(1234 + sidx);
@@ -178,7 +287,7 @@ int main(int argc, char **argv) {
         float *Md, *Xd, *Yd;
         CK(cudaMalloc(&Md, M.size() * 4)); CK(cudaMalloc(&Xd, X.size() * 4)); CK(cudaMalloc(&Yd, (size_t)m * kTP * 4));
         CK(cudaMemcpy(Md, M.data(), M.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(Xd, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
-        for (int variant = 0; variant < 3; variant++) {
+        for (int variant = 0; variant < 5; variant++) {
             int ldm = m;
             if (variant == 2) { ldm = m; while ((ldm & 31) != 8) ldm++; }
             const size_t smem = ((size_t)((ldm * K + 31) & ~31) + (size_t)(K + 8) * kTP + 128 * kTP + 128 * kTP) * 4;
