@@ -74,6 +74,8 @@ Engine::Engine(SmpcConfiguration *smpcConfig) {
         else if (v != "persistent") { std::cerr << "rapidnet_b200: RAPIDNET_SWEEP=" << v << " is not persistent|chain|per_stage" << std::endl; std::exit(EXIT_FAILURE); }
     }
     check(rn_set_modes(h, sm, fm), "rn_set_modes");
+    // RAPIDNET_GRID_LIMIT: share of the SMs for this Engine's persistent kernel when several controllers run side by side
+    if (const char *e = std::getenv("RAPIDNET_GRID_LIMIT")) check(rn_set_grid_limit(h, std::atoi(e)), "rn_set_grid_limit");
 }
 
 Engine::~Engine() {

@@ -19,6 +19,9 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <chrono>
+#include <thread>
+#include <vector>
 
 #include "rapidjson/document.h"
 #include "rapidjson/filereadstream.h"
@@ -287,11 +290,61 @@ static int closed_loop(const std::string &cfgPath, int steps, const std::string 
     return 0;
 }
 
+// ---- closed-loop lanes: several controllers of ONE GPU side by side (closed-loop Monte-Carlo instances, BASELINE config[3]).
+// main.cu:27-63 runs one controller; here `lanes` SmpcController objects, each with its own Engine (= library handle and
+// CUDA stream) and its own host thread, run the same loop concurrently.  RAPIDNET_GRID_LIMIT gives each Engine a share of
+// the SMs.  All lanes get the same inputs here, so every lane must produce the same controls as lane 0, bit for bit.
+static int closed_loop_lanes(const std::string &cfgPath, int steps, int lanes, const std::string &outPath) {
+    std::vector<SmpcController *> ctl(lanes, nullptr);
+    for (int l = 0; l < lanes; l++) ctl[l] = new SmpcController(cfgPath);
+    const uint_t nu = ctl[0]->getSmpcConfiguration()->getNU();
+    std::vector<std::vector<real_t>> u0(lanes, std::vector<real_t>((size_t)steps * nu, 0.f));
+    std::vector<int> ok(lanes, 1);
+    auto run = [&](int l) {
+        std::fstream ctrl(outPath + ".control" + std::to_string(l), std::fstream::out);
+        for (int t = 0; t < steps; t++) {
+            if (ctl[l]->getForecaster()->predictDemand(t) != 1 || ctl[l]->getForecaster()->predictPrices(t) != 1) { ok[l] = 0; return; }
+            if (t == 0) ctl[l]->initialiseSmpcController();
+            if (ctl[l]->controlAction(u0[l].data() + (size_t)t * nu) != 1) { ok[l] = 0; return; }
+            if (ctl[l]->controlAction(ctrl) != 1) { ok[l] = 0; return; }
+            ctl[l]->moveForewardInTime();
+        }
+    };
+    run(0);                                                    // warm-up on lane 0 alone (also the sequential timing)
+    const auto t0 = std::chrono::steady_clock::now();
+    run(0);
+    const double one_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const auto t1 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int l = 0; l < lanes; l++) th.emplace_back(run, l);
+    for (auto &t : th) t.join();
+    const double all_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    int same = 1;
+    for (int l = 0; l < lanes; l++) {
+        T_ASSERT(ok[l] == 1);
+        // lane 0 has moved forward twice before (warm-up + timing): compare the lanes that started from the same state
+        if (l > 1 && std::memcmp(u0[l].data(), u0[1].data(), u0[l].size() * sizeof(real_t)) != 0) same = 0;
+    }
+    std::ofstream out(outPath);
+    out << std::setprecision(9) << "{\"lanes\": " << lanes << ", \"steps\": " << steps << ", \"ms_one_lane\": " << one_ms
+        << ", \"ms_all_lanes\": " << all_ms << ", \"solves_per_s_one\": " << steps / (one_ms * 1e-3) << ", \"solves_per_s_lanes\": "
+        << (double)lanes * steps / (all_ms * 1e-3) << ", \"lanes_identical\": " << same << ", \"u0_lane1\": [";
+    const int ref = lanes > 1 ? 1 : 0;
+    for (size_t i = 0; i < u0[ref].size(); i++) out << (i ? ", " : "") << u0[ref][i];
+    out << "]}" << std::endl;
+    for (auto *c : ctl) delete c;
+    T_ASSERT(same == 1);
+    std::cout << "host_tests lanes: ok (" << lanes << " lanes, " << steps / (one_ms * 1e-3) << " -> " << (double)lanes * steps / (all_ms * 1e-3)
+              << " solves/s)" << std::endl;
+    return 0;
+}
+
 int main(int argc, char **argv) {
-    if (argc < 3) { std::cerr << "usage: host_tests loaders|engine|smpc|closedloop <controllerConfig.json> ..." << std::endl; return 2; }
+    if (argc < 3) { std::cerr << "usage: host_tests loaders|engine|smpc|closedloop|lanes <controllerConfig.json> ..." << std::endl; return 2; }
     const std::string mode = argv[1], cfg = argv[2];
     if (mode == "loaders") return test_loaders(cfg);
     if (mode == "closedloop") { T_ASSERT(argc >= 5); return closed_loop(cfg, std::atoi(argv[3]), argv[4]); }
+    if (mode == "lanes") { T_ASSERT(argc >= 6); return closed_loop_lanes(cfg, std::atoi(argv[3]), std::atoi(argv[4]), argv[5]); }
     T_ASSERT(argc >= 4);
     rapidjson::Document eg;
     parse(argv[3], eg);

@@ -106,3 +106,37 @@ def test_closed_loop_matches_ctypes_path(tmp_path, factors):
         x, up, dp = xn, ua, fc.demand[t][: prob.network.nd].astype(np.float32)
     assert np.isfinite(res["economic_kpi"]) and res["steps"][0]["ms"] > 0
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("RN_RUN_UNVALIDATED") != "1",
+                    reason="host_tests 'lanes' was written after round 1's GPU budget was spent: run once with "
+                           "RN_RUN_UNVALIDATED=1 on a B200, then remove this gate")
+def test_cpp_lanes_side_by_side(tmp_path):
+    """Four SmpcController objects of one GPU, each with its own Engine / stream / host thread and a quarter of the SMs
+    (RAPIDNET_GRID_LIMIT), run main.cu's closed loop concurrently: every lane gives the same controls (same inputs), equal
+    to the ctypes path with the same grid cap."""
+    import torch
+    from rapidnet_b200 import cabi
+    from rapidnet_b200.datagen import named_problem
+    prob = named_problem("C1r6", max_iter=40)
+    cfg = write_problem(prob, str(tmp_path))
+    cap = max(8, torch.cuda.get_device_properties(0).multi_processor_count // 4)
+    out = tmp_path / "lanes.json"
+    _run("lanes", cfg, 2, 4, out, env={"RAPIDNET_GRID_LIMIT": str(cap), "RAPIDNET_FACTORS": "shared"})
+    res = json.load(open(out))
+    assert res["lanes"] == 4 and res["lanes_identical"] == 1 and res["solves_per_s_lanes"] > 0
+    c, fc = prob.config, prob.forecast
+    s = cabi.Solver(prob)
+    s.set_modes(cabi.SWEEP_PERSISTENT, cabi.FACTORS_SHARED)
+    s.set_grid_limit(cap)
+    s.factor_step()
+    x, up, dp = c.current_x.copy(), c.prev_u.copy(), c.prev_demand.copy()
+    u = []
+    for t in range(2):
+        u.append(s.control_action(x, up, dp, fc.demand[t], fc.prices[t], 40).copy())
+        s.control_action(x, up, dp, fc.demand[t], fc.prices[t], 40, clamp=True)
+        x, up = s.move_forward()
+        dp = fc.demand[t][: prob.network.nd].astype(np.float32)
+    assert np.array_equal(np.float32(res["u0_lane1"]), np.concatenate(u))
+    s.close()

@@ -17,5 +17,5 @@ FLAGS=(-std=c++17 -O2 -fPIC -Wall -Wno-class-memaccess -I"$ROOT/include" -isyste
 "$CXX" "${FLAGS[@]}" -shared -o "$SRC/librapidnet_host.so" "$SRC/loaders.cpp" "$SRC/engine.cpp" \
     -L"$ROOT/rapidnet_b200" -lrapidnet_b200 -Wl,-rpath,'$ORIGIN/..'
 "$CXX" "${FLAGS[@]}" -o "$SRC/host_tests" "$SRC/host_tests.cpp" -L"$SRC" -lrapidnet_host -L"$ROOT/rapidnet_b200" -lrapidnet_b200 \
-    -L"$CUDA/lib64" -lcudart -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/..'
+    -L"$CUDA/lib64" -lcudart -pthread -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/..'
 echo "built $SRC/librapidnet_host.so $SRC/host_tests"
