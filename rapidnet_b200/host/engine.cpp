@@ -3,9 +3,13 @@
 //   SmpcController  /root/reference/src/SmpcController.cu:32-116 (ctors), :476-487, :535-864 (steps), :1500-1525 (APG),
 //                   :1593-1667 (controller calls), :1679-1717 (moveForewardInTime), :1778-1859 (KPIs)
 // Error behaviour as in the reference (_CUDA / _CUBLAS / _ASSERT, src/Configuration.h:38-81): print and exit.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
+
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
 
 #include "rapidnet_host.hpp"
 
@@ -78,10 +82,96 @@ Engine::Engine(SmpcConfiguration *smpcConfig) {
     if (const char *e = std::getenv("RAPIDNET_GRID_LIMIT")) check(rn_set_grid_limit(h, std::atoi(e)), "rn_set_grid_limit");
 }
 
+// Engine.cuh:246.  The library does not use cuBLAS; a handle is created on first request for callers that expect the
+// Engine to own one (the reference creates it in its constructor, Engine.cu:139).
+cublasHandle_t Engine::getCublasHandle() {
+    if (!cublasHandle && cublasCreate(&cublasHandle) != CUBLAS_STATUS_SUCCESS) {
+        std::cerr << "rapidnet_b200: cublasCreate failed" << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
+    return cublasHandle;
+}
+
 Engine::~Engine() {
+    if (cublasHandle) cublasDestroy(cublasHandle);
+    for (void *p : ownedDevice) cudaFree(p);
     if (h) rn_destroy(h);
     delete ptrMyNetwork;
     delete ptrMyScenarioTree;
+}
+
+void *Engine::toDevice(const void *host, size_t bytes) {
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes ? bytes : 1) != cudaSuccess || cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        std::cerr << "rapidnet_b200: device copy of " << bytes << " bytes failed: " << cudaGetErrorString(cudaGetLastError()) << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
+    ownedDevice.push_back(d);
+    return d;
+}
+
+// Engine.cu:80-110, 191-230 (factor matrices), :336-360 (system matrices)
+real_t **Engine::ptrTable(PtrTableId id) {
+    if (devPtrTables[id]) return devPtrTables[id];
+    ScenarioTree *t = ptrMyScenarioTree;
+    const size_t nodes = t->getNumNodes(), N = t->getPredHorizon(), K = t->getNumScenarios();
+    const size_t nx = ptrMySmpcConfig->getNX(), nu = ptrMySmpcConfig->getNU(), nv = ptrMySmpcConfig->getNV();
+    const uint_t *nps = t->getNodesPerStage(), *cum = t->getNodesPerStageCumul();
+    const size_t fb = t->getFinalBranchNode();
+    std::vector<real_t *> tab(id == PT_G ? K : nodes, nullptr);
+    auto per_node = [&](real_t *base, size_t stride) { for (size_t i = 0; i < tab.size(); i++) tab[i] = base + i * stride; };
+    auto shared = [&](real_t *base) { for (size_t i = 0; i < tab.size(); i++) tab[i] = base; };
+    auto aliased = [&](real_t *base, size_t stride) {   // Engine.cu:210-221
+        for (size_t s = 0; s < N; s++)
+            for (size_t j = 0; j < (size_t)nps[s]; j++) {
+                const size_t c0 = (size_t)cum[s], cur = fb <= c0 ? fb - K + j : c0 + j;
+                tab[c0 + j] = base + cur * stride;
+            }
+    };
+    switch (id) {
+        case PT_PHI: per_node(getMatPhi(), nv * 2 * nx); break;
+        case PT_PSI: per_node(getMatPsi(), nv * nu); break;
+        case PT_D: per_node(getMatD(), nv * 2 * nx); break;
+        case PT_F: per_node(getMatF(), nv * nu); break;
+        case PT_SIGMA: per_node(getMatSigma(), nv); break;
+        case PT_OMEGA: aliased(getMatOmega(), nv * nv); break;
+        case PT_THETA: aliased(getMatTheta(), nx * nv); break;
+        case PT_G: shared(getMatG()); break;
+        case PT_SYS_B: shared(getSysMatB()); break;
+        case PT_SYS_L: shared(getSysMatL()); break;
+        case PT_SYS_LHAT: shared(getSysMatLhat()); break;
+        case PT_SYS_F: per_node(getSysMatF(), 2 * nx * nx); break;
+        case PT_SYS_G: per_node(getSysMatG(), nu * nu); break;
+        default: break;
+    }
+    devPtrTables[id] = static_cast<real_t **>(toDevice(tab.data(), tab.size() * sizeof(real_t *)));
+    return devPtrTables[id];
+}
+
+// Engine.cu:256-290: the host arrays of ScenarioTree, copied as they are
+uint_t *Engine::treeU(int which) {
+    if (devTreeU[which]) return devTreeU[which];
+    ScenarioTree *t = ptrMyScenarioTree;
+    const size_t nodes = t->getNumNodes(), N = t->getPredHorizon(), K = t->getNumScenarios(), nl = t->getNumNonleafNodes();
+    const std::vector<uint_t> *src[7] = {&t->stageArray, &t->nodesPerStage, &t->nodesPerStageCumul, &t->leaveArray, &t->nChildArray,
+                                         &t->ancestorArray, &t->nChildCumulArray};
+    const size_t cnt[7] = {nodes, N + 1, N + 2, K, nl, nodes, nodes};   // the sizes the reference allocates (Engine.cu:256-262)
+    std::vector<uint_t> host(cnt[which], 0);
+    for (size_t i = 0; i < host.size() && i < src[which]->size(); i++) host[i] = (*src[which])[i];
+    devTreeU[which] = static_cast<uint_t *>(toDevice(host.data(), host.size() * sizeof(uint_t)));
+    return devTreeU[which];
+}
+
+real_t *Engine::treeF(int which) {
+    if (devTreeF[which]) return devTreeF[which];
+    ScenarioTree *t = ptrMyScenarioTree;
+    const size_t nodes = t->getNumNodes(), nd = ptrMySmpcConfig->getND(), nu = ptrMySmpcConfig->getNU();
+    const std::vector<real_t> *src[3] = {&t->probNodeArray, &t->errorDemandArray, &t->errorPriceArray};
+    const size_t cnt[3] = {nodes, nodes * nd, nodes * nu};
+    std::vector<real_t> host(cnt[which], 0.f);
+    for (size_t i = 0; i < host.size() && i < src[which]->size(); i++) host[i] = (*src[which])[i];
+    devTreeF[which] = static_cast<real_t *>(toDevice(host.data(), host.size() * sizeof(real_t)));
+    return devTreeF[which];
 }
 
 real_t *Engine::buf(rn_buffer_id id) {
@@ -252,6 +342,27 @@ void SmpcController::moveForewardInTime() {
         ptrMySmpcConfig->setPreviousControl();
         ptrMySmpcConfig->setPreviousDemand();
     }
+}
+
+// Stand-alone form of the infeasibility measure (SmpcController.cu:1480-1496): signed residual at the arg-max-abs of each
+// block, the larger of the two.  Inside algorithmApg the persistent kernel logs the same quantity per iteration
+// (vecPrimalInfs); this one serves callers that drive the steps by hand, with the same two cuBLAS calls as the reference.
+real_t SmpcController::updatePrimalInfeasibity() {
+    refreshDevicePointers();
+    check(rn_sync(ptrMyEngine->handle()), "rn_sync");
+    const int nx = (int)ptrMyEngine->getDwnNetwork()->getNumTanks(), nu = (int)ptrMyEngine->getDwnNetwork()->getNumControls();
+    const int nodes = (int)ptrMyEngine->getScenarioTree()->getNumNodes();
+    cublasHandle_t cb = ptrMyEngine->getCublasHandle();
+    int ixi = 0, ipsi = 0;
+    real_t vxi = 0, vpsi = 0;
+    if (cublasIsamax(cb, 2 * nx * nodes, devVecFixedPointResidualXi, 1, &ixi) != CUBLAS_STATUS_SUCCESS ||
+        cublasIsamax(cb, nu * nodes, devVecFixedPointResidualPsi, 1, &ipsi) != CUBLAS_STATUS_SUCCESS ||
+        cudaMemcpy(&vxi, devVecFixedPointResidualXi + (ixi - 1), sizeof(real_t), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(&vpsi, devVecFixedPointResidualPsi + (ipsi - 1), sizeof(real_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        std::cerr << "rapidnet_b200: SmpcController::updatePrimalInfeasibity failed" << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
+    return std::max(vxi, vpsi);
 }
 
 void SmpcController::updateKpi(real_t *state, real_t *control) {

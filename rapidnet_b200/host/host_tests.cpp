@@ -179,6 +179,7 @@ public:
     using SmpcController::SmpcController;
     int testEngine(const rapidjson::Document &g);
     int testApgSteps(const rapidjson::Document &g);
+    int testSurface();
 };
 
 static void prepare(TestSmpcController &ctl, const rapidjson::Document &engineGolden) {
@@ -253,6 +254,71 @@ int TestSmpcController::testApgSteps(const rapidjson::Document &g) {
     dualUpdate();
     T_ASSERT(smpc_close(devVecUpdateXi, arr(g, "finalUpdateXi")) && smpc_close(devVecUpdatePsi, arr(g, "finalUpdatePsi")));
     std::cout << "host_tests smpc: ok" << std::endl;
+    return 0;
+}
+
+// ---- the rest of the Engine / SmpcController surface: per-node pointer tables (Engine.cuh:128-230), the tree on the device
+// (Engine.cuh:252-288), the cuBLAS handle, and the stand-alone infeasibility measure against the kernel's own log
+int TestSmpcController::testSurface() {
+    Engine *e = getEngine();
+    ScenarioTree *tree = getScenarioTree();
+    const size_t nx = getDwnNetwork()->getNumTanks(), nu = getDwnNetwork()->getNumControls(), nv = getSmpcConfiguration()->getNV();
+    const size_t nodes = tree->getNumNodes(), N = tree->getPredHorizon(), K = tree->getNumScenarios(), fb = tree->getFinalBranchNode();
+    auto table = [&](real_t **dev, size_t n) {
+        std::vector<real_t *> h(n);
+        T_ASSERT(cudaMemcpy(h.data(), dev, n * sizeof(real_t *), cudaMemcpyDeviceToHost) == cudaSuccess);
+        return h;
+    };
+    const std::vector<real_t *> phi = table(e->getPtrMatPhi(), nodes), psi = table(e->getPtrMatPsi(), nodes), d = table(e->getPtrMatD(), nodes),
+                                f = table(e->getPtrMatF(), nodes), sg = table(e->getPtrMatSigma(), nodes), om = table(e->getPtrMatOmega(), nodes),
+                                th = table(e->getPtrMatTheta(), nodes), g = table(e->getPtrMatG(), K), sb = table(e->getPtrSysMatB(), nodes),
+                                sl = table(e->getPtrSysMatL(), nodes), slh = table(e->getPtrSysMatLhat(), nodes),
+                                sf = table(e->getPtrSysMatF(), nodes), sgg = table(e->getPtrSysMatG(), nodes);
+    for (size_t i = 0; i < nodes; i++) {
+        T_ASSERT(phi[i] == e->getMatPhi() + i * nv * 2 * nx && psi[i] == e->getMatPsi() + i * nv * nu);
+        T_ASSERT(d[i] == e->getMatD() + i * nv * 2 * nx && f[i] == e->getMatF() + i * nv * nu && sg[i] == e->getMatSigma() + i * nv);
+        T_ASSERT(sb[i] == e->getSysMatB() && sl[i] == e->getSysMatL() && slh[i] == e->getSysMatLhat());
+        T_ASSERT(sf[i] == e->getSysMatF() + i * 2 * nx * nx && sgg[i] == e->getSysMatG() + i * nu * nu);
+    }
+    for (size_t k = 0; k < K; k++) T_ASSERT(g[k] == e->getMatG());
+    for (size_t s = 0; s < N; s++)
+        for (size_t j = 0; j < (size_t)tree->getNodesPerStage()[s]; j++) {
+            const size_t c0 = tree->getNodesPerStageCumul()[s], cur = fb <= c0 ? fb - K + j : c0 + j;   // Engine.cu:210-221
+            T_ASSERT(om[c0 + j] == e->getMatOmega() + cur * nv * nv && th[c0 + j] == e->getMatTheta() + cur * nx * nv);
+        }
+    // the matrices behind the tables are the ones the getters return: Phi of the last node through its table entry
+    {
+        const std::vector<real_t> a = from_device(phi[nodes - 1], nv * 2 * nx), b = from_device(e->getMatPhi() + (nodes - 1) * nv * 2 * nx, nv * 2 * nx);
+        T_ASSERT(std::memcmp(a.data(), b.data(), a.size() * sizeof(real_t)) == 0);
+    }
+    auto treeu = [&](uint_t *dev, const uint_t *host, size_t n) {
+        std::vector<uint_t> h(n);
+        T_ASSERT(cudaMemcpy(h.data(), dev, n * sizeof(uint_t), cudaMemcpyDeviceToHost) == cudaSuccess);
+        T_ASSERT(std::memcmp(h.data(), host, n * sizeof(uint_t)) == 0);
+    };
+    treeu(e->getTreeStages(), tree->getStageNodes(), nodes);
+    treeu(e->getTreeNodesPerStage(), tree->getNodesPerStage(), N + 1);
+    treeu(e->getTreeNodesPerStageCumul(), tree->getNodesPerStageCumul(), N + 2);
+    treeu(e->getTreeLeaves(), tree->getLeaveArray(), K);
+    treeu(e->getTreeNumChildren(), tree->getNumChildren(), tree->getNumNonleafNodes());
+    treeu(e->getTreeAncestor(), tree->getAncestorArray(), nodes);
+    treeu(e->getTreeNumChildrenCumul(), tree->getNumChildrenCumul(), nodes);
+    {
+        const std::vector<real_t> p = from_device(e->getTreeProb(), nodes);
+        T_ASSERT(std::memcmp(p.data(), tree->getProbArray(), nodes * sizeof(real_t)) == 0);
+        const std::vector<real_t> ed = from_device(e->getTreeErrorDemand(), nodes * getSmpcConfiguration()->getND());
+        T_ASSERT(std::memcmp(ed.data(), tree->getErrorDemandArray(), ed.size() * sizeof(real_t)) == 0);
+        const std::vector<real_t> ep = from_device(e->getTreeErrorPrices(), nodes * nu);
+        T_ASSERT(std::memcmp(ep.data(), tree->getErrorPriceArray(), ep.size() * sizeof(real_t)) == 0);
+    }
+    T_ASSERT(e->getCublasHandle() != nullptr && e->getCublasHandle() == e->getCublasHandle());
+    // updatePrimalInfeasibity (:1480-1496) after the loop == the last entry the kernel logged
+    T_ASSERT(algorithmApg() == 1);
+    const uint_t iters = getSmpcConfiguration()->getMaxIterations();
+    const real_t standalone = updatePrimalInfeasibity(), logged = getPrimalInfeasibility()[iters - 1];
+    std::cout << "primal infeasibility: stand-alone " << standalone << ", logged by the kernel " << logged << std::endl;
+    T_ASSERT(standalone == logged);
+    std::cout << "host_tests surface: ok" << std::endl;
     return 0;
 }
 
@@ -340,7 +406,7 @@ static int closed_loop_lanes(const std::string &cfgPath, int steps, int lanes, c
 }
 
 int main(int argc, char **argv) {
-    if (argc < 3) { std::cerr << "usage: host_tests loaders|engine|smpc|closedloop|lanes <controllerConfig.json> ..." << std::endl; return 2; }
+    if (argc < 3) { std::cerr << "usage: host_tests loaders|engine|smpc|surface|closedloop|lanes <controllerConfig.json> ..." << std::endl; return 2; }
     const std::string mode = argv[1], cfg = argv[2];
     if (mode == "loaders") return test_loaders(cfg);
     if (mode == "closedloop") { T_ASSERT(argc >= 5); return closed_loop(cfg, std::atoi(argv[3]), argv[4]); }
@@ -351,6 +417,7 @@ int main(int argc, char **argv) {
     TestSmpcController ctl(cfg);
     prepare(ctl, eg);
     if (mode == "engine") return ctl.testEngine(eg);
+    if (mode == "surface") return ctl.testSurface();
     if (mode == "smpc") {
         T_ASSERT(argc >= 5);
         rapidjson::Document sg;

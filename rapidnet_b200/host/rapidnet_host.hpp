@@ -23,6 +23,10 @@
 
 #include "../../include/rapidnet_b200.h"
 
+// the declaration of cublas_api.h, repeated so that this header does not pull in cuBLAS (Engine::getCublasHandle)
+struct cublasContext;
+typedef struct cublasContext *cublasHandle_t;
+
 namespace rapidnet {
 
 typedef float real_t;   // /root/reference/src/Configuration.h:30-31
@@ -75,6 +79,7 @@ public:
     real_t *getErrorPriceArray() { return errorPriceArray.data(); }
 
 private:
+    friend class Engine;   // device copies of the arrays (Engine::getTree*)
     uint_t nPredHorizon = 0, nScenario = 0, nNodes = 0, nChildrenTot = 0, nNonLeafNodes = 0;
     std::vector<uint_t> stageArray, nodesPerStage, nodesPerStageCumul, leaveArray, childArray, ancestorArray, nChildArray,
         nChildCumulArray;
@@ -185,10 +190,52 @@ public:
     bool getNamaFlag() { return namaFlag; }
     void setPriceUncertaintyFlag(bool inputFlag);
     void setDemandUncertaintyFlag(bool inputFlag);
+    // Per-node pointer tables on the device (Engine.cuh:128-230; built by Engine.cu:80-110, 191-230, 336-360): entry i points at
+    // node i's matrix inside the packed arrays above.  The library itself does not use them (its kernels index the packed
+    // arrays); they are built on first use for callers that feed cuBLAS batched routines the way the reference does.
+    // Omega / Theta alias from the final branching node on (Engine.cu:210-221); B, L, Lhat and G exist once here (the
+    // reference keeps one copy per scenario), so every entry of those tables points at the same matrix.
+    real_t **getPtrSysMatB() { return ptrTable(PT_SYS_B); }
+    real_t **getPtrSysMatF() { return ptrTable(PT_SYS_F); }
+    real_t **getPtrSysMatG() { return ptrTable(PT_SYS_G); }
+    real_t **getPtrSysMatL() { return ptrTable(PT_SYS_L); }
+    real_t **getPtrSysMatLhat() { return ptrTable(PT_SYS_LHAT); }
+    real_t **getPtrMatPhi() { return ptrTable(PT_PHI); }
+    real_t **getPtrMatPsi() { return ptrTable(PT_PSI); }
+    real_t **getPtrMatTheta() { return ptrTable(PT_THETA); }
+    real_t **getPtrMatOmega() { return ptrTable(PT_OMEGA); }
+    real_t **getPtrMatSigma() { return ptrTable(PT_SIGMA); }
+    real_t **getPtrMatD() { return ptrTable(PT_D); }
+    real_t **getPtrMatF() { return ptrTable(PT_F); }
+    real_t **getPtrMatG() { return ptrTable(PT_G); }
+    // The scenario tree on the device, the host arrays of ScenarioTree verbatim (Engine.cu:256-290; 1-based node ids as in the
+    // JSON).  Also built on first use: the library keeps its own 0-based copy.
+    uint_t *getTreeStages() { return treeU(0); }
+    uint_t *getTreeNodesPerStage() { return treeU(1); }
+    uint_t *getTreeNodesPerStageCumul() { return treeU(2); }
+    uint_t *getTreeLeaves() { return treeU(3); }
+    uint_t *getTreeNumChildren() { return treeU(4); }
+    uint_t *getTreeAncestor() { return treeU(5); }
+    uint_t *getTreeNumChildrenCumul() { return treeU(6); }
+    real_t *getTreeProb() { return treeF(0); }
+    real_t *getTreeErrorDemand() { return treeF(1); }
+    real_t *getTreeErrorPrices() { return treeF(2); }
+    cublasHandle_t getCublasHandle();
     // the C-ABI handle underneath (what a binding of the reference would hold)
     rn_handle *handle() { return h; }
 
 private:
+    enum PtrTableId { PT_SYS_B, PT_SYS_F, PT_SYS_G, PT_SYS_L, PT_SYS_LHAT, PT_PHI, PT_PSI, PT_THETA, PT_OMEGA, PT_SIGMA, PT_D, PT_F,
+                      PT_G, PT_COUNT_ };
+    real_t **ptrTable(PtrTableId id);
+    uint_t *treeU(int which);
+    real_t *treeF(int which);
+    void *toDevice(const void *host, size_t bytes);
+    real_t **devPtrTables[PT_COUNT_] = {};
+    uint_t *devTreeU[7] = {};
+    real_t *devTreeF[3] = {};
+    std::vector<void *> ownedDevice;
+    cublasHandle_t cublasHandle = nullptr;
     real_t *buf(rn_buffer_id id);
     void check(rn_status rc, const char *what);
     DwnNetwork *ptrMyNetwork = nullptr;
@@ -228,6 +275,7 @@ protected:
     void computeFixedPointResidual();                      // :839-850
     void dualUpdate();                                     // :854-864
     uint_t algorithmApg();                                 // :1500-1525
+    real_t updatePrimalInfeasibity();                      // :1480-1496 (stand-alone; inside the APG loop the kernel logs it)
     void initialiseAlgorithm();                            // :420-450
     // the library's device buffers under the reference's member names; xi / psi / update roles swap physical
     // buffers with the iteration parity, so the pointers are refreshed after every call that runs iterations
