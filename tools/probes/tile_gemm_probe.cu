@@ -8,6 +8,8 @@
 //   variant 3: variant 1 with half the conversions (hi = cvt.rna.tf32, lo = x - hi passed as raw fp32 bits: the tensor core
 //              truncates it, an error of 2^-21 of x) and the operands of step s+1 loaded before the MMAs of step s
 //   variant 4: FFMA on all 512 threads: 1 row x 12 columns x half of k per thread (twice the right-hand-side loads)
+//   variant 5: FFMA, 4 rows x 12 columns x half of k per thread on 128 threads: 16 shared-memory wavefronts per 48 FMAs
+//              instead of 14 per 24 (the product is wavefront-bound), at the price of one warp per scheduler
 // Prints ns per product (device clock, mean over the repetitions of the slowest CTA) and the largest error against a
 // double-precision product, relative to max|Y|.
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tile_gemm_probe tile_gemm_probe.cu
@@ -241,6 +243,53 @@ __device__ __noinline__ void gemm_ffma512(const float *M, int m, int K, const fl
     cbar();
 }
 
+
+// ---- variant 5: FFMA, 4 rows x 12 columns per thread, 128 threads ---------------------------------------------------------------
+__device__ __noinline__ void gemm_ffma_4x12(const float *M, int m, int K, const float *X, float *Y, float *scr2) {
+    const int t = threadIdx.x, ks = t >> 6, u = t & 63, rp = u & 31, cg = u >> 5;   // threads 0..127: ks = 0, 1
+    const bool work = t < 128 && rp < m;
+    const int o1 = rp + 32 < m ? 32 : 0, o2 = rp + 64 < m ? 64 : 0, o3 = rp + 96 < m ? 96 : 0;
+    float a[4][12];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int i = 0; i < 12; i++) a[r][i] = 0.f;
+    if (work) {
+        const int kh = (K + 1) >> 1, k0 = ks ? kh : 0, k1 = ks ? K : kh;
+        const float *mp = M + (size_t)k0 * m + rp;
+        const float *xp = X + k0 * kTP + cg * 12;
+#pragma unroll 2
+        for (int k = k0; k < k1; k++, mp += m, xp += kTP) {
+            const float mv[4] = {mp[0], mp[o1], mp[o2], mp[o3]};
+            const float4 x0 = *reinterpret_cast<const float4 *>(xp), x1 = *reinterpret_cast<const float4 *>(xp + 4),
+                         x2 = *reinterpret_cast<const float4 *>(xp + 8);
+            const float xv[12] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w};
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int i = 0; i < 12; i++) a[r][i] = fmaf(mv[r], xv[i], a[r][i]);
+        }
+        if (ks == 1) {
+            float *d = scr2 + u * 48;
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int i = 0; i < 12; i++) d[r * 12 + i] = a[r][i];
+        }
+    }
+    cbar();
+    if (work && ks == 0) {
+        const float *sp = scr2 + u * 48;
+        const int off[4] = {0, o1, o2, o3};
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (r == 0 || off[r])
+#pragma unroll
+                for (int i = 0; i < 12; i++) Y[(rp + off[r]) * kTP + cg * 12 + i] = a[r][i] + sp[r * 12 + i];
+    }
+    cbar();
+}
+
 __global__ void __launch_bounds__(kPC, 1) k_probe(int variant, int m, int ldm, int K, const float *Mg, const float *Xg, float *Yg, int reps,
                                                   unsigned long long *ns_out) {
     extern __shared__ __align__(128) float smem[];
@@ -253,6 +302,7 @@ __global__ void __launch_bounds__(kPC, 1) k_probe(int variant, int m, int ldm, i
         if (variant == 0) gemm_ffma(M, m, K, X, Y, scr2);
         else if (variant == 3) gemm_mma_pipe(M, m, ldm, K, X, Y, scr2);
         else if (variant == 4) gemm_ffma512(M, m, K, X, Y, scr2);
+        else if (variant == 5) gemm_ffma_4x12(M, m, K, X, Y, scr2);
         else gemm_mma(M, m, ldm, K, X, Y, scr2);
     }
     const unsigned long long t1 = globaltimer();
@@ -287,7 +337,7 @@ int main(int argc, char **argv) {
         float *Md, *Xd, *Yd;
         CK(cudaMalloc(&Md, M.size() * 4)); CK(cudaMalloc(&Xd, X.size() * 4)); CK(cudaMalloc(&Yd, (size_t)m * kTP * 4));
         CK(cudaMemcpy(Md, M.data(), M.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(Xd, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
-        for (int variant = 0; variant < 5; variant++) {
+        for (int variant = 0; variant < 6; variant++) {
             int ldm = m;
             if (variant == 2) { ldm = m; while ((ldm & 31) != 8) ldm++; }
             const size_t smem = ((size_t)((ldm * K + 31) & ~31) + (size_t)(K + 8) * kTP + 128 * kTP + 128 * kTP) * 4;
