@@ -360,6 +360,55 @@ __device__ __forceinline__ void row_store(float *row, const float (&v)[kTP]) {
 // Y[r][c] = sum_k M[r + k*m] X[k][c],  r < m, c < kTP.  M (m x K, column-major), X, Y and scr2 in shared memory.
 // 256 threads compute: thread = (rows {rp, rp + 64}, 12 columns, one half of k); the upper half of k is handed over
 // through scr2.  All kPC threads call; ends with a CTA barrier.
+#ifdef RN_EXP_GEMM_4X12
+// Experimental (tools/build_variants.sh, not part of the default build): 4 rows x 12 columns x half of k per thread on 128
+// threads -- 16 shared-memory wavefronts per 48 FMAs instead of 14 per 24, one warp per scheduler.  Same summation order
+// per element as the default product, so the iterates are bit-identical.
+__device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float *X, float *Y, float *scr2) {
+    const int t = threadIdx.x, ks = t >> 6, u = t & 63, rp = u & 31, cg = u >> 5;
+    const bool work = t < 128 && rp < m;
+    const int o1 = rp + 32 < m ? 32 : 0, o2 = rp + 64 < m ? 64 : 0, o3 = rp + 96 < m ? 96 : 0;
+    float a[4][12];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int i = 0; i < 12; i++) a[r][i] = 0.f;
+    if (work) {
+        const int kh = (K + 1) >> 1, k0 = ks ? kh : 0, k1 = ks ? K : kh;
+        const float *mp = M + (size_t)k0 * m + rp;
+        const float *xp = X + k0 * kTP + cg * 12;
+#pragma unroll 2
+        for (int k = k0; k < k1; k++, mp += m, xp += kTP) {
+            const float mv[4] = {mp[0], mp[o1], mp[o2], mp[o3]};
+            const float4 x0 = *reinterpret_cast<const float4 *>(xp), x1 = *reinterpret_cast<const float4 *>(xp + 4),
+                         x2 = *reinterpret_cast<const float4 *>(xp + 8);
+            const float xv[12] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w};
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int i = 0; i < 12; i++) a[r][i] = fmaf(mv[r], xv[i], a[r][i]);
+        }
+        if (ks == 1) {
+            float *d = scr2 + u * 48;
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int i = 0; i < 12; i++) d[r * 12 + i] = a[r][i];
+        }
+    }
+    cbar();
+    if (work && ks == 0) {
+        const float *sp = scr2 + u * 48;
+        const int off[4] = {0, o1, o2, o3};
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (r == 0 || off[r])
+#pragma unroll
+                for (int i = 0; i < 12; i++) Y[(rp + off[r]) * kTP + cg * 12 + i] = a[r][i] + sp[r * 12 + i];
+    }
+    cbar();
+}
+#else
 __device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float *X, float *Y, float *scr2) {
     const int t = threadIdx.x, ks = t >> 7, u = t & 127, rp = u & 63, cg = u >> 6;
     const bool work = ks < 2 && rp < m;
@@ -408,6 +457,7 @@ __device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float
     }
     cbar();
 }
+#endif
 
 
 // The same product for two columns c0, c1 only (a crown tile of one node: the 24-column GEMM would spend 3 us on 1-2
@@ -772,11 +822,16 @@ __device__ __noinline__ void range_sum(const float *__restrict__ a, int lda, boo
                                        const float *__restrict__ b2, int ldb, bool eb, bool three, int lo, int hi, float &sa, float &sb) {
     const int g = threadIdx.x >> 7;
     float accA = 0.f, accB = 0.f;
+#ifdef RN_EXP_RANGESUM16   // experimental (tools/build_variants.sh): 16 rows in flight per trip for the long head ranges of large crowns
+    constexpr int kRows = 16;
+#else
+    constexpr int kRows = 8;
+#endif
 #pragma unroll 1
-    for (int jn = lo + g; jn < hi; jn += 32) {
-        float av[8], bv[8];
+    for (int jn = lo + g; jn < hi; jn += 4 * kRows) {
+        float av[kRows], bv[kRows];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < kRows; k++) {
             const int r = jn + 4 * k;
             const bool ok = r < hi;
             const size_t rr = (size_t)(ok ? r : lo);
@@ -789,7 +844,7 @@ __device__ __noinline__ void range_sum(const float *__restrict__ a, int lda, boo
             bv[k] = bb;
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) { accA += av[k]; accB += bv[k]; }
+        for (int k = 0; k < kRows; k++) { accA += av[k]; accB += bv[k]; }
     }
     sa = accA; sb = accB;
 }

@@ -1,5 +1,6 @@
 #!/usr/bin/env bash
-# A/B of library variants under ab_libs/: parity tests + bench (with the alt legs) for each, then the in-tree library's bench.
+# A/B of library variants under ab_libs/ (tools/build_variants.sh): parity tests + bench (with the alt legs) for each, then the
+# in-tree library's bench.  AB_WORKLOADS="C2 C3" adds workloads (default C2).
 set -uo pipefail
 TAG="${1:-ab}"
 OUT=gpurun_out/$TAG
@@ -14,13 +15,18 @@ for k in ("alt_formulation","alt_formulation_shared"):
     if a: print(sys.argv[2], k, round(a["value"]), a["roofline"].get("iteration_ms_by_kernel"))
 PY
 }
+WL="${AB_WORKLOADS:-C2}"
 for lib in ab_libs/*.so; do
   [ -e "$lib" ] || continue
   n=$(basename "$lib" .so)
   RAPIDNET_B200_LIB="$PWD/$lib" timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_shared_factors.py tests/test_gpu_golden.py -m gpu -x -q --timeout 200 > "$OUT/pytest_$n.log" 2>&1; echo "pytest $n rc=$?" | tee -a "$OUT/summary.txt"
   tail -2 "$OUT/pytest_$n.log"
-  RAPIDNET_B200_LIB="$PWD/$lib" timeout 200 python bench.py $QB > "$OUT/bench_$n.json" 2> "$OUT/bench_$n.err"; echo "bench $n rc=$?" | tee -a "$OUT/summary.txt"
-  show "$OUT/bench_$n.json" "$n"
+  for w in $WL; do
+    RAPIDNET_B200_LIB="$PWD/$lib" timeout 300 python bench.py $QB --workload $w > "$OUT/bench_${n}_$w.json" 2> "$OUT/bench_${n}_$w.err"; echo "bench $n $w rc=$?" | tee -a "$OUT/summary.txt"
+    show "$OUT/bench_${n}_$w.json" "$n/$w"
+  done
 done
-timeout 200 python bench.py $QB > "$OUT/bench_tree.json" 2> "$OUT/bench_tree.err"; echo "bench in-tree rc=$?" | tee -a "$OUT/summary.txt"
-show "$OUT/bench_tree.json" in-tree
+for w in $WL; do
+  timeout 300 python bench.py $QB --workload $w > "$OUT/bench_tree_$w.json" 2> "$OUT/bench_tree_$w.err"; echo "bench in-tree $w rc=$?" | tee -a "$OUT/summary.txt"
+  show "$OUT/bench_tree_$w.json" "in-tree/$w"
+done
