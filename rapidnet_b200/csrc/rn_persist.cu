@@ -408,6 +408,71 @@ __device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float
     }
     cbar();
 }
+#elif defined(RN_EXP_GEMM_FFMA2)
+// Experimental (tools/build_variants.sh, not part of the default build): the default product with packed FMAs
+// (fma.rn.f32x2 = SASS FFMA2: two IEEE fp32 FMAs per instruction, so the results are bit-identical).  The product runs at
+// the rate of the FP32 FMA pipe -- 128 x 24 x K lane-FMAs at one 3-register FFMA per two cycles and SM sub-partition is the
+// 21 ns per k that the phase clock shows -- so half the FMA instructions should take close to half the variable time.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float *X, float *Y, float *scr2) {
+    const int t = threadIdx.x, ks = t >> 7, u = t & 127, rp = u & 63, cg = u >> 6;
+    const bool work = ks < 2 && rp < m;
+    const bool two = rp + 64 < m;
+    unsigned long long a0[6], a1[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { a0[i] = 0ull; a1[i] = 0ull; }
+    if (work) {
+        const int kh = (K + 1) >> 1, k0 = ks ? kh : 0, k1 = ks ? K : kh;
+        const float *mp = M + (size_t)k0 * m + rp;
+        const int d1 = two ? 64 : 0;
+        const float *xp = X + k0 * kTP + cg * 12;
+#pragma unroll 2
+        for (int k = k0; k < k1; k++, mp += m, xp += kTP) {
+            const float m0 = mp[0], m1 = mp[d1];
+            const unsigned long long mm0 = pack2(m0, m0), mm1 = pack2(m1, m1);
+            const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(xp), x1 = *reinterpret_cast<const ulonglong2 *>(xp + 4),
+                             x2 = *reinterpret_cast<const ulonglong2 *>(xp + 8);
+            const unsigned long long xv[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
+#pragma unroll
+            for (int i = 0; i < 6; i++) { a0[i] = ffma2(mm0, xv[i], a0[i]); a1[i] = ffma2(mm1, xv[i], a1[i]); }
+        }
+        if (ks == 1) {
+            unsigned long long *d = reinterpret_cast<unsigned long long *>(scr2 + u * kTP);
+#pragma unroll
+            for (int i = 0; i < 6; i++) { d[i] = a0[i]; d[6 + i] = a1[i]; }
+        }
+    }
+    cbar();
+    if (work && ks == 0) {
+        const float *sp = scr2 + u * kTP;
+        float *y0 = Y + rp * kTP + cg * 12, *y1 = Y + (rp + 64) * kTP + cg * 12;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            float lo, hi;
+            unpack2(a0[i], lo, hi);
+            y0[2 * i] = lo + sp[2 * i]; y0[2 * i + 1] = hi + sp[2 * i + 1];
+        }
+        if (two) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                float lo, hi;
+                unpack2(a1[i], lo, hi);
+                y1[2 * i] = lo + sp[12 + 2 * i]; y1[2 * i + 1] = hi + sp[12 + 2 * i + 1];
+            }
+        }
+    }
+    cbar();
+}
 #else
 __device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float *X, float *Y, float *scr2) {
     const int t = threadIdx.x, ks = t >> 7, u = t & 127, rp = u & 63, cg = u >> 6;

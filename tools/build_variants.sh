@@ -4,12 +4,13 @@
 #   tools/gpu_ab.sh then runs the parity tests and the bench for every library under ab_libs/ and for the in-tree one.
 # Usage: bash tools/build_variants.sh [FLAG ...]      (default: every flag listed below)
 #   RN_EXP_GEMM_4X12    tile_gemm with 4 rows x 12 columns per thread on 128 threads (fewer shared-memory wavefronts per FMA)
+#   RN_EXP_GEMM_FFMA2   tile_gemm with packed FMAs (fma.rn.f32x2): half the FMA instructions, bit-identical results
 #   RN_EXP_RANGESUM16   crown head sums with 16 rows in flight per trip (large crowns: C3's root adds 480 heads)
 set -euo pipefail
 ROOT="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 SRC="$ROOT/rapidnet_b200/csrc"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-FLAGS_ALL=(RN_EXP_GEMM_4X12 RN_EXP_RANGESUM16)
+FLAGS_ALL=(RN_EXP_GEMM_4X12 RN_EXP_GEMM_FFMA2 RN_EXP_RANGESUM16)
 if [ $# -gt 0 ]; then FLAGS_ALL=("$@"); fi
 mkdir -p "$ROOT/ab_libs"
 for f in "${FLAGS_ALL[@]}"; do

@@ -8,6 +8,9 @@
 //   variant 3: variant 1 with half the conversions (hi = cvt.rna.tf32, lo = x - hi passed as raw fp32 bits: the tensor core
 //              truncates it, an error of 2^-21 of x) and the operands of step s+1 loaded before the MMAs of step s
 //   variant 4: FFMA on all 512 threads: 1 row x 12 columns x half of k per thread (twice the right-hand-side loads)
+//   variant 6: variant 0 with packed FMAs (fma.rn.f32x2 = SASS FFMA2, two IEEE fp32 FMAs per instruction: bit-identical
+//              results): the product runs at the rate of the FP32 FMA pipe (3-register FFMA issues every other cycle per
+//              SM sub-partition), so half the FMA instructions should be close to half the variable time
 //   variant 5: FFMA, 4 rows x 12 columns x half of k per thread on 128 threads: 16 shared-memory wavefronts per 48 FMAs
 //              instead of 14 per 24 (the product is wavefront-bound), at the price of one warp per scheduler
 // Prints ns per product (device clock, mean over the repetitions of the slowest CTA) and the largest error against a
@@ -290,6 +293,68 @@ __device__ __noinline__ void gemm_ffma_4x12(const float *M, int m, int K, const 
     cbar();
 }
 
+
+// ---- variant 6: the FFMA product with packed FMAs ------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __noinline__ void gemm_ffma2(const float *M, int m, int K, const float *X, float *Y, float *scr2) {
+    const int t = threadIdx.x, ks = t >> 7, u = t & 127, rp = u & 63, cg = u >> 6;
+    const bool work = ks < 2 && rp < m;
+    const bool two = rp + 64 < m;
+    unsigned long long a0[6], a1[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { a0[i] = 0ull; a1[i] = 0ull; }
+    if (work) {
+        const int kh = (K + 1) >> 1, k0 = ks ? kh : 0, k1 = ks ? K : kh;
+        const float *mp = M + (size_t)k0 * m + rp;
+        const int d1 = two ? 64 : 0;
+        const float *xp = X + k0 * kTP + cg * 12;
+#pragma unroll 2
+        for (int k = k0; k < k1; k++, mp += m, xp += kTP) {
+            const float m0 = mp[0], m1 = mp[d1];
+            const unsigned long long mm0 = pack2(m0, m0), mm1 = pack2(m1, m1);
+            const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(xp), x1 = *reinterpret_cast<const ulonglong2 *>(xp + 4),
+                             x2 = *reinterpret_cast<const ulonglong2 *>(xp + 8);
+            const unsigned long long xv[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
+#pragma unroll
+            for (int i = 0; i < 6; i++) { a0[i] = ffma2(mm0, xv[i], a0[i]); a1[i] = ffma2(mm1, xv[i], a1[i]); }
+        }
+        if (ks == 1) {
+            unsigned long long *d = reinterpret_cast<unsigned long long *>(scr2 + u * kTP);
+#pragma unroll
+            for (int i = 0; i < 6; i++) { d[i] = a0[i]; d[6 + i] = a1[i]; }
+        }
+    }
+    cbar();
+    if (work && ks == 0) {
+        const float *sp = scr2 + u * kTP;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            float lo, hi;
+            unpack2(a0[i], lo, hi);
+            Y[rp * kTP + cg * 12 + 2 * i] = lo + sp[2 * i]; Y[rp * kTP + cg * 12 + 2 * i + 1] = hi + sp[2 * i + 1];
+        }
+        if (two) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                float lo, hi;
+                unpack2(a1[i], lo, hi);
+                Y[(rp + 64) * kTP + cg * 12 + 2 * i] = lo + sp[12 + 2 * i]; Y[(rp + 64) * kTP + cg * 12 + 2 * i + 1] = hi + sp[12 + 2 * i + 1];
+            }
+        }
+    }
+    cbar();
+}
+
 __global__ void __launch_bounds__(kPC, 1) k_probe(int variant, int m, int ldm, int K, const float *Mg, const float *Xg, float *Yg, int reps,
                                                   unsigned long long *ns_out) {
     extern __shared__ __align__(128) float smem[];
@@ -303,6 +368,7 @@ __global__ void __launch_bounds__(kPC, 1) k_probe(int variant, int m, int ldm, i
         else if (variant == 3) gemm_mma_pipe(M, m, ldm, K, X, Y, scr2);
         else if (variant == 4) gemm_ffma512(M, m, K, X, Y, scr2);
         else if (variant == 5) gemm_ffma_4x12(M, m, K, X, Y, scr2);
+        else if (variant == 6) gemm_ffma2(M, m, K, X, Y, scr2);
         else gemm_mma(M, m, ldm, K, X, Y, scr2);
     }
     const unsigned long long t1 = globaltimer();
@@ -337,7 +403,7 @@ int main(int argc, char **argv) {
         float *Md, *Xd, *Yd;
         CK(cudaMalloc(&Md, M.size() * 4)); CK(cudaMalloc(&Xd, X.size() * 4)); CK(cudaMalloc(&Yd, (size_t)m * kTP * 4));
         CK(cudaMemcpy(Md, M.data(), M.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(Xd, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
-        for (int variant = 0; variant < 6; variant++) {
+        for (int variant = 0; variant < 7; variant++) {
             int ldm = m;
             if (variant == 2) { ldm = m; while ((ldm & 31) != 8) ldm++; }
             const size_t smem = ((size_t)((ldm * K + 31) & ~31) + (size_t)(K + 8) * kTP + 128 * kTP + 128 * kTP) * 4;
