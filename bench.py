@@ -7,19 +7,26 @@ scenario tree (default workload C2: Barcelona-shaped DWN 63/114/88, N=24, tree [
 iterations).  Synthetic data of the reference's shape (rapidnet_b200/datagen.py; the true Barcelona blobs are
 missing from the reference).
 
-  value : APG iterations/s, whole job (all ranks), duals cold-started on the device, inputs resident in HBM;
-          CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+  value : APG iterations/s, whole job, duals cold-started on the device, inputs resident in HBM; CUDA events on the
+          launching stream, barrier + synchronize on both sides, max over ranks.
   e2e   : the same metric through rn_control_action (the reference's controlAction(real_t*)): HOST buffers in
           (state, previous control/demand, demand and price forecasts), affine-term refresh, the APG solve, u0 back
           to the host -- H2D and D2H inside the timed region.
-  N > 1 : one process per GPU, each rank solves its own independent SMPC instance (same network and tree, its
-          own initial tank levels): closed-loop Monte-Carlo instances shard with no data-path collective ("weak").
-          The same line also carries "tree_partition": ONE larger tree (C3, K=480, 10 171 nodes) cut below its last
-          branching stage across the N GPUs -- the crown replicated, the chains split, q/r of the chain heads and the
-          prox distances exchanged inside the persistent kernel over NVLink peer memory (rapidnet_b200/partition.py).
+  roofline : kernel level: SURVEY 8(d) Tier-A algorithmic bytes of one APG iteration over the CUDA-event time of one
+          iteration of k_apg_persistent (the one kernel that runs) against MEASURED_PEAKS.json; the factor-stream phase
+          (in-kernel %globaltimer clock of one CTA) is a sub-field.
+  N = 1 : workload C2 (BASELINE config[1]); `by_config` carries the same three numbers (value, e2e, roofline fraction)
+          for the other scenario counts of the metric ("vs scenario count"): C1, C1r6, C1r30, C3, C3b.
+  N > 1 : the headline is STRONG scaling of ONE tree (BASELINE config[2]: C3, K=480, 10 171 nodes) cut below its last
+          branching stage across the N GPUs, one process per GPU -- the crown replicated, the chains split, the near-root
+          contributions and the prox distances exchanged inside the persistent kernel over NVLink peer memory
+          (rapidnet_b200/partition.py); its e2e goes through the distributed controlAction, its iterates are checked
+          against the same tree solved on one GPU in the same run.  N independent C2 instances (closed-loop Monte-Carlo
+          replicas, no data-path collective) are the secondary record `replicas`.
   --impl reference : the reference's own CUDA/cuBLAS build (oracle/_ref/ref_driver, compiled from
-          /root/reference/src in place) on the same workload through its controlAction(real_t*); if that binary is
-          missing, the CPU oracle port on the host cores.  Rank 0 only.
+          /root/reference/src in place) on the SAME workload as this arm's headline at that N (C2 at N=1, C3 at N>1; the
+          reference is single-GPU) through its controlAction(real_t*); if that binary is missing, the CPU oracle port on
+          the host cores.  Rank 0 only.  Its repetitions are capped so that the run ends within minutes.
 """
 import argparse
 import json
@@ -129,23 +136,40 @@ def cpu_baseline(prob, iters_sample, threads):
     return done / dt, dt
 
 
+def line_config(workload, prob, iters, desc=None):
+    """`config` of the JSON line -- the same dict in both arms (the driver compares them)"""
+    return {"workload": desc or describe(workload, prob), "iterations_per_solve": iters,
+            "cold_cache": "inputs larger than L2: the factor matrices of one solve exceed the 126 MB L2"}
+
+
+def headline_workload(args, world):
+    """C2 on one GPU (BASELINE config[1]); the partitioned tree (config[2]) when the run spans several GPUs"""
+    return args.workload if world == 1 or not args.partition_workload else args.partition_workload
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    prob = rank_problem(args.workload, args.iters, 0)
-    cfg = {"workload": describe(args.workload, prob), "iterations_per_solve": args.iters, "cold_cache": "factors > L2"}
+    wl = headline_workload(args, world)
+    prob = rank_problem(wl, args.iters, 0)
+    # bounded: the reference needs seconds per solve (launch-bound on one host thread)
+    reps, warm = max(1, min(args.steps, args.ref_max_steps)), min(args.warmup, 1)
+    cfg = line_config(wl, prob, args.iters)
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     have_gpu = shutil.which("nvidia-smi") is not None and subprocess.call(
         ["nvidia-smi", "-L"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 0
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": cfg}
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "setup": {"repetitions": f"{reps} timed solves after {warm} warm-up (capped: --ref-max-steps)", "gpus_used": 1}}
+    if world > 1:
+        line["setup"]["note"] = "the reference is a single-GPU program: it solves the same tree on one GPU at every N"
     if os.path.exists(ref_bin) and have_gpu and not args.cpu_reference:
         from rapidnet_b200.problem import write_problem
         tmp = tempfile.mkdtemp(prefix="rn_ref_")
         cfg_path = write_problem(prob, tmp)
         env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
-        out = subprocess.run([ref_bin, cfg_path, "0", str(args.warmup), str(args.steps)], capture_output=True,
+        out = subprocess.run([ref_bin, cfg_path, "0", str(warm), str(reps)], capture_output=True,
                              text=True, env=env, timeout=3000)
         shutil.rmtree(tmp, ignore_errors=True)
         rec = [ln for ln in out.stdout.splitlines() if ln.startswith("REF ")]
@@ -158,7 +182,7 @@ def run_reference(args, rank, world):
         line.update({"value": val, "ms_per_step": ms,
                      "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference",
                                       "sample": "the reference's own CUDA/cuBLAS build (it has no CPU path): full "
-                                                f"controlAction, {args.iters} iterations, median of {args.steps} on 1 GPU, "
+                                                f"controlAction, {args.iters} iterations, median of {reps} on 1 GPU, "
                                                 "one host thread driving cuBLAS"},
                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                      "reference_build": "oracle/_ref/ref_driver (unmodified /root/reference/src, nvcc sm_100, cuBLAS)"})
@@ -178,38 +202,163 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def bench_partition(args, rank, world, local, stream):
-    """ONE tree cut across the `world` GPUs (strong scaling): iterations/s of the partitioned solve, max over ranks."""
+def measure_handle(s, prob, iters, steps, warmup, stream, barrier):
+    """One factored handle: `steps` cold-started solves with device-resident inputs (CUDA events on the launching stream),
+    then the same through rn_control_action with host buffers.  Returns this rank's figures (ms over all steps)."""
+    import torch
+    c, fc = prob.config, prob.forecast
+    with torch.cuda.stream(stream):
+        for _ in range(max(warmup, 3)):
+            s.apg_solve(iters, want_u0=False)
+        barrier()
+        l0 = s.info().kernel_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            s.apg_solve(iters, want_u0=False)
+        e1.record(stream)
+        barrier()
+        ms_dev = e0.elapsed_time(e1)
+        launches = s.info().kernel_launches - l0
+        host_in = [np.ascontiguousarray(a, dtype=np.float32) for a in
+                   (c.current_x, c.prev_u, c.prev_demand, fc.demand[0], fc.prices[0])]
+        u0 = np.zeros(prob.network.nu, dtype=np.float32)
+        for _ in range(2):
+            s.control_action(*host_in, iters, out=u0)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            s.control_action(*host_in, iters, out=u0)
+        f1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max(f0.elapsed_time(f1), wall_ms)
+    return {"ms_dev": ms_dev, "ms_e2e": ms_e2e, "launches": int(launches), "h2d": int(sum(a.nbytes for a in host_in)),
+            "d2h": int(u0.nbytes), "finite": bool(np.isfinite(u0).all())}
+
+
+def bench_config(name, args, local, stream, barrier, peak):
+    """value / e2e / kernel-level roofline fraction of one scenario-count configuration on ONE GPU (by_config)"""
+    from rapidnet_b200 import cabi
+    prob = rank_problem(name, args.iters, 0)
+    fc = prob.forecast
+    s = cabi.Solver(prob, device=local)
+    s.set_stream(stream.cuda_stream)
+    s.set_modes({"persistent": cabi.SWEEP_PERSISTENT, "chain": cabi.SWEEP_CHAIN, "per_stage": cabi.SWEEP_PER_STAGE}[args.sweep],
+                {"full": cabi.FACTORS_FULL, "df": cabi.FACTORS_DF, "shared": cabi.FACTORS_SHARED}[args.factors])
+    s.factor_step(); s.update_state(); s.eliminate_coupling(fc.demand[0], fc.prices[0])
+    big = prob.tree.nodes > 20000
+    steps = max(1, min(args.steps, 2 if big else 5))
+    m = measure_handle(s, prob, args.iters, steps, 1 if big else 3, stream, barrier)
+    info = s.info()
+    it_s = m["ms_dev"] / steps / args.iters * 1e-3
+    out = {"workload": describe(name, prob), "scenarios": int(prob.tree.K), "nodes": int(prob.tree.nodes), "steps": steps,
+           "value": steps * args.iters / (m["ms_dev"] * 1e-3), "unit": UNIT, "ms_per_solve": m["ms_dev"] / steps,
+           "e2e": {"value": steps * args.iters / (m["ms_e2e"] * 1e-3), "ms_per_solve": m["ms_e2e"] / steps},
+           "persistent_kernel": bool(info.launches_per_iteration == 0),
+           "factor_mb": info.factor_bytes / 1e6,
+           "roofline": {"bytes_per_iteration": info.apg_bytes_per_iteration,
+                        "achieved": info.apg_bytes_per_iteration / it_s / 1e9, "unit": "GB/s",
+                        "frac": info.apg_bytes_per_iteration / it_s / 1e9 / peak,
+                        "note": "factors fit the 126 MB L2: the HBM roofline does not bound this configuration"
+                        if info.factor_bytes < 100e6 else None}}
+    s.close()
+    return out
+
+
+def bench_partition(args, rank, world, local, stream, workload):
+    """ONE tree cut across the `world` GPUs (strong scaling): iterations/s of the partitioned solve (device-resident inputs)
+    and through the distributed controlAction (host buffers), max over ranks; rank 0 also solves the whole tree on its own
+    GPU: the 1-GPU figure of the same workload and the iterate check of the partition."""
     import torch
     import torch.distributed as dist
     from rapidnet_b200 import cabi
     from rapidnet_b200.datagen import named_problem
     from rapidnet_b200.partition import DistributedSolver
-    prob = named_problem(args.partition_workload, max_iter=args.iters)
+    prob = named_problem(workload, max_iter=args.iters)
+    c, fc, n = prob.config, prob.forecast, prob.network
+    fmode = {"full": cabi.FACTORS_FULL, "df": cabi.FACTORS_DF, "shared": cabi.FACTORS_SHARED}[args.factors]
     ds = DistributedSolver(prob, rank, world, device=local)
     ds.solver.set_stream(stream.cuda_stream)
-    ds.solver.set_modes(cabi.SWEEP_PERSISTENT, {"full": cabi.FACTORS_FULL, "df": cabi.FACTORS_DF, "shared": cabi.FACTORS_SHARED}[args.factors])
+    ds.solver.set_modes(cabi.SWEEP_PERSISTENT, fmode)
     ds.setup(slot=0)
-    iters, steps = args.iters, max(1, min(args.steps, 3))
+    iters, steps = args.iters, max(1, min(args.steps, 5))
+    host_in = [np.ascontiguousarray(a, dtype=np.float32) for a in (c.current_x, c.prev_u, c.prev_demand, fc.demand[0], fc.prices[0])]
     with torch.cuda.stream(stream):
-        ds.apg_solve(iters, want_u0=False)
+        for _ in range(2):
+            ds.apg_solve(iters, want_u0=False)
         dist.barrier(); torch.cuda.synchronize()
+        l0 = ds.solver.info().kernel_launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
-            ds.apg_solve(iters, want_u0=False)
+            ds.apg_solve(iters, want_u0=False, check=False)
         e1.record(stream)
         dist.barrier(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        launches = ds.solver.info().kernel_launches - l0
+        if ds.solver.dist_error():
+            raise RuntimeError("a cross-GPU wait timed out during the timed solves")
+        # end to end: host buffers in on every rank, u0 back on the host of every rank
+        u0 = ds.control_action(*host_in, iters)
+        dist.barrier(); torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            u0 = ds.control_action(*host_in, iters)
+        f1.record(stream)
+        dist.barrier(); torch.cuda.synchronize()
+        ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0])
+    ms, ms_e2e = float(t[0]), float(t[1])
+    # iterate check + the 1-GPU figure of the same tree (rank 0, the other GPUs idle)
+    got = {name: ds.gather(name, dim) for name, dim in (("VEC_U", n.nu), ("VEC_X", n.nx), ("VEC_UPDATE_XI", 2 * n.nx))}
+    check = None
+    if rank == 0 and not args.no_partition_check:
+        ref = cabi.Solver(prob, device=local)
+        ref.set_stream(stream.cuda_stream)
+        ref.set_modes(cabi.SWEEP_PERSISTENT, fmode)
+        ref.factor_step()
+        with torch.cuda.stream(stream):
+            ru0 = ref.control_action(*host_in, iters)
+            worst = 0.0
+            for name, a in got.items():
+                b = ref.read(name).reshape(a.shape).astype(np.float64)
+                worst = max(worst, float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)))
+            u0_err = float(np.linalg.norm(u0.astype(np.float64) - ru0) / max(np.linalg.norm(ru0), 1e-30))
+            ref.apg_solve(iters, want_u0=False)
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            one_steps = max(1, min(steps, 3))
+            g0.record(stream)
+            for _ in range(one_steps):
+                ref.apg_solve(iters, want_u0=False)
+            g1.record(stream)
+            torch.cuda.synchronize()
+            one_ms = g0.elapsed_time(g1) / one_steps
+        check = {"iterations": iters, "worst_rel_err_U_X_y_vs_one_gpu": worst, "u0_rel_err_vs_one_gpu": u0_err,
+                 "ok": bool(worst < 1e-4 and u0_err < 1e-4),
+                 "one_gpu": {"value": iters / (one_ms * 1e-3), "unit": UNIT, "ms_per_solve": one_ms,
+                             "note": "the same tree solved on ONE GPU of this box in the same run (rank 0)"}}
+        ref.close()
+    dist.barrier()
     d = prob.dims
-    out = {"workload": describe(args.partition_workload, prob), "n_gpus": world, "scaling": "strong", "steps": steps,
+    info = ds.solver.info()
+    out = {"workload": describe(workload, prob), "n_gpus": world, "scaling": "strong", "steps": steps,
            "value": steps * iters / (ms * 1e-3), "unit": UNIT, "ms_per_solve": ms / steps,
+           "e2e": {"value": steps * iters / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_solve": ms_e2e / steps,
+                   "h2d_bytes_per_step": int(sum(a.nbytes for a in host_in)) * world, "d2h_bytes_per_step": int(u0.nbytes) * world,
+                   "api": "DistributedSolver.control_action: rn_control_action on every rank (host buffers in, u0 out)"},
+           "gpu_launches": int(launches),
            "nodes_per_rank": int(ds.local.tree.nodes), "crown_nodes_replicated": int(ds.meta.n_crown),
-           "exchange_bytes_per_iteration_per_rank": int((ds.local.tree.K * (d["nx"] + d["nv"]) * 4 + 16) * (world - 1)),
-           "exchange": "in-kernel stores to peer memory (CUDA IPC over NVLink) + flag barriers; no NCCL on the data path"}
+           "exchange_bytes_per_iteration_per_rank": int(ds.exchange_bytes_per_iteration()),
+           "exchange": "in-kernel stores to peer memory (CUDA IPC over NVLink) + flag barriers; no NCCL on the data path",
+           "bytes_per_iteration_per_rank": info.apg_bytes_per_iteration,
+           "check_vs_one_gpu": check}
     ds.close()
     return out
 
@@ -298,15 +447,19 @@ def main():
     ap.add_argument("--iters", type=int, default=500, help="APG iterations per SMPC solve (reference: 500)")
     ap.add_argument("--cpu-sample-iters", type=int, default=2000, help="CPU baseline: APG iterations of the bounded sample (about 10-15 s on 16 cores)")
     ap.add_argument("--cpu-reference", action="store_true", help="--impl reference: force the CPU oracle port")
+    ap.add_argument("--ref-max-steps", type=int, default=5, help="--impl reference: most timed solves (seconds each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the legs of the two reformulations (D, F only; shared factors)")
+    ap.add_argument("--by-config", default="C1,C1r6,C1r30,C3,C3b", help="N = 1: other scenario counts measured next to the headline ('' = skip)")
     ap.add_argument("--closed-loop-instances", type=int, default=4, help="closed-loop Monte-Carlo leg: instances PER RANK (0 = skip)")
     ap.add_argument("--closed-loop-lanes", type=int, default=4, help="that leg again with this many handles per GPU side by side (1 = skip)")
     ap.add_argument("--closed-loop-steps", type=int, default=2, help="receding-horizon steps per instance in that leg")
     ap.add_argument("--closed-loop-workload", default="C1r30", help="tree of that leg (SURVEY C4: the shipped K=30 tree)")
     ap.add_argument("--sweep", default="persistent", choices=["persistent", "chain", "per_stage"])
     ap.add_argument("--factors", default="full", choices=["full", "df", "shared"])
-    ap.add_argument("--partition-workload", default="C3", help="N > 1: the tree that is cut across the GPUs ('' = skip)")
+    ap.add_argument("--partition-workload", default="C3", help="N > 1: the tree that is cut across the GPUs = the headline ('' = replicas only)")
+    ap.add_argument("--partition-extra", default="C3b", help="N > 1: a second, larger tree cut across the GPUs ('' = skip)")
+    ap.add_argument("--no-partition-check", action="store_true", help="N > 1: skip the 1-GPU solve of the partitioned tree (check + 1-GPU figure)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -332,7 +485,7 @@ def main():
         torch.cuda.synchronize()
 
     prob = rank_problem(args.workload, args.iters, rank)
-    c, fc = prob.config, prob.forecast
+    fc = prob.forecast
     s = cabi.Solver(prob, device=local)
     stream = torch.cuda.Stream()
     s.set_stream(stream.cuda_stream)          # torch.cuda.Event sees the stream the kernels are launched on
@@ -342,42 +495,14 @@ def main():
     s.update_state()
     s.eliminate_coupling(fc.demand[0], fc.prices[0])
     iters = args.iters
+    peak, peak_src = measured_peaks()
 
-    with torch.cuda.stream(stream):
-        for _ in range(max(args.warmup, 3)):
-            s.apg_solve(iters, want_u0=False)
-        barrier()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-        l0 = s.info().kernel_launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record(stream)
-        for _ in range(args.steps):
-            s.apg_solve(iters, want_u0=False)
-        e1.record(stream)
-        barrier()
-        ms_dev = e0.elapsed_time(e1)
-        launches = s.info().kernel_launches - l0
-
-        # end to end through the reference-facing call: host buffers in, u0 back on the host
-        host_in = [np.ascontiguousarray(a, dtype=np.float32) for a in
-                   (c.current_x, c.prev_u, c.prev_demand, fc.demand[0], fc.prices[0])]
-        u0 = np.zeros(prob.network.nu, dtype=np.float32)
-        for _ in range(2):
-            s.control_action(*host_in, iters, out=u0)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            s.control_action(*host_in, iters, out=u0)
-        f1.record(stream)
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        ms_e2e = max(f0.elapsed_time(f1), wall_ms)
-        clocks = sampler.stop() if rank == 0 else None
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    m = measure_handle(s, prob, iters, args.steps, args.warmup, stream, barrier)
+    ms_dev, ms_e2e, launches = m["ms_dev"], m["ms_e2e"], m["launches"]
+    clocks = sampler.stop() if rank == 0 and world == 1 else None
 
     # the same solve with the two exact reformulations of the factor step.  Reported next to the headline, never instead of
     # it; each roofline uses the bytes its own formulation has to move:
@@ -403,16 +528,15 @@ def main():
                 ph_alt = {k: round(v) for k, v in s.phase_times().items()}
             except Exception:
                 ph_alt = None
-            peak_alt, _ = measured_peaks()
-            ach = info_alt.stream_bytes_per_iteration / (prof_alt["stream"] * 1e-3) / 1e9 if prof_alt["stream"] > 0 else 0.0
             it_ms = ms_alt / args.steps / iters
+            ach = info_alt.apg_bytes_per_iteration / (it_ms * 1e-3) / 1e9
+            ach_s = info_alt.stream_bytes_per_iteration / (prof_alt["stream"] * 1e-3) / 1e9 if prof_alt["stream"] > 0 else 0.0
             return {"formulation": text, "value": args.steps * iters / (ms_alt * 1e-3), "unit": UNIT, "ms_per_solve": ms_alt / args.steps,
-                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_alt, "unit": "GB/s", "frac": ach / peak_alt,
-                                 "algorithmic_bytes_per_launch": info_alt.stream_bytes_per_iteration, "launch_ms": prof_alt["stream"],
-                                 "iteration_ms_by_kernel": prof_alt, "phase_clock_ns_per_iteration": ph_alt,
-                                 "whole_iteration": {"bytes": info_alt.apg_bytes_per_iteration,
-                                                     "achieved": info_alt.apg_bytes_per_iteration / (it_ms * 1e-3) / 1e9,
-                                                     "frac": info_alt.apg_bytes_per_iteration / (it_ms * 1e-3) / 1e9 / peak_alt}}}
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                 "algorithmic_bytes_per_launch": info_alt.apg_bytes_per_iteration, "launch_ms": it_ms,
+                                 "phase_S": {"bytes": info_alt.stream_bytes_per_iteration, "ms": prof_alt["stream"], "achieved": ach_s,
+                                             "frac": ach_s / peak},
+                                 "iteration_ms_by_phase": prof_alt, "phase_clock_ns_per_iteration": ph_alt}}
         def guarded(mode, text):
             try:
                 return alt_leg(mode, text)
@@ -423,6 +547,16 @@ def main():
                                                   "from the shared matrices in shared memory, v = -1/2 Omega r")
         s.set_modes(cabi.SWEEP_PERSISTENT, cabi.FACTORS_FULL)
 
+    # metric "vs scenario count": the other trees on ONE GPU, same three numbers each
+    by_config = None
+    if world == 1 and args.by_config:
+        by_config = {}
+        for name in [x for x in args.by_config.split(",") if x and x != args.workload]:
+            try:
+                by_config[name] = bench_config(name, args, local, stream, barrier, peak)
+            except Exception as ex:   # noqa: BLE001
+                by_config[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
     # closed-loop Monte-Carlo sample (BASELINE config[3]): instances sharded over the ranks, one factored handle per rank
     # the secondary legs never take the headline line down with them: an exception is recorded in their place
     loop = None
@@ -432,12 +566,23 @@ def main():
         except Exception as ex:   # noqa: BLE001
             loop = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
-    part = None
+    part, part_extra = None, None
     if world > 1 and args.partition_workload:
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
         try:
-            part = bench_partition(args, rank, world, local, stream)
+            part = bench_partition(args, rank, world, local, stream, args.partition_workload)
         except Exception as ex:   # noqa: BLE001
             part = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        clocks = sampler2.stop() if rank == 0 else None
+        if args.partition_extra:
+            try:
+                part_extra = bench_partition(args, rank, world, local, stream, args.partition_extra)
+            except Exception as ex:   # noqa: BLE001
+                part_extra = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    elif world > 1 and rank == 0:
+        clocks = sampler.stop()
 
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -453,48 +598,81 @@ def main():
             phases = {k: round(v) for k, v in s.phase_times().items()} if args.sweep == "persistent" else None
         except Exception:
             phases = None
-        peak, peak_src = measured_peaks()
-        stream_bytes = info.stream_bytes_per_iteration
-        achieved = stream_bytes / (prof["stream"] * 1e-3) / 1e9 if prof["stream"] > 0 else 0.0
+        it_s = ms_dev / args.steps / iters * 1e-3                      # CUDA-event time of one iteration of the one kernel that runs
+        achieved = info.apg_bytes_per_iteration / it_s / 1e9
+        ach_s = info.stream_bytes_per_iteration / (prof["stream"] * 1e-3) / 1e9 if prof["stream"] > 0 else 0.0
         total_prof = sum(prof.values())
         traffic, traffic_note = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath) and args.workload == "C2" and args.sweep == "persistent" and args.factors == "full":
-            tj = json.load(open(tpath))
-            traffic = tj["dram_bytes_per_iteration"]
-            traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of {tj['kernel']} "
-                            f"({tj['iterations_in_capture']} iterations, ALL phases) / iterations; compare with the whole-iteration "
-                            f"algorithmic bytes {info.apg_bytes_per_iteration:.0f}")
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": describe(args.workload, prob), "iterations_per_solve": iters,
-                       "instances": world, "parallelism": f"{world} independent SMPC instance(s), one per GPU",
-                       "sweep": args.sweep, "factors": args.factors,
-                       "cold_cache": f"factor matrices {info.factor_bytes / 1e6:.0f} MB > L2 (126 MB): inputs larger than L2"},
-            "ms_per_solve": ms_dev / args.steps,
+        for tname in ("r02_traffic.json", "r01_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath) and args.workload == "C2" and args.sweep == "persistent" and args.factors == "full":
+                tj = json.load(open(tpath))
+                traffic = tj["dram_bytes_per_iteration"]
+                traffic_note = (f"profiles/{tname}: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of "
+                                f"{tj['kernel']} ({tj['iterations_in_capture']} iterations) / iterations")
+                break
+        single = {
+            "value": value, "unit": UNIT, "ms_per_solve": ms_dev / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_solve": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(sum(a.nbytes for a in host_in)), "d2h_bytes_per_step": int(u0.nbytes),
+                    "h2d_bytes_per_step": m["h2d"] * world, "d2h_bytes_per_step": m["d2h"] * world,
                     "api": "rn_control_action (SmpcController::controlAction(real_t*))"},
-            "gpu_launches": int(launches),
-            "launches_per_iteration": int(info.launches_per_iteration),
-            "clocks": clocks,
+            "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm",
-                         "kernel": ("k_apg_persistent, phase S (factor-matrix stream + fused element-wise pass) of one iteration"
-                                    if args.sweep == "persistent" else "k_stream"),
-                         "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
-                         "algorithmic_bytes_per_launch": stream_bytes, "launch_ms": prof["stream"],
-                         "share_of_iteration": prof["stream"] / total_prof if total_prof > 0 else None,
-                         "iteration_ms_by_kernel": prof,
-                         "phase_clock_ns_per_iteration": phases,
-                         "whole_iteration": {"bytes": info.apg_bytes_per_iteration,
-                                             "achieved": info.apg_bytes_per_iteration / (ms_dev / args.steps / iters * 1e-3) / 1e9,
-                                             "frac": info.apg_bytes_per_iteration / (ms_dev / args.steps / iters * 1e-3) / 1e9 / peak}},
+                         "kernel": "k_apg_persistent: one APG iteration (factor stream + fused element-wise pass + tree sweeps + prox), "
+                                   "CUDA events around the launch / iterations" if args.sweep == "persistent" else "per-iteration kernels",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_note": traffic_note,
+                         "algorithmic_bytes_per_launch": info.apg_bytes_per_iteration, "launch_ms": it_s * 1e3,
+                         "bytes_formula": "SURVEY.md 8(d) Tier A: per-node Engine factor matrices once + diagonals + vector traffic",
+                         "phase_S": {"what": "factor-matrix stream + fused element-wise pass incl. its grid barrier (in-kernel %globaltimer clock of one CTA)",
+                                     "bytes": info.stream_bytes_per_iteration, "ms": prof["stream"], "achieved": ach_s, "frac": ach_s / peak,
+                                     "share_of_iteration": prof["stream"] / total_prof if total_prof > 0 else None},
+                         "iteration_ms_by_phase": prof, "phase_clock_ns_per_iteration": phases},
         }
-        if part is not None:
-            line["tree_partition"] = part
+        setup = {"sweep": args.sweep, "factors": args.factors}
+        if world > 1 and part is not None and "value" in part:
+            # strong scaling of ONE tree is the headline of a multi-GPU run; the independent instances are secondary
+            line = {
+                "metric": METRIC, "value": part["value"], "unit": UNIT, "n_gpus": world, "steps": part["steps"],
+                "warmup": max(args.warmup, 3), "ms_per_step": part["ms_per_solve"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": line_config(None, None, iters, desc=part["workload"]),
+                "setup": dict(setup, parallelism=f"one tree cut across {world} GPUs below its last branching stage (crown replicated, chains split)"),
+                "ms_per_solve": part["ms_per_solve"], "e2e": part["e2e"], "gpu_launches": part["gpu_launches"] * world,
+                "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "k_apg_persistent on every rank, one APG iteration of the partitioned tree",
+                             "achieved": part["bytes_per_iteration_per_rank"] * world / (part["ms_per_solve"] / iters * 1e-3) / 1e9,
+                             "peak": peak * world, "unit": "GB/s",
+                             "frac": part["bytes_per_iteration_per_rank"] / (part["ms_per_solve"] / iters * 1e-3) / 1e9 / peak,
+                             "peak_source": peak_src + f" x {world} GPUs", "traffic": None,
+                             "algorithmic_bytes_per_launch": part["bytes_per_iteration_per_rank"] * world,
+                             "launch_ms": part["ms_per_solve"] / iters},
+                "tree_partition": part,
+                "replicas": dict(single, workload=describe(args.workload, prob), scaling="weak",
+                                 parallelism=f"{world} independent SMPC instances, one per GPU, no data-path collective"),
+            }
+            if part_extra is not None:
+                line["tree_partition_extra"] = part_extra
+        else:
+            line = {
+                "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": line_config(args.workload, prob, iters),
+                "setup": dict(setup, instances=world, parallelism=f"{world} independent SMPC instance(s), one per GPU",
+                              factor_mb=info.factor_bytes / 1e6),
+                "ms_per_solve": single["ms_per_solve"], "e2e": single["e2e"], "gpu_launches": single["gpu_launches"],
+                "launches_per_iteration": int(info.launches_per_iteration), "clocks": clocks, "roofline": single["roofline"],
+            }
+            if part is not None:
+                line["tree_partition"] = part
+        if by_config is not None:
+            by_config[args.workload] = {"workload": describe(args.workload, prob), "scenarios": int(prob.tree.K), "nodes": int(prob.tree.nodes),
+                                        "value": value, "unit": UNIT, "ms_per_solve": ms_dev / args.steps,
+                                        "e2e": {"value": e2e_value, "ms_per_solve": ms_e2e / args.steps},
+                                        "roofline": {"bytes_per_iteration": info.apg_bytes_per_iteration, "achieved": achieved,
+                                                     "unit": "GB/s", "frac": achieved / peak}}
+            line["by_config"] = by_config
         if alt is not None:
             line["alt_formulation"] = alt
         if alt_shared is not None:

@@ -233,6 +233,18 @@ rn_status rn_step(rn_handle *h, rn_step_kind kind, float lambda);
  *   u0_host          nullable, nu floats   = devVecU[0:nu]
  *   primal_infs_host nullable, iterations floats = vecPrimalInfs (updatePrimalInfeasibity :1480-1496) */
 rn_status rn_apg_solve(rn_handle *h, int iterations, float *u0_host, float *primal_infs_host);
+/* rn_apg_solve's primal_infs_host is this rank's log when the tree is partitioned (rn_dist_prepare with world > 1);
+ * rn_read_pinf_parts + the host merge give the global one.
+ *
+ * Continue from the duals in place instead of cold-starting (no counterpart in the reference, whose algorithmApg always
+ * zeroes them, :1509; opt-in).  Persistent sweep only; asynchronous.
+ *   warm_restart == 0: devVecUpdateXi/Psi is y_k, devVecXi/Psi is y_{k-1}; lambda_host (nullable, `iterations` floats)
+ *                      replaces the theta recursion for these iterations.  With one iteration and the golden inputs of
+ *                      TestSmpcController.cu:134-398 this runs extrapolate -> solve -> prox -> residual -> update through
+ *                      the persistent kernel.
+ *   warm_restart != 0: warm start of a closed-loop step: y_0 = y_{-1} = the duals the previous solve left, theta restarts
+ *                      at 1 (lambda_host ignored). */
+rn_status rn_apg_continue(rn_handle *h, int iterations, const float *lambda_host, int warm_restart);
 /* SmpcController::controlAction(real_t* u) (:1607-1625) when clamp == 0;
  * SmpcController::controlAction(fstream&) control vector (:1633-1667) when clamp != 0 (u0 clamped with
  * the node-0 preconditioned bounds).  Host buffers in, u0 (nu floats) out; blocking. */
@@ -246,14 +258,16 @@ rn_status rn_move_forward(rn_handle *h, float *x_next_host, float *u_applied_hos
 /* ---- one tree across several GPUs (no counterpart in the reference, which is single-GPU) ------------------------
  * Subtree partition: every rank (one process per GPU) holds the stages above the last branching stage (the "crown",
  * replicated) and a contiguous range of the scenario chains below it; its handle is created on that LOCAL tree.  Per
- * APG iteration the ranks exchange, inside the persistent kernel and over NVLink peer memory, q and r of their
- * chain heads (the near-root contributions of SmpcController::solveStep's backward sweep, :661-672) and the two
- * squared prox distances (:792, :810).  Call order: rn_create (local tree) -> rn_dist_prepare -> exchange the 64-byte
+ * APG iteration the ranks exchange, inside the persistent kernel and over NVLink peer memory, the sums of q and r over
+ * the chain heads below each node of the last crown stage (the near-root contributions of SmpcController::solveStep's
+ * backward sweep, :661-672 -- what solveSumChildren leaves in the parent's slot) and the two squared prox distances
+ * (:792, :810).  Call order: rn_create (local tree) -> rn_dist_prepare -> exchange the 64-byte
  * handles between the processes (e.g. torch.distributed.all_gather_object) -> rn_dist_connect -> factor step, solves. */
 #define RN_IPC_HANDLE_BYTES 64
 /* world <= 8 ranks; this rank owns global chains [chain_offset, chain_offset + K_local) of K_global; head_lo/head_hi
- * [number of crown nodes]: global chain-index range of the chain heads below each crown node.  Writes the CUDA IPC
- * handle of this rank's exchange buffer to ipc_handle_out. */
+ * [number of crown nodes]: global chain-index range of the chain heads below each crown node (used to check that the
+ * chains below every node of the last crown stage sit on ONE rank).  Writes the CUDA IPC handle of this rank's exchange
+ * buffer to ipc_handle_out.  Per iteration a rank sends (nx + nv) floats per node of the last crown stage it owns. */
 rn_status rn_dist_prepare(rn_handle *h, int world, int rank, int K_global, int chain_offset, const int *head_lo,
                           const int *head_hi, unsigned char *ipc_handle_out /*[RN_IPC_HANDLE_BYTES]*/);
 /* handles: world x RN_IPC_HANDLE_BYTES, rank-major (the entry of this rank is ignored) */
@@ -263,6 +277,13 @@ rn_status rn_dist_connect(rn_handle *h, const unsigned char *handles);
  * the host sums the ranks' contributions and hands the corrected zeta rows of nodes [first, first + count) back;
  * beta = 2 (W L)' zeta + p L' alpha (Engine.cu:1253-1261) is recomputed for them. */
 rn_status rn_dist_fix_crown_beta(rn_handle *h, int first, int count, const float *zeta_rows /*[count*nu]*/);
+/* The same coupling without the host in the data path.  The partition is aligned to the nodes just above the chain heads
+ * (rn_dist_prepare rejects one that is not), so the rank that holds a node's chains has its exact zeta / beta row:
+ *   pull == 0: store this rank's rows into every rank's staging table (peer memory); then synchronise the stream and
+ *              pass a barrier across the ranks;
+ *   pull != 0: copy the rows this rank does not own from its staging table into beta.
+ * Asynchronous on the handle's stream. */
+rn_status rn_dist_sync_crown_beta(rn_handle *h, int pull);
 /* per iteration (|res|, res) at the arg-max of the xi block and of the psi block of THIS rank's nodes, 4 floats each:
  * the host merges them across ranks into vecPrimalInfs (updatePrimalInfeasibity, :1480-1496) */
 rn_status rn_read_pinf_parts(rn_handle *h, int iterations, float *host /*[iterations*4]*/);
@@ -301,6 +322,9 @@ rn_status rn_phase_times(rn_handle *h, double *ns_per_iteration /*[32]*/);
 /* Load balance of the factor stream in the last rn_profile_kernels run: out[2k] = ns per iteration CTA k spent in phase S,
  * out[2k+1] = the SM it ran on.  n_ctas = size of the persistent grid. */
 rn_status rn_cta_times(rn_handle *h, double *out /*[2*cap_ctas]*/, int cap_ctas, int *n_ctas);
+/* Allocates now what the first solve would allocate lazily (the persistent kernel's private buffers), so that the first
+ * solve -- in particular the first launch of a partitioned tree, whose in-kernel waits span the GPUs -- does not. */
+rn_status rn_prepare(rn_handle *h);
 /* Caps the grid of the persistent kernel at max_ctas CTAs (0 = one per SM, the default).  Independent SMPC instances
  * (closed-loop Monte-Carlo, BASELINE config[3]) shard with no collective; on ONE GPU several handles, each on its own
  * stream with a share of the SMs, solve side by side: a tree with K scenarios keeps only K CTAs busy in its sweeps.

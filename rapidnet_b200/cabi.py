@@ -41,7 +41,7 @@ EXPORTS = [
     "rn_set_uncertainty", "rn_apg_init", "rn_step", "rn_apg_solve", "rn_control_action", "rn_move_forward",
     "rn_buffer", "rn_read_buffer", "rn_write_buffer", "rn_profile_stream", "rn_profile_kernels", "rn_phase_times", "rn_cta_times",
     "rn_dist_prepare", "rn_dist_connect", "rn_dist_fix_crown_beta", "rn_read_pinf_parts", "rn_dist_error",
-    "rn_set_grid_limit",
+    "rn_set_grid_limit", "rn_apg_continue", "rn_dist_sync_crown_beta", "rn_prepare",
 ]
 
 
@@ -107,6 +107,7 @@ def load():
     lib.rn_step.argtypes = [H, C.c_int, C.c_float]
     lib.rn_apg_solve.argtypes = [H, C.c_int, FP, FP]
     lib.rn_control_action.argtypes = [H, FP, FP, FP, FP, FP, C.c_int, C.c_int, FP]
+    lib.rn_apg_continue.argtypes = [H, C.c_int, FP, C.c_int]
     lib.rn_move_forward.argtypes = [H, FP, FP]
     lib.rn_buffer.argtypes = [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.rn_read_buffer.argtypes = [H, C.c_int, FP, C.c_size_t]
@@ -120,6 +121,8 @@ def load():
     lib.rn_dist_fix_crown_beta.argtypes = [H, C.c_int, C.c_int, FP]
     lib.rn_read_pinf_parts.argtypes = [H, C.c_int, FP]
     lib.rn_dist_error.argtypes = [H, IP]
+    lib.rn_dist_sync_crown_beta.argtypes = [H, C.c_int]
+    lib.rn_prepare.argtypes = [H]
     for name in EXPORTS:
         if name != "rn_last_error":
             getattr(lib, name).restype = C.c_int
@@ -246,6 +249,16 @@ class Solver:
                                         _fp(infs) if want_infs else None), "rn_apg_solve")
         return u0, (infs[:iterations] if want_infs else None)
 
+    def apg_continue(self, iterations: int, lambdas=None, warm_restart=False):
+        """Iterations that continue from the duals in place (UPDATE = y_k, XI/PSI = y_{k-1}); `lambdas` replaces the theta
+        recursion; warm_restart: y_0 = y_{-1} = the previous solve's duals, theta restarted.  Persistent sweep only."""
+        lam = None if lambdas is None else np.ascontiguousarray(lambdas, dtype=np.float32)
+        if lam is not None and lam.size < iterations:
+            raise ValueError("apg_continue: one lambda per iteration")
+        self._check(load().rn_apg_continue(self.h, int(iterations), _fp(lam) if lam is not None else None,
+                                           int(bool(warm_restart))), "rn_apg_continue")
+        self.sync()
+
     def control_action(self, x, u_prev, d_prev, d_hat, alpha_hat, iterations: int, clamp=False, out=None):
         args = [np.ascontiguousarray(a, dtype=np.float32) for a in (x, u_prev, d_prev, d_hat, alpha_hat)]
         u0 = np.zeros(self.dims.nu, dtype=np.float32) if out is None else out
@@ -269,6 +282,13 @@ class Solver:
     def dist_fix_crown_beta(self, first: int, zeta_rows):
         z = np.ascontiguousarray(zeta_rows, dtype=np.float32)
         self._check(load().rn_dist_fix_crown_beta(self.h, int(first), int(z.shape[0]), _fp(z)), "rn_dist_fix_crown_beta")
+
+    def dist_sync_crown_beta(self, pull: bool):
+        self._check(load().rn_dist_sync_crown_beta(self.h, int(bool(pull))), "rn_dist_sync_crown_beta")
+
+    def prepare_persistent(self):
+        """allocate what the first solve would allocate (so that the first timed / cross-GPU launch does not)"""
+        self._check(load().rn_prepare(self.h), "rn_prepare")
 
     def pinf_parts(self, iterations: int) -> np.ndarray:
         out = np.zeros((max(iterations, 1), 4), dtype=np.float32)

@@ -514,6 +514,7 @@ struct FinalArgs {
     float *scal;          // [0] d1, [1] d2, [2] branch-1 taken, [3] branch-2 taken
     float *pinf;          // per-iteration primal infeasibility log
     float *pinf_part;     // [grid][6] : abs, signed, idx for xi ; abs, signed, idx for psi
+    float *pinf4;         // nullable: [iterations][4] |res|, res at the arg-max of the xi block and of the psi block (rn_read_pinf_parts)
     int *iter;
     unsigned int *done;
     int nodes, nx, nu, n_slots;
@@ -608,6 +609,7 @@ __global__ void __launch_bounds__(kEwThreads) k_finalize(const __grid_constant__
         }
         const int it = *F.iter;
         F.pinf[it] = fmaxf(x.v, p.v);    // max(maxValueXi, maxValuePsi) (:1495)
+        if (F.pinf4) { float *o4 = F.pinf4 + 4 * (size_t)it; o4[0] = x.a; o4[1] = x.v; o4[2] = p.a; o4[3] = p.v; }
         F.scal[0] = d1; F.scal[1] = d2; F.scal[2] = br1; F.scal[3] = br2;
         *F.iter = it + 1;
         *F.done = 0u;
@@ -903,6 +905,7 @@ static rn_status enqueue_persistent(Handle *h, int iterations) {
         FinalArgs F = make_final_args(h);
         F.yA_xi = h->yA_xi; F.yA_psi = h->yA_psi; F.yB_xi = h->yB_xi; F.yB_psi = h->yB_psi;
         F.n_slots = h->dist_world > 1 ? 1 : h->persist_grid;   // several GPUs: the kernel left the global sums in slot 0
+        F.pinf4 = h->pinf4;                                    // the last iteration's row of the per-rank log
         F.do_branch = 1; F.do_residual = 1; F.do_update = 1; F.parity_swap = 1; F.log_inf = 1;
         k_finalize<<<finalize_grid(h), kEwThreads, 0, h->stream>>>(F);
         RN_CUDA(h, cudaGetLastError());
@@ -947,6 +950,49 @@ rn_status apg_enqueue(Handle *h, int iterations) {
     h->launches += per_iter * iterations;
     if (iterations & 1) { std::swap(h->upd_xi, h->xi); std::swap(h->upd_psi, h->psi); }   // y_k now lives in the B buffers
     return RN_OK;
+}
+
+// `iterations` fused iterations that CONTINUE from the duals in place instead of the cold start of algorithmApg (:1509):
+// devVecUpdateXi/Psi is taken as y_k and devVecXi/Psi as y_{k-1}; lambda_host (nullable) replaces the theta recursion for
+// these iterations.  The persistent kernel's iteration 0 forms y_0 = w_prev + step (Hx - z), so it is handed
+// w_prev = y_k with Hx = z = 0 (y_0 == y_k exactly) and y_{k-1} in the "previous" iterate buffer.
+rn_status apg_continue(Handle *h, int iterations, const float *lambda_host) {
+    if (!use_persistent(h)) return fail(h, RN_ERR_INVALID, "rn_apg_continue needs the persistent sweep on a tree it supports");
+    if (iterations <= 0) return RN_OK;
+    const rn_dims &d = h->d;
+    RN_CHECK(ensure_lambda(h, iterations));
+    if (lambda_host) {
+        RN_CUDA(h, cudaMemcpyAsync(h->lambda_tab, lambda_host, (size_t)iterations * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        RN_CUDA(h, cudaStreamSynchronize(h->stream));   // the caller's array may be pageable
+        h->lambda_ready = 0;                            // the next cold solve restores the theta recursion
+    }
+    const size_t bx = (size_t)d.nodes * 2 * d.nx * sizeof(float), bp = (size_t)d.nodes * d.nu * sizeof(float);
+    const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+    // y_k -> wB first (it never aliases a y buffer), then y_{k-1} -> yB unless it already lives there
+    RN_CUDA(h, cudaMemcpyAsync(h->wB_xi, h->upd_xi, bx, k, h->stream));
+    RN_CUDA(h, cudaMemcpyAsync(h->wB_psi, h->upd_psi, bp, k, h->stream));
+    if (h->xi != h->yB_xi) {
+        RN_CUDA(h, cudaMemcpyAsync(h->yB_xi, h->xi, bx, k, h->stream));
+        RN_CUDA(h, cudaMemcpyAsync(h->yB_psi, h->psi, bp, k, h->stream));
+    }
+    RN_CUDA(h, cudaMemsetAsync(h->pri_xi, 0, bx, h->stream)); RN_CUDA(h, cudaMemsetAsync(h->pri_psi, 0, bp, h->stream));
+    RN_CUDA(h, cudaMemsetAsync(h->dual_xi, 0, bx, h->stream)); RN_CUDA(h, cudaMemsetAsync(h->dual_psi, 0, bp, h->stream));
+    RN_CUDA(h, cudaMemsetAsync(h->iter_dev, 0, sizeof(int), h->stream));
+    RN_CUDA(h, cudaMemsetAsync(h->done_ctr, 0, sizeof(unsigned int), h->stream));
+    h->upd_xi = h->yA_xi; h->upd_psi = h->yA_psi; h->xi = h->yB_xi; h->psi = h->yB_psi;
+    h->acc_xi = h->wA_xi; h->acc_psi = h->wA_psi;
+    return enqueue_persistent(h, iterations);
+}
+
+// warm start (opt-in; the reference always cold-starts, :420-450, :1509): y_0 = y_{-1} = the duals the previous
+// solve left in devVecUpdateXi/Psi, theta restarted at 1
+rn_status apg_warm(Handle *h, int iterations) {
+    if (!use_persistent(h)) return fail(h, RN_ERR_INVALID, "warm start needs the persistent sweep on a tree it supports");
+    const rn_dims &d = h->d;
+    const size_t bx = (size_t)d.nodes * 2 * d.nx * sizeof(float), bp = (size_t)d.nodes * d.nu * sizeof(float);
+    RN_CUDA(h, cudaMemcpyAsync(h->xi, h->upd_xi, bx, cudaMemcpyDeviceToDevice, h->stream));
+    RN_CUDA(h, cudaMemcpyAsync(h->psi, h->upd_psi, bp, cudaMemcpyDeviceToDevice, h->stream));
+    return apg_continue(h, iterations, nullptr);
 }
 
 rn_status apg_step(Handle *h, rn_step_kind kind, float lambda) {

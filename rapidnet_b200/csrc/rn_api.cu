@@ -365,6 +365,15 @@ rn_status rn_apg_solve(rn_handle *hh, int iterations, float *u0_host, float *pri
     return RN_OK;
 }
 
+rn_status rn_apg_continue(rn_handle *hh, int iterations, const float *lambda_host, int warm_restart) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || iterations < 0) return RN_ERR_INVALID;
+    if (!h->factored || !h->eliminated) return rn::fail(h, RN_ERR_STATE, "rn_apg_continue before factor step / eliminate");
+    RN_CUDA(h, cudaSetDevice(h->device));
+    if (warm_restart) return rn::apg_warm(h, iterations);
+    return rn::apg_continue(h, iterations, lambda_host);
+}
+
 rn_status rn_control_action(rn_handle *hh, const float *x, const float *u_prev, const float *d_prev,
                             const float *d_hat, const float *alpha_hat, int iterations, int clamp, float *u0_host) {
     Handle *h = reinterpret_cast<Handle *>(hh);
@@ -406,6 +415,17 @@ rn_status rn_dist_prepare(rn_handle *hh, int world, int rank, int K_global, int 
     const int n_crown = h->h_cum[h->chain_stage];
     if (chain_offset < 0 || chain_offset + h->d.K > K_global) return rn::fail(h, RN_ERR_INVALID, "rn_dist_prepare: chain range outside K_global");
     if (world > 1 && (!head_lo || !head_hi)) return rn::fail(h, RN_ERR_INVALID, "rn_dist_prepare: head ranges missing");
+    if (world > 1) {
+        // the partition must be aligned to the bottom-crown nodes (stage cs-1): the chains below one of them live on ONE rank
+        // (its sum over them, S_p, and its zeta are then formed by that rank alone, in the order of the single-GPU solve)
+        const int cs = h->chain_stage;
+        if (cs <= 0) return rn::fail(h, RN_ERR_INVALID, "rn_dist_prepare: the tree has no crown to cut below");
+        for (int p = h->h_cum[cs - 1]; p < h->h_cum[cs]; p++) {
+            const int local = h->h_child_count[p], global = head_hi[p] - head_lo[p];
+            if (local != 0 && local != global)
+                return rn::fail(h, RN_ERR_INVALID, "rn_dist_prepare: the chains below crown node %d are split across ranks (%d of %d here)", p, local, global);
+        }
+    }
     h->dist_world = world; h->dist_rank = rank; h->dist_K_glob = K_global; h->dist_chain_off = chain_offset;
     if (world > 1) { h->dist_head_lo.assign(head_lo, head_lo + n_crown); h->dist_head_hi.assign(head_hi, head_hi + n_crown); }
     RN_CUDA(h, cudaSetDevice(h->device));
@@ -440,11 +460,29 @@ rn_status rn_dist_fix_crown_beta(rn_handle *hh, int first, int count, const floa
     return rn::fix_beta(h, first, count, zeta_rows);
 }
 
+rn_status rn_prepare(rn_handle *hh) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return RN_ERR_INVALID;
+    RN_CUDA(h, cudaSetDevice(h->device));
+    if (h->sweep_mode == RN_SWEEP_PERSISTENT && rn::persistent_supported(h)) RN_CHECK(rn::persistent_prepare(h));
+    RN_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RN_OK;
+}
+
+rn_status rn_dist_sync_crown_beta(rn_handle *hh, int pull) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return RN_ERR_INVALID;
+    if (!h->eliminated) return rn::fail(h, RN_ERR_STATE, "rn_dist_sync_crown_beta before rn_eliminate_coupling");
+    RN_CUDA(h, cudaSetDevice(h->device));
+    return rn::dist_crown_beta(h, pull);
+}
+
 rn_status rn_read_pinf_parts(rn_handle *hh, int iterations, float *host) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (!h || !host || iterations < 0) return RN_ERR_INVALID;
     if (iterations > h->pinf4_cap) return rn::fail(h, RN_ERR_STATE, "rn_read_pinf_parts: only %d iterations were logged", h->pinf4_cap);
-    // iterations 0 .. n-2 come from the persistent kernel; the last one is finished by k_finalize (scalar log only)
+    // rows 0 .. n-2 come from the persistent kernel, row n-1 from k_finalize.  With a partitioned tree every row holds THIS
+    // rank's arg-max (rn_apg_solve's primal_infs_host is then rank-local too); partition.merge_pinf combines the ranks.
     RN_CUDA(h, cudaMemcpyAsync(host, h->pinf4, (size_t)iterations * 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     RN_CUDA(h, cudaStreamSynchronize(h->stream));
     return RN_OK;
@@ -455,14 +493,8 @@ rn_status rn_dist_error(rn_handle *hh, int *timed_out) {
     if (!h || !timed_out) return RN_ERR_INVALID;
     *timed_out = 0;
     if (!h->xchg) return RN_OK;
-    // the flag is the last word of the exchange buffer (rn_persist.cu: xchg_layout)
     RN_CUDA(h, cudaStreamSynchronize(h->stream));
-    size_t off = 0;
-    {
-        const size_t Kg = (size_t)(h->dist_world > 1 ? h->dist_K_glob : h->d.K);
-        auto take = [&](size_t bytes) { size_t at = off; off = (off + bytes + 255) & ~size_t(255); return at; };
-        take(Kg * h->d.nx * 4); take(Kg * h->d.nv * 4); take(8 * 4 * 8); take(8 * 4); take(4);
-    }
+    const size_t off = rn::xchg_err_offset(h);
     RN_CUDA(h, cudaMemcpy(timed_out, static_cast<char *>(h->xchg) + off, sizeof(int), cudaMemcpyDeviceToHost));
     return RN_OK;
 }

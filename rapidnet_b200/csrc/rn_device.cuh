@@ -49,6 +49,11 @@ __device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src, u
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
+// global -> L2 bulk prefetch (no shared-memory destination): 16-B aligned address, size multiple of 16; SASS: UBLKPF.L2
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ float clampf(float v, float lo, float hi) {   // projectionBox (Utilities.cu:237-254)
     if (v < lo) return lo; else if (v > hi) return hi; return v;
 }

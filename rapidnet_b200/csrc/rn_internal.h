@@ -108,6 +108,7 @@ struct Handle {
     bool xchg_opened[8] = {false, false, false, false, false, false, false, false};
     unsigned int xepoch = 0;
     float *pinf4 = nullptr;
+    float *head_q = nullptr, *head_r = nullptr;    // q / r of this rank's chain heads (persistent kernel)
     int pinf4_cap = 0;
     float *cm_c = nullptr, *cm_lv = nullptr, *cm_beta = nullptr, *cm_uhat = nullptr, *cm_e = nullptr;   // chain-major arrays
     int *crown_rng = nullptr, *pos_dev = nullptr, *crown_path = nullptr;
@@ -115,6 +116,7 @@ struct Handle {
     unsigned long long *phase_ns = nullptr, *cta_ns = nullptr;
     std::vector<unsigned long long> last_cta_ns;
     bool persist_ready = false;
+    bool pack_dirty = true;          // the sweep pack must be re-copied from the factor-step outputs before the next launch
     unsigned long long last_phase_ns[32] = {0};
     int last_phase_iters = 0;
     int persist_grid = 0;
@@ -189,12 +191,16 @@ rn_status fix_beta(Handle *h, int first, int count, const float *zeta_rows);
 rn_status apg_init(Handle *h);
 rn_status apg_step(Handle *h, rn_step_kind kind, float lambda);
 rn_status apg_enqueue(Handle *h, int iterations);
+rn_status apg_continue(Handle *h, int iterations, const float *lambda_host);
+rn_status apg_warm(Handle *h, int iterations);
 rn_status apg_release_graph(Handle *h);
 rn_status profile_stream(Handle *h, int reps, float *mean_ms);
 rn_status profile_kernels(Handle *h, int iterations, float *ms_out);
 bool persistent_supported(const Handle *h);
 rn_status persistent_prepare(Handle *h);
 rn_status ensure_xchg(Handle *h);
+size_t xchg_err_offset(const Handle *h);
+rn_status dist_crown_beta(Handle *h, int pull);
 rn_status persistent_launch(Handle *h, cudaStream_t st, int iters);
 rn_status clamp_control(Handle *h);
 rn_status move_forward(Handle *h);

@@ -56,6 +56,7 @@ constexpr int kMaxCs = 8;                       // deepest crown supported (stag
 constexpr int kDimMax = 128;                    // max(2nx, nu, nv) supported by this kernel
 constexpr int kMaxRanks = 8;                    // GPUs of one node
 constexpr double kL2KeepDefault = 0.1;          // RN_L2_KEEP default: share of the L2 given to evict_last factor matrices
+constexpr double kL2PrefDefault = 0.4;          // RN_L2_PREFETCH default: share of the L2 refilled with the next iteration's matrices during the sweeps
 
 struct PArgs {
     const int *parent, *child_first, *child_count, *omega_idx, *cum, *stages;
@@ -65,6 +66,7 @@ struct PArgs {
     unsigned int branch_mask;                   // bit s: stage s has more nodes than stage s-1 (the reference's branching stages, :699-719)
     int N, cs, K, nodes, n_crown, n_mats, df_mode, iters, nx, nu, nv, cols_per_chunk, clock_cta;
     float l2_keep;                              // share of every CTA's stream units whose matrices are loaded with L2 evict_last (0 = plain loads)
+    float l2_pref;                              // share of every CTA's stream units (behind the kept ones) pulled into L2 while the sweeps run
     int sh_mode, sh_tile;                       // RN_FACTORS_SHARED: no per-node matrix is read; nodes per tile of its phase S
     int sh_oLt, sh_oC, sh_oGc, sh_oY, sh_oScr2, sh_oVec;   // its shared-memory layout (float offsets; G sits at kOffSweep)
     int n_stages, stage_stride;                 // matrix ring: stages and floats per stage (payload + 32 floats of slack)
@@ -84,16 +86,21 @@ struct PArgs {
     // the crown is replicated.  Every rank's exchange buffer is mapped into every process (CUDA IPC); index = rank.
     int n_ranks, rank, K_glob, chain_off;
     unsigned int epoch0;                        // cross-GPU barrier epochs of this launch start after epoch0
-    float *qh_peer[kMaxRanks], *rh_peer[kMaxRanks];        // q / r of ALL chain heads [K_glob*nx], [K_glob*nv] on each rank
+    float *hq, *hr;                             // q / r of this rank's chain heads [K*nx], [K*nv] (local)
+    // Near-root exchange: S_p = sum over the chain heads below bottom-crown node p (stage cs-1) of (q, r), formed by the rank
+    // that owns p's chains in ascending child order (the same bits for any number of ranks) and stored into EVERY rank's
+    // table, indexed by crown node id: [n_crown*nx], [n_crown*nv].  solveSumChildren (Utilities.cu:168-201) one level up.
+    float *Sq_peer[kMaxRanks], *Sr_peer[kMaxRanks];
+    unsigned int *par_ctr;                      // [n_crown] local: chains of a bottom-crown node whose head q, r are in hq / hr (cumulative)
+    unsigned int *s_ctr;                        // local, one GPU: bottom-crown nodes whose S row is published (cumulative)
+    int bottom0, n_bottom, n_owned;             // bottom-crown nodes: first id, count, how many of them have their chains on this rank
     double *dslot_peer[kMaxRanks];              // [kMaxRanks][2] squared prox distances of each rank, on each rank
     unsigned int *xflag_peer[kMaxRanks];        // [kMaxRanks] arrival epochs, on each rank
-    unsigned int *release;                      // local: epoch up to which the cross-GPU barriers are released
     int *xerr;                                  // local: set when a cross-GPU wait timed out
     float *pinf4;                               // [iters][4] |res|, res at the arg-max of the xi block and of the psi block
     float *pinf, *pinf_part;                    // [iters], [grid*6]
     const float *lambda_tab;
     unsigned int *bar;
-    unsigned int *heads_ctr;                    // chains whose head q, r are published (single GPU: the crown waits on it instead of a grid barrier)
     int *iter_dev;
     unsigned long long *phase_ns;               // [32] fine-grained phase clock of one CTA (see cabi.PHASE_NAMES)
     unsigned long long *cta_ns;                 // [grid][2] per CTA: time spent in phase S (ns, summed over iterations), SM id
@@ -182,27 +189,27 @@ __device__ __forceinline__ void wait_sys(const unsigned int *p, unsigned int wan
 // grid sync does at device scope.
 __device__ __noinline__ void grid_sync_cross(const PArgs &P, unsigned int target, unsigned int ep, int publish_it) {
     cbar();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        atomicAdd(P.bar, 1u);
+    if (threadIdx.x < 32) {   // one warp; lane r talks to peer r
+        const int lane = threadIdx.x;
+        if (lane == 0) { __threadfence_system(); atomicAdd(P.bar, 1u); }
         if (blockIdx.x == 0) {
-            while (ld_acquire_u32(P.bar) < target) {}
-            if (publish_it >= 0) {
-                double t1 = 0, t2 = 0;   // this rank's share, CTA order
-                for (int k = 0; k < (int)gridDim.x; k++) { t1 += __ldcg(P.dist_part + 2 * k); t2 += __ldcg(P.dist_part + 2 * k + 1); }
-                for (int r = 0; r < P.n_ranks; r++) {
-                    double *ds = P.dslot_peer[r] + 2 * (publish_it & 1) + 4 * P.rank;
+            if (lane == 0) while (ld_acquire_u32(P.bar) < target) {}
+            __syncwarp();
+            if (publish_it >= 0) {   // this rank's share of the two squared prox distances, CTA order, fixed lane tree
+                double t1 = 0, t2 = 0;
+                for (int k = lane; k < (int)gridDim.x; k += 32) { t1 += __ldcg(P.dist_part + 2 * k); t2 += __ldcg(P.dist_part + 2 * k + 1); }
+                for (int o = 16; o > 0; o >>= 1) { t1 += __shfl_xor_sync(0xffffffffu, t1, o); t2 += __shfl_xor_sync(0xffffffffu, t2, o); }
+                if (lane < P.n_ranks) {
+                    double *ds = P.dslot_peer[lane] + 2 * (publish_it & 1) + 4 * P.rank;
                     ds[0] = t1; ds[1] = t2;
                 }
             }
-            __threadfence_system();
-            for (int r = 0; r < P.n_ranks; r++) st_release_sys_u32(P.xflag_peer[r] + P.rank, ep);
-            for (int r = 0; r < P.n_ranks; r++) wait_sys(P.xflag_peer[P.rank] + r, ep, P.xerr);
-            __threadfence_system();
-            st_release_sys_u32(P.release, ep);
-        } else {
-            wait_sys(P.release, ep, P.xerr);
+            __threadfence_system();   // lane 0's acquire of the local arrivals + every lane's own stores, before its flag store
+            if (lane < P.n_ranks) st_release_sys_u32(P.xflag_peer[lane] + P.rank, ep);
         }
+        // every CTA polls the arrival flags itself (they live in this GPU's memory): no second hop through a release word
+        if (lane < P.n_ranks) wait_sys(P.xflag_peer[P.rank] + lane, ep, P.xerr);
+        __syncwarp();
         __threadfence();
     }
     cbar();
@@ -221,7 +228,7 @@ constexpr int kOffMeta = kOffMisc + 4 * kTP;                             // 64 w
 constexpr int kOffFix = kOffMeta + 64;                                  // u_prev | uhat_prev | x_cur, kVStride floats each (per launch)
 constexpr int kOffClk = (kOffFix + 3 * kVStride + 1) & ~1;                   // 34 x u64: phase clock accumulators, t_prev, enabled
 constexpr int kOffPArgs = kOffClk + 2 * 34;                            // a copy of the kernel arguments (see k_apg_persistent)
-constexpr int kPArgsWords = 256;
+constexpr int kPArgsWords = 288;
 constexpr int kOffBar = kOffPArgs + kPArgsWords;                                  // mbarriers
 constexpr int kNumBars = 2 * kPStages + 2 * kVecSlots + 8 + 8;
 constexpr int kOffVec = (kOffBar + 2 * kNumBars + 31) & ~31;            // kVecSlots x kVecCount x kVStride
@@ -671,8 +678,7 @@ __device__ __noinline__ void chain_qscan(const PArgs &P, int j) {
         x1[s] = qrun;
         qrun = c + qrun;
     }
-    const size_t hrow = (size_t)(P.chain_off + j) * nx + e;   // every rank's copy of the table (own copy: plain store)
-    for (int r = 0; r < P.n_ranks; r++) P.qh_peer[r][hrow] = qrun;
+    P.hq[(size_t)j * nx + e] = qrun;
 }
 
 // r-scan: sigma = beta + r_child (:599); r = ((sigma + D xi) + F psi) + G q_bar (:631-646).  Y = G q_bar on entry.
@@ -694,8 +700,7 @@ __device__ __noinline__ void chain_rscan(const PArgs &P, int j) {
         rrun = ((sg + s0[s * nvp]) + s1[s * nvp]) + ys;
         x1[s] = -0.5f * (df ? rrun : sg + ys);
     }
-    const size_t hrow = (size_t)(P.chain_off + j) * nv + e;
-    for (int r = 0; r < P.n_ranks; r++) P.rh_peer[r][hrow] = rrun;
+    P.hr[(size_t)j * nv + e] = rrun;
 }
 
 __device__ __noinline__ void chain_backward(const PArgs &P, int j, int next_chain, uint32_t mpar, StagePhase &ph) {
@@ -711,9 +716,9 @@ __device__ __noinline__ void chain_backward(const PArgs &P, int j, int next_chai
     mbar_wait(&S.sfull[1], ph.r); ph.r ^= 1;
     chain_rscan(P, j);
     cbar();
-    if (threadIdx.x == 0 && P.n_ranks == 1 && P.n_crown > 0) {   // this chain's head q, r are in the tables: tell the crown
+    if (threadIdx.x == 0 && P.n_crown > 0) {   // this chain's head q, r are in the tables: tell whoever sums its parent's heads
         __threadfence();
-        atomicAdd(P.heads_ctr, 1u);
+        atomicAdd(P.par_ctr + S.anc[P.cs - 1], 1u);
     }
     dstamp(P, 5);
     sweep_backward_finish(P, P.N - P.cs, true, mpar, ph, next_chain);
@@ -881,92 +886,127 @@ __device__ __noinline__ void chain_forward(const PArgs &P, int j, int next_chain
 //   QS_i    = sum_{crown j below i} q_bar_j = sum_{crown j below i} (s_j - s_i - 1) c_j + (cs - 1 - s_i) sum_{heads} q_h
 // (the descendants of a node are one contiguous id range per stage: children are contiguous, Utilities.cu:184-199).
 // X1 q-rows: columns 0..n-1 = QS_i, columns 12..12+n-1 = q_bar_i (one G GEMM gives both products); V rows = base_i
-// sums over the rows lo + g, lo + g + 4, ... < hi (g = thread group) of a[row][lda] and of b0[row][ldb] (three:
-// (b0 + b1) + b2, same rows), eight rows in flight per trip; rows are added in ascending order
-__device__ __noinline__ void range_sum(const float *__restrict__ a, int lda, bool ea, const float *__restrict__ b0, const float *__restrict__ b1,
-                                       const float *__restrict__ b2, int ldb, bool eb, bool three, int lo, int hi, float &sa, float &sb) {
-    const int g = threadIdx.x >> 7;
-    float accA = 0.f, accB = 0.f;
-#ifdef RN_EXP_RANGESUM16   // experimental (tools/build_variants.sh): 16 rows in flight per trip for the long head ranges of large crowns
-    constexpr int kRows = 16;
-#else
+// Sums over the rows [lo, hi) of chain-major arrays, as float4 columns.  The CTA is 8 row groups of two warps: the even warp of
+// a pair adds rows of A (row length ldA: c or S_q), the odd warp rows of B0 (+ B1 + B2: beta + D xi + F psi, or S_r); lane =
+// float4 column.  Group g takes rows lo + g, lo + g + 8, ...; kRows of them in flight per trip, added in ascending order.
+// acc += sum, accw += w * sum (even warps only; w = how many times the rows count in QS).
+struct F4 { float x, y, z, w; };
+__device__ __forceinline__ void f4_add(F4 &a, const float4 &v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+__device__ __noinline__ void range_sum(const float *__restrict__ A, int ldA, int dimA, const float *__restrict__ B0, const float *__restrict__ B1,
+                                       const float *__restrict__ B2, int ldB, int dimB, bool three, int lo, int hi, float w, F4 &acc, F4 &accw) {
+    const int t = threadIdx.x, g = t >> 6, role = (t >> 5) & 1, c4 = t & 31;
     constexpr int kRows = 8;
-#endif
+    const bool active = 4 * c4 < (role ? dimB : dimA);
+    if (!active) return;
+    const float *base = (role ? B0 : A) + 4 * c4;
+    const int ld = role ? ldB : ldA;
+    const ptrdiff_t d1 = B1 - B0, d2 = B2 - B0;
+    F4 sum{0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int jn = lo + g; jn < hi; jn += 4 * kRows) {
-        float av[kRows], bv[kRows];
+    for (int jn = lo + g; jn < hi; jn += 8 * kRows) {
+        float4 v[kRows];
 #pragma unroll
         for (int k = 0; k < kRows; k++) {
-            const int r = jn + 4 * k;
-            const bool ok = r < hi;
-            const size_t rr = (size_t)(ok ? r : lo);
-            av[k] = (ea && ok) ? __ldcg(a + rr * lda) : 0.f;
-            float bb = 0.f;
-            if (eb && ok) {
-                bb = __ldcg(b0 + rr * ldb);
-                if (three) bb = (bb + __ldcg(b1 + rr * ldb)) + __ldcg(b2 + rr * ldb);
+            const int r = jn + 8 * k;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < hi) {
+                const float *q = base + (size_t)r * ld;
+                v[k] = __ldcg(reinterpret_cast<const float4 *>(q));
+                if (role && three) {
+                    const float4 b1 = __ldcg(reinterpret_cast<const float4 *>(q + d1)), b2 = __ldcg(reinterpret_cast<const float4 *>(q + d2));
+                    v[k].x = (v[k].x + b1.x) + b2.x; v[k].y = (v[k].y + b1.y) + b2.y; v[k].z = (v[k].z + b1.z) + b2.z; v[k].w = (v[k].w + b1.w) + b2.w;
+                }
             }
-            bv[k] = bb;
         }
 #pragma unroll
-        for (int k = 0; k < kRows; k++) { accA += av[k]; accB += bv[k]; }
+        for (int k = 0; k < kRows; k++) f4_add(sum, v[k]);
     }
-    sa = accA; sb = accB;
+    acc.x += sum.x; acc.y += sum.y; acc.z += sum.z; acc.w += sum.w;
+    if (!role) { accw.x += w * sum.x; accw.y += w * sum.y; accw.z += w * sum.z; accw.w += w * sum.w; }
 }
 
-// `wait_heads`: single GPU -- the heads' q, r are awaited here (a counter the chains bump after their r-scan), after the
+// S_p of bottom-crown node p (stage cs-1): q and r of its chain heads added in ascending child order -- what
+// solveSumChildren (Utilities.cu:168-201) leaves in the parent's slot -- stored into every rank's table.  The CTA waits
+// for p's chains (a counter they bump after their r-scan).  Threads 0..127: q rows, 128..255: r rows.
+__device__ __noinline__ void parent_sum(const PArgs &P, int p, int it) {
+    const int t = threadIdx.x, nx = P.nx, nv = P.nv;
+    const int c0 = __ldg(P.child_first + p) - __ldg(P.cum + P.cs), nc = __ldg(P.child_count + p);   // chain indices of p's heads
+    if (t == 0) {
+        const unsigned int want = (unsigned)nc * (unsigned)(it + 1);
+        while ((int)(ld_acquire_u32(P.par_ctr + p) - want) < 0) {}
+        __threadfence();
+    }
+    cbar();
+    const bool isq = t < 128;
+    const int e = isq ? t : t - 128, dim = isq ? nx : nv;
+    if (t < 256 && e < dim) {
+        const float *src = (isq ? P.hq : P.hr) + (size_t)c0 * dim + e;
+        float acc = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < nc; cb += 8) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = cb + k < nc ? __ldcg(src + (size_t)(cb + k) * dim) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (cb + k < nc) acc = (cb + k == 0) ? v[k] : acc + v[k];
+        }
+        const size_t o = (size_t)p * (isq ? P.nxp : P.nvp) + e;
+        for (int r = 0; r < P.n_ranks; r++) (isq ? P.Sq_peer[r] : P.Sr_peer[r])[o] = acc;
+    }
+    cbar();
+    if (t == 0 && P.n_ranks == 1) { __threadfence(); atomicAdd(P.s_ctr, 1u); }   // several GPUs: the barrier across them follows
+}
+
+// `wait_s`: single GPU -- the S rows of the bottom-crown nodes are awaited here (a counter parent_sum bumps), after the
 // first column's sums over its crown descendants, so that the crown overlaps the chains' backward sweep
-__device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols, unsigned int wait_heads, uint32_t mpar) {
+__device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols, unsigned int wait_s, uint32_t mpar) {
     const SweepSmem S = sweep_smem(P);
-    const int t = threadIdx.x, g = t >> 7, e = t & 127, nx = P.nx, nv = P.nv, cs = P.cs, nxp = P.nxp, nvp = P.nvp;
-    const bool ex = e < nx, ev = e < nv;
+    const int t = threadIdx.x, g = t >> 6, role = (t >> 5) & 1, c4 = t & 31, nx = P.nx, nv = P.nv, cs = P.cs, nxp = P.nxp, nvp = P.nvp;
+    static_assert(8 * 3 * 128 <= 128 * kTP, "partial sums of the row groups fit the split-K scratch");
 #pragma unroll 1
     for (int col = 0; col < ncols; col++) {
         const int i = i0 + col, si = __ldg(P.stages + i);
         const int *rng = P.crown_rng + (size_t)i * (kMaxCs + 1) * 2;
-        float qb = 0.f, qs = 0.f, bs = 0.f;
+        F4 acc{0.f, 0.f, 0.f, 0.f}, accw{0.f, 0.f, 0.f, 0.f};   // even warps: q_bar, QS; odd warps: sums of beta + D xi + F psi and of r
 #pragma unroll 1
-        for (int s = si + 1; s < cs; s++) {
-            float cpart, bpart;
-            range_sum(P.cm_c + e, nxp, ex, P.cm_beta + e, P.part[0] + e, P.part[1] + e, nvp, ev, true, __ldg(rng + 2 * s), __ldg(rng + 2 * s + 1),
-                      cpart, bpart);
-            qb += cpart; qs += (float)(s - si - 1) * cpart; bs += bpart;
-        }
-        if (col == 0 && wait_heads) {
+        for (int s = si + 1; s < cs; s++)
+            range_sum(P.cm_c, nxp, nx, P.cm_beta, P.part[0], P.part[1], nvp, nv, true, __ldg(rng + 2 * s), __ldg(rng + 2 * s + 1),
+                      (float)(s - si - 1), acc, accw);
+        if (col == 0 && wait_s) {
             // while the chains are still scanning: run the GEMM once on whatever X1 holds (two k-steps, result overwritten
             // later) -- it pulls tile_gemm's code into the instruction cache, which is cold at this point of every iteration
             mbar_wait(&S.mfull[0], mpar);
             if (ncols == 1) tile_gemv2(S.G, nv, 4, S.X1, S.Y, S.scr2, 0, 12);
             else tile_gemm(S.G, nv, 2, S.X1, S.Y, S.scr2);
             if (t == 0) {
-                while ((int)(ld_acquire_u32(P.heads_ctr) - wait_heads) < 0) {}
+                while ((int)(ld_acquire_u32(P.s_ctr) - wait_s) < 0) {}
                 __threadfence();
             }
             cbar();
         }
         {
-            float hq, hr;   // (global) chain indices of the heads below i
-            range_sum(P.qh_peer[P.rank] + e, nx, ex, P.rh_peer[P.rank] + e, nullptr, nullptr, nv, ev, false, __ldg(rng + 2 * cs),
-                      __ldg(rng + 2 * cs + 1), hq, hr);
-            qb += hq; qs += (float)(cs - 1 - si) * hq; bs += hr;
+            // the heads below i, through the S rows of the bottom-crown nodes below i (i itself when it is one)
+            const int blo = si == cs - 1 ? i : __ldg(rng + 2 * (cs - 1)), bhi = si == cs - 1 ? i + 1 : __ldg(rng + 2 * (cs - 1) + 1);
+            range_sum(P.Sq_peer[P.rank], nxp, nx, P.Sr_peer[P.rank], nullptr, nullptr, nvp, nv, false, blo, bhi, (float)(cs - 1 - si), acc, accw);
         }
-        float *sc = S.scr2 + g * 3 * 128;
-        sc[e] = qb; sc[128 + e] = qs; sc[256 + e] = bs;
+        {
+            float *sc = S.scr2 + (g * 3 + (role ? 2 : 0)) * 128 + 4 * c4;
+            *reinterpret_cast<float4 *>(sc) = make_float4(acc.x, acc.y, acc.z, acc.w);
+            if (!role) *reinterpret_cast<float4 *>(sc + 128) = make_float4(accw.x, accw.y, accw.z, accw.w);
+        }
         cbar();
-        if (g == 0) {
-            const float *s0 = S.scr2;
-            if (ex) {
-                S.X1[e * kTP + 12 + col] = ((s0[e] + s0[384 + e]) + s0[768 + e]) + s0[1152 + e];                      // q_bar
-                S.X1[e * kTP + col] = ((s0[128 + e] + s0[512 + e]) + s0[896 + e]) + s0[1280 + e];                     // QS
-            }
-            if (ev)
-                S.V[e * kTP + col] = __ldg(P.cm_beta + (size_t)i * nvp + e) +
-                                     (((s0[256 + e] + s0[640 + e]) + s0[1024 + e]) + s0[1408 + e]);                   // sigma - G QS
+        if (t < 128) {
+            const float *s0 = S.scr2 + t;
+            float qb = s0[0], qs = s0[128], bs = s0[256];
+#pragma unroll
+            for (int k = 1; k < 8; k++) { qb += s0[k * 384]; qs += s0[k * 384 + 128]; bs += s0[k * 384 + 256]; }
+            if (t < nx) { S.X1[t * kTP + 12 + col] = qb; S.X1[t * kTP + col] = qs; }                    // q_bar, QS
+            if (t < nv) S.V[t * kTP + col] = __ldg(P.cm_beta + (size_t)i * nvp + t) + bs;               // sigma - G QS
         }
         cbar();
     }
-    if (g == 0 && ex) {   // unused columns: zeros
-        float *x1 = S.X1 + e * kTP;
+    if (t < nx) {   // unused columns: zeros
+        float *x1 = S.X1 + t * kTP;
         for (int col = ncols; col < 12; col++) { x1[col] = 0.f; x1[12 + col] = 0.f; }
     }
     cbar();
@@ -1190,6 +1230,24 @@ __device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderS
     L.st = st; L.ph = ph; L.vs = vs; L.vph = vph;
     cyc_go += clock64() - cg_;
     (void)cyc_empty; (void)cyc_vec; (void)cyc_go;
+}
+
+// One thread, at the start of the sweeps: HBM is idle until the next phase S (the sweeps' operands are L2 / shared-memory
+// resident), so the matrices this CTA streams right after its kept ones are pulled into L2 now (cp.async.bulk.prefetch.L2,
+// SASS UBLKPF.L2): the next phase S finds them there.  Whole nodes [n0, n1) of each of the n_mats arrays, as 16-byte windows.
+__device__ __noinline__ void l2_prefetch_next(const PArgs &P, const Slice &R) {
+    const int n_units = R.u_end - R.u_begin;
+    if (P.l2_pref <= 0.f || n_units <= 0) return;
+    const int u0 = R.u_begin + (P.l2_keep > 0.f ? (int)(P.l2_keep * (float)n_units) : 0);
+    const int u1 = min(R.u_end, u0 + (int)(P.l2_pref * (float)n_units));
+    const int n0 = (u0 + P.n_mats - 1) / P.n_mats, n1 = u1 / P.n_mats;
+    if (n1 <= n0) return;
+    for (int m = 0; m < P.n_mats; m++) {
+        const size_t sz = (size_t)P.nv * ((m & 1) == 0 ? 2 * P.nx : P.nu) * sizeof(float);
+        const uintptr_t a0 = (reinterpret_cast<uintptr_t>(P.mat[m]) + (size_t)n0 * sz) & ~uintptr_t(15);
+        const uintptr_t a1 = (reinterpret_cast<uintptr_t>(P.mat[m]) + (size_t)n1 * sz + 15) & ~uintptr_t(15);
+        for (uintptr_t a = a0; a < a1; a += 65536) bulk_prefetch_l2(reinterpret_cast<const void *>(a), (uint32_t)min((uintptr_t)65536, a1 - a));
+    }
 }
 
 // ---- GEMV warps: part[m][node] = (factor matrix m of the node) x (w segment).  A warp owns a contiguous block of the
@@ -1728,6 +1786,7 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
     // ---- phase B: backward sweep of the chains (operand blocks by bulk TMA, one chain ahead)
     dstamp(P, 2);
     if (threadIdx.x == 0 && j0 < nK) issue_chain_backward_loads(P, j0);
+    if (threadIdx.x == 32 && !P.sh_mode && it + 1 < P.iters) l2_prefetch_next(P, K.R);
 #pragma unroll 1
     for (int j = j0; j < nK; j += grid) chain_backward(P, j, j + grid < nK ? j + grid : -1, mpar, K.SP);
     dstamp(P, 10);
@@ -1739,8 +1798,15 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
         // rest of the chains' backward sweep
         const CrownTiles C = crown_tiles(P);
         const int n_crown = P.n_crown;
+        // near-root contributions: the S rows of the bottom-crown nodes whose chains live on this rank, dealt from the last
+        // CTA down like the crown tiles
+#pragma unroll 1
+        for (int pb = grid - 1 - j0; pb < P.n_bottom; pb += grid) {
+            const int p = P.bottom0 + pb;
+            if (__ldg(P.child_count + p) > 0) parent_sum(P, p, it);
+        }
         if (P.n_ranks > 1) grid_sync_cross(P, bar_count(P, it, 1), P.epoch0 + 2u * (unsigned)it + 1u, -1);
-        unsigned int wait_heads = P.n_ranks > 1 ? 0u : (unsigned)nK * (unsigned)(it + 1);   // counter value once every head is in
+        unsigned int wait_heads = P.n_ranks > 1 ? 0u : (unsigned)P.n_owned * (unsigned)(it + 1);   // counter value once every S row is in
         dstamp(P, 20);
 #pragma unroll 1
         for (int tl = grid - 1 - j0; tl < C.n_tiles; tl += grid) {
@@ -2005,17 +2071,61 @@ __global__ void k_to_chain_major(int nodes, int dim, int dimp, const int *__rest
 }
 
 // Exchange buffer of this rank (one cudaMalloc, so that one CUDA IPC handle maps it into the peer processes):
-//   qh table [K_glob*nx] | rh table [K_glob*nv] | distance slots [kMaxRanks][2][2] doubles | flags [kMaxRanks] | release | err
-struct XchgLayout { size_t qh, rh, dslot, flags, release, err, bytes; };
+//   S_q table [n_crown*nxp] | S_r table [n_crown*nvp] (rows padded to 16 bytes) | beta rows of the crown [n_crown*nv] | distance slots [kMaxRanks][2][2] doubles | flags [kMaxRanks] | err
+struct XchgLayout { size_t sq, sr, beta, dslot, flags, err, bytes; };
 static XchgLayout xchg_layout(const Handle *h) {
     XchgLayout X{};
-    const size_t Kg = (size_t)(h->dist_world > 1 ? h->dist_K_glob : h->d.K);
+    const size_t nc = (size_t)std::max(h->h_cum[h->chain_stage], 1);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~size_t(255); return at; };
-    X.qh = take(Kg * h->d.nx * 4); X.rh = take(Kg * h->d.nv * 4); X.dslot = take(kMaxRanks * 4 * 8);
-    X.flags = take(kMaxRanks * 4); X.release = take(4); X.err = take(4); X.bytes = o;
+    X.sq = take(nc * pad4(h->d.nx) * 4 + 64); X.sr = take(nc * pad4(h->d.nv) * 4 + 64); X.beta = take(nc * h->d.nv * 4); X.dslot = take(kMaxRanks * 4 * 8);
+    X.flags = take(kMaxRanks * 4); X.err = take(4); X.bytes = o;
     return X;
 }
+size_t xchg_err_offset(const Handle *h) { return xchg_layout(h).err; }
+// The one per-SOLVE quantity that couples the ranks: zeta (hence beta) of a bottom-crown node sums over its children
+// (calculateZeta, Utilities.cu:100-131), and those live on one rank only -- the partition is aligned to these nodes.  The
+// owner's beta row is exact; it is pushed into every rank's staging table (push), and after a barrier across the ranks every
+// rank copies the rows it does not own into its beta (pull).
+__global__ void k_push_beta(int bottom0, int n_bottom, int nv, int n_ranks, const int *__restrict__ child_count,
+                            const float *__restrict__ beta, float *s0, float *s1, float *s2, float *s3, float *s4, float *s5,
+                            float *s6, float *s7) {
+    const int p = bottom0 + blockIdx.x;
+    if ((int)blockIdx.x >= n_bottom || child_count[p] == 0) return;
+    float *dst[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
+    for (int t = threadIdx.x; t < nv; t += blockDim.x) {
+        const float v = beta[(size_t)p * nv + t];
+        for (int r = 0; r < n_ranks; r++) dst[r][(size_t)p * nv + t] = v;
+    }
+}
+__global__ void k_pull_beta(int bottom0, int n_bottom, int nv, const int *__restrict__ child_count, const float *__restrict__ stage,
+                            float *__restrict__ beta) {
+    const int p = bottom0 + blockIdx.x;
+    if ((int)blockIdx.x >= n_bottom || child_count[p] != 0) return;
+    for (int t = threadIdx.x; t < nv; t += blockDim.x) beta[(size_t)p * nv + t] = stage[(size_t)p * nv + t];
+}
+rn_status dist_crown_beta(Handle *h, int pull) {
+    const int cs = h->chain_stage;
+    if (h->dist_world <= 1 || cs <= 0) return RN_OK;
+    const XchgLayout X = xchg_layout(h);
+    const int bottom0 = h->h_cum[cs - 1], n_bottom = h->h_cum[cs] - bottom0;
+    if (pull) {
+        k_pull_beta<<<n_bottom, 128, 0, h->stream>>>(bottom0, n_bottom, h->d.nv, h->t.child_count,
+                                                     reinterpret_cast<const float *>(static_cast<char *>(h->xchg) + X.beta), h->beta);
+    } else {
+        float *dst[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        for (int r = 0; r < h->dist_world; r++) {
+            if (!h->xchg_peer[r]) return fail(h, RN_ERR_STATE, "rank %d's exchange buffer is not connected (rn_dist_connect)", r);
+            dst[r] = reinterpret_cast<float *>(static_cast<char *>(h->xchg_peer[r]) + X.beta);
+        }
+        k_push_beta<<<n_bottom, 128, 0, h->stream>>>(bottom0, n_bottom, h->d.nv, h->dist_world, h->t.child_count, h->beta, dst[0], dst[1],
+                                                     dst[2], dst[3], dst[4], dst[5], dst[6], dst[7]);
+    }
+    h->launches += 1;
+    RN_CUDA(h, cudaGetLastError());
+    return RN_OK;
+}
+
 rn_status ensure_xchg(Handle *h) {
     if (h->xchg) return RN_OK;
     const XchgLayout X = xchg_layout(h);
@@ -2025,6 +2135,21 @@ rn_status ensure_xchg(Handle *h) {
     RN_CUDA(h, cudaMemset(h->xchg, 0, X.bytes));
     for (int r = 0; r < kMaxRanks; r++) h->xchg_peer[r] = nullptr;
     h->xchg_peer[h->dist_rank] = h->xchg;
+    return RN_OK;
+}
+
+// The shared matrices of the sweeps are outputs of the factor step (G = Bbar', OmegaBar, L and L' change with the
+// null-space basis, rn_set_null_space): the pack is re-copied on `st` whenever a factor step has run since the last launch.
+static rn_status refresh_pack(Handle *h, cudaStream_t st) {
+    const rn_dims &d = h->d;
+    const SweepLayout Y = sweep_layout(h);
+    const size_t f = sizeof(float);
+    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pG, h->G, (size_t)d.nv * d.nx * f, cudaMemcpyDeviceToDevice, st));
+    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pOm, h->OmegaBar, (size_t)d.nv * d.nv * f, cudaMemcpyDeviceToDevice, st));
+    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pL, h->L, (size_t)d.nu * d.nv * f, cudaMemcpyDeviceToDevice, st));
+    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pB, h->B, (size_t)d.nx * d.nu * f, cudaMemcpyDeviceToDevice, st));
+    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pLt, h->Lt, (size_t)d.nv * d.nu * f, cudaMemcpyDeviceToDevice, st));
+    h->pack_dirty = false;
     return RN_OK;
 }
 
@@ -2038,17 +2163,14 @@ rn_status persistent_prepare(Handle *h) {
     RN_CHECK(dev_alloc(h, &h->cm_c, n * Y.nxp)); RN_CHECK(dev_alloc(h, &h->cm_lv, n * Y.nup));
     RN_CHECK(dev_alloc(h, &h->cm_beta, n * Y.nvp)); RN_CHECK(dev_alloc(h, &h->cm_uhat, n * Y.nup)); RN_CHECK(dev_alloc(h, &h->cm_e, n * Y.nxp));
     RN_CHECK(ensure_xchg(h));
-    RN_CHECK(dev_alloc(h, &h->grid_bar, 64));   // [0] grid barrier, [32] heads counter (its own 128-byte line)
+    // [0] grid barrier, [32] published-S counter (its own 128-byte line), [64 ...] per bottom-crown node: heads in
+    RN_CHECK(dev_alloc(h, &h->grid_bar, 64 + (size_t)std::max(n_crown, 1)));
+    RN_CHECK(dev_alloc(h, &h->head_q, (size_t)d.K * d.nx)); RN_CHECK(dev_alloc(h, &h->head_r, (size_t)d.K * d.nv));
     RN_CHECK(dev_alloc(h, &h->phase_ns, 32));
     RN_CHECK(dev_alloc(h, &h->cta_ns, 2 * 1024));
     // G | OmegaBar | L | B | L', each padded to 16 bytes: the bulk copies of the sweeps (and of phase S in shared-factor mode)
     RN_CHECK(dev_alloc(h, &h->sweep_pack, (size_t)Y.pack_floats));
-    const size_t f = sizeof(float);
-    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pG, h->G, (size_t)d.nv * d.nx * f, cudaMemcpyDeviceToDevice, h->stream));
-    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pOm, h->OmegaBar, (size_t)d.nv * d.nv * f, cudaMemcpyDeviceToDevice, h->stream));
-    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pL, h->L, (size_t)d.nu * d.nv * f, cudaMemcpyDeviceToDevice, h->stream));
-    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pB, h->B, (size_t)d.nx * d.nu * f, cudaMemcpyDeviceToDevice, h->stream));
-    RN_CUDA(h, cudaMemcpyAsync(h->sweep_pack + Y.pLt, h->Lt, (size_t)d.nv * d.nu * f, cudaMemcpyDeviceToDevice, h->stream));
+    h->pack_dirty = true;   // filled by refresh_pack at the next launch (and again after every factor step)
     // chain-major row of every node: crown nodes keep their id, chain j / stage cs+s sits at n_crown + j T + s
     std::vector<int> pos(n);
     for (int i = 0; i < d.nodes; i++) {
@@ -2065,12 +2187,9 @@ rn_status persistent_prepare(Handle *h) {
         for (int s = h->h_stages[i] + 1; s <= cs; s++) {
             const int nlo = h->h_child_first[lo], nhi = h->h_child_first[hi - 1] + h->h_child_count[hi - 1];
             lo = nlo; hi = nhi;
-            int a = lo, b = hi;
-            if (s == cs) {
-                if (h->dist_world > 1) { a = h->dist_head_lo[i]; b = h->dist_head_hi[i]; }
-                else { a = lo - h->h_cum[cs]; b = hi - h->h_cum[cs]; }
-            }
-            rng[((size_t)i * (kMaxCs + 1) + s) * 2] = a; rng[((size_t)i * (kMaxCs + 1) + s) * 2 + 1] = b;
+            // (stage cs is not tabulated: the heads enter through the S rows of the bottom-crown nodes, parent_sum)
+            if (s == cs) break;
+            rng[((size_t)i * (kMaxCs + 1) + s) * 2] = lo; rng[((size_t)i * (kMaxCs + 1) + s) * 2 + 1] = hi;
         }
     }
     // path root -> node of every crown node
@@ -2084,10 +2203,9 @@ rn_status persistent_prepare(Handle *h) {
     RN_CHECK(dev_alloc(h, &h->crown_rng, rng.size()));
     RN_CUDA(h, cudaMemcpyAsync(h->crown_rng, rng.data(), rng.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     RN_CUDA(h, cudaStreamSynchronize(h->stream));
-    // the attribute is set once: cover the shared-factor layout too when it fits (rn_set_modes may switch later)
     size_t smem = persist_smem_bytes(h);
     if ((size_t)shared_layout(h).end * 4 + 128 <= 227 * 1024) smem = std::max(smem, (size_t)shared_layout(h).end * 4 + 128);
-    RN_CUDA(h, cudaFuncSetAttribute(k_apg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RN_CUDA(h, cudaFuncSetAttribute(k_apg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // for the occupancy query; set again at every launch
     int per_sm = 0;
     RN_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_apg_persistent, kPT, smem));
     if (per_sm < 1) return fail(h, RN_ERR_INVALID, "persistent kernel does not fit on an SM (%zu B shared memory)", smem);
@@ -2122,6 +2240,11 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
         P.l2_keep = 0.f;
         if (keep_l2 > 0 && !P.sh_mode && bytes > 0)
             P.l2_keep = (float)std::min(1.0, keep_l2 * (double)h->l2_bytes * h->persist_grid / h->sm_count / bytes);
+        static const char *penv = getenv("RN_L2_PREFETCH");
+        static const double pref_l2 = penv ? atof(penv) : kL2PrefDefault;
+        P.l2_pref = 0.f;
+        if (pref_l2 > 0 && !P.sh_mode && bytes > 0)
+            P.l2_pref = (float)std::min(1.0 - P.l2_keep, pref_l2 * (double)h->l2_bytes * h->persist_grid / h->sm_count / bytes);
     }
     {
         const SharedLayout SL = shared_layout(h);
@@ -2148,13 +2271,18 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
         for (int r = 0; r < P.n_ranks; r++) {
             char *base = static_cast<char *>(h->xchg_peer[r]);
             if (!base) return fail(h, RN_ERR_STATE, "rank %d's exchange buffer is not connected (rn_dist_connect)", r);
-            P.qh_peer[r] = reinterpret_cast<float *>(base + X.qh); P.rh_peer[r] = reinterpret_cast<float *>(base + X.rh);
+            P.Sq_peer[r] = reinterpret_cast<float *>(base + X.sq); P.Sr_peer[r] = reinterpret_cast<float *>(base + X.sr);
             P.dslot_peer[r] = reinterpret_cast<double *>(base + X.dslot);
             P.xflag_peer[r] = reinterpret_cast<unsigned int *>(base + X.flags);
         }
         char *own = static_cast<char *>(h->xchg);
-        P.release = reinterpret_cast<unsigned int *>(own + X.release);
         P.xerr = reinterpret_cast<int *>(own + X.err);
+        P.hq = h->head_q; P.hr = h->head_r;
+        const int cs_ = h->chain_stage;
+        P.bottom0 = cs_ > 0 ? h->h_cum[cs_ - 1] : 0; P.n_bottom = cs_ > 0 ? h->h_cum[cs_] - h->h_cum[cs_ - 1] : 0;
+        P.n_owned = 0;
+        for (int b = 0; b < P.n_bottom; b++) P.n_owned += h->h_child_count[P.bottom0 + b] > 0 ? 1 : 0;
+        RN_CUDA(h, cudaMemsetAsync(own + X.err, 0, sizeof(int), st));   // a timed-out wait of an earlier launch does not poison this one
         P.epoch0 = h->xepoch;
         h->xepoch += 2u * (unsigned)iters + 2u;   // every rank runs the same launches: the epochs stay aligned
     }
@@ -2165,7 +2293,7 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     P.pinf4 = h->pinf4;
     P.cm_c = h->cm_c; P.cm_lv = h->cm_lv; P.cm_beta = h->cm_beta; P.cm_uhat = h->cm_uhat; P.cm_e = h->cm_e;
     P.dist_part = h->dist_part; P.pinf = h->pinf; P.pinf_part = h->pinf_part;
-    P.lambda_tab = h->lambda_tab; P.bar = h->grid_bar; P.heads_ctr = h->grid_bar + 32; P.iter_dev = h->iter_dev; P.phase_ns = h->phase_ns; P.cta_ns = h->cta_ns;
+    P.lambda_tab = h->lambda_tab; P.bar = h->grid_bar; P.s_ctr = h->grid_bar + 32; P.par_ctr = h->grid_bar + 64; P.iter_dev = h->iter_dev; P.phase_ns = h->phase_ns; P.cta_ns = h->cta_ns;
     P.step = h->step; P.inv_step = 1 / h->step; P.pen_x = h->pen_x; P.pen_xs = h->pen_xs;
     const SweepLayout Y = sweep_layout(h);
     P.oG = Y.oG; P.oOm = Y.oOm; P.oL = Y.oL; P.oX1 = Y.oX1; P.oY = Y.oY; P.oV = Y.oV; P.oScr2 = Y.oScr2; P.oStg = Y.oStg; P.oXb = Y.oXb;
@@ -2178,8 +2306,12 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     k_to_chain_major<<<d.nodes, 128, 0, st>>>(d.nodes, d.nu, Y.nup, h->pos_dev, h->uhat, h->cm_uhat);
     k_to_chain_major<<<d.nodes, 128, 0, st>>>(d.nodes, d.nx, Y.nxp, h->pos_dev, h->e, h->cm_e);
     h->launches += 3;
-    RN_CUDA(h, cudaMemsetAsync(h->grid_bar, 0, 64 * sizeof(unsigned int), st));
+    RN_CUDA(h, cudaMemsetAsync(h->grid_bar, 0, (64 + (size_t)std::max(P.n_crown, 1)) * sizeof(unsigned int), st));
     RN_CUDA(h, cudaMemsetAsync(h->dist_part, 0, 2 * sizeof(double) * h->persist_grid, st));
+    if (h->pack_dirty) RN_CHECK(refresh_pack(h, st));
+    // the attribute belongs to the function and the device, not to the handle: a handle of a smaller problem prepared later
+    // would otherwise lower the limit under this one (launch_stream / launch_sweeps do the same for their kernels)
+    RN_CUDA(h, cudaFuncSetAttribute(k_apg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem_bytes(h)));
     void *args[] = {&P};
     RN_CUDA(h, cudaLaunchCooperativeKernel((const void *)k_apg_persistent, dim3(h->persist_grid), dim3(kPT), args,
                                            persist_smem_bytes(h), st));

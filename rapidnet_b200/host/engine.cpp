@@ -285,12 +285,19 @@ void SmpcController::step(rn_step_kind kind, real_t lambda, const char *what) {
     check(rn_sync(ptrMyEngine->handle()), "rn_sync");
 }
 void SmpcController::dualExtrapolationStep(real_t lambda) { step(RN_STEP_EXTRAPOLATE, lambda, "SmpcController::dualExtrapolationStep"); }
-void SmpcController::solveStep() { step(RN_STEP_SOLVE, 0.f, "SmpcController::solveStep"); }
+// The reference factors lazily: solveStep() runs initialiseSmpcController() when no factor step has happened yet
+// (SmpcController.cu:579-582), so a fresh controller may go straight to controlAction / algorithmApg.  Every entry that
+// reaches solveStep in the reference does the same here, before the C ABI (which insists on the order) is called.
+void SmpcController::ensureFactored() {
+    if (!factorStepFlag) initialiseSmpcController();
+}
+void SmpcController::solveStep() { ensureFactored(); step(RN_STEP_SOLVE, 0.f, "SmpcController::solveStep"); }
 void SmpcController::proximalFunG() { step(RN_STEP_PROX, 0.f, "SmpcController::proximalFunG"); }
 void SmpcController::computeFixedPointResidual() { step(RN_STEP_RESIDUAL, 0.f, "SmpcController::computeFixedPointResidual"); }
 void SmpcController::dualUpdate() { step(RN_STEP_DUAL_UPDATE, 0.f, "SmpcController::dualUpdate"); }
 
 uint_t SmpcController::algorithmApg() {
+    ensureFactored();
     const uint_t iters = ptrMySmpcConfig->getMaxIterations();
     check(rn_apg_solve(ptrMyEngine->handle(), iters, nullptr, vecPrimalInfs.data()), "SmpcController::algorithmApg");
     refreshDevicePointers();
@@ -298,12 +305,14 @@ uint_t SmpcController::algorithmApg() {
 }
 
 void SmpcController::controllerSmpc() {
+    ensureFactored();
     ptrMyEngine->updateStateControl(ptrMySmpcConfig->getCurrentX(), ptrMySmpcConfig->getPrevU(), ptrMySmpcConfig->getPrevDemand());
     ptrMyEngine->eliminateInputDistubanceCoupling(ptrMyForecaster->getNominalDemand(), ptrMyForecaster->getNominalPrices());
     algorithmApg();
 }
 
 uint_t SmpcController::controlAction(real_t *u) {
+    ensureFactored();
     check(rn_control_action(ptrMyEngine->handle(), ptrMySmpcConfig->getCurrentX(), ptrMySmpcConfig->getPrevU(),
                             ptrMySmpcConfig->getPrevDemand(), ptrMyForecaster->getNominalDemand(),
                             ptrMyForecaster->getNominalPrices(), ptrMySmpcConfig->getMaxIterations(), /*clamp=*/0, u),
@@ -314,6 +323,7 @@ uint_t SmpcController::controlAction(real_t *u) {
 
 uint_t SmpcController::controlAction(std::fstream &controlOutputJson) {
     if (!controlOutputJson.is_open()) return 0;
+    ensureFactored();
     const uint_t nu = ptrMySmpcConfig->getNU();
     std::vector<real_t> currentControl(nu);
     check(rn_control_action(ptrMyEngine->handle(), ptrMySmpcConfig->getCurrentX(), ptrMySmpcConfig->getPrevU(),

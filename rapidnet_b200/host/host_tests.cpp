@@ -405,10 +405,24 @@ static int closed_loop_lanes(const std::string &cfgPath, int steps, int lanes, c
     return 0;
 }
 
+// ---- lazy factor step (SmpcController.cu:579-582): controlAction on a controller that was never initialised -----------------
+static int fresh_controller(const std::string &cfgPath) {
+    SmpcController lazy(cfgPath), eager(cfgPath);
+    const uint_t nu = lazy.getSmpcConfiguration()->getNU();
+    std::vector<real_t> a(nu, 0.f), b(nu, 1.f);
+    T_ASSERT(lazy.controlAction(a.data()) == 1);            // the reference factors inside solveStep on first use
+    eager.initialiseSmpcController();
+    T_ASSERT(eager.controlAction(b.data()) == 1);
+    T_ASSERT(std::memcmp(a.data(), b.data(), nu * sizeof(real_t)) == 0);
+    std::cout << "host_tests fresh: ok" << std::endl;
+    return 0;
+}
+
 int main(int argc, char **argv) {
-    if (argc < 3) { std::cerr << "usage: host_tests loaders|engine|smpc|surface|closedloop|lanes <controllerConfig.json> ..." << std::endl; return 2; }
+    if (argc < 3) { std::cerr << "usage: host_tests loaders|engine|smpc|surface|closedloop|lanes|fresh <controllerConfig.json> ..." << std::endl; return 2; }
     const std::string mode = argv[1], cfg = argv[2];
     if (mode == "loaders") return test_loaders(cfg);
+    if (mode == "fresh") return fresh_controller(cfg);
     if (mode == "closedloop") { T_ASSERT(argc >= 5); return closed_loop(cfg, std::atoi(argv[3]), argv[4]); }
     if (mode == "lanes") { T_ASSERT(argc >= 6); return closed_loop_lanes(cfg, std::atoi(argv[3]), std::atoi(argv[4]), argv[5]); }
     T_ASSERT(argc >= 4);

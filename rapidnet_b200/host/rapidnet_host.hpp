@@ -277,6 +277,7 @@ protected:
     uint_t algorithmApg();                                 // :1500-1525
     real_t updatePrimalInfeasibity();                      // :1480-1496 (stand-alone; inside the APG loop the kernel logs it)
     void initialiseAlgorithm();                            // :420-450
+    void ensureFactored();                                 // the lazy factor step of solveStep (:579-582)
     // the library's device buffers under the reference's member names; xi / psi / update roles swap physical
     // buffers with the iteration parity, so the pointers are refreshed after every call that runs iterations
     void refreshDevicePointers();

@@ -7,10 +7,13 @@ first stage of its non-branching tail ("chain stage" cs: below it every scenario
   * rank r owns a contiguous range of the K scenario chains (stages cs .. N-1), i.e. ~1/G of the nodes, of the Engine
     factor matrices and of the duals.
 
-Each rank builds an ordinary, smaller problem (crown + its chains, nodes renumbered breadth-first) and creates its
-handle on it; per APG iteration the ranks exchange -- inside the persistent kernel, over NVLink peer memory mapped with
-CUDA IPC -- the q and r of their chain heads (so that every rank can finish the crown) and the two squared prox
-distances.  Nothing else crosses GPUs.  torch.distributed is used only to hand the 64-byte IPC handles around.
+The cut is aligned to the nodes of the last crown stage (stage cs-1, the "bottom-crown" nodes): all chains below one of
+them go to the same rank.  Each rank builds an ordinary, smaller problem (crown + its chains, nodes renumbered
+breadth-first) and creates its handle on it; per APG iteration the ranks exchange -- inside the persistent kernel, over
+NVLink peer memory mapped with CUDA IPC -- for every bottom-crown node they own the sum of q and of r over its chain
+heads (nx + nv floats: what the reference's solveSumChildren leaves in the parent's slot, so that every rank can finish
+the crown) and the two squared prox distances.  Per solve, the beta rows of the bottom-crown nodes travel the same way.
+Nothing else crosses GPUs.  torch.distributed hands the 64-byte IPC handles around and provides the host barrier.
 """
 from __future__ import annotations
 
@@ -39,11 +42,28 @@ def chain_stage(tree: Tree) -> int:
     return int(cs)
 
 
-def split_chains(K: int, world: int) -> List[Tuple[int, int]]:
-    """Contiguous, balanced chain ranges [lo, hi) per rank."""
-    if world < 1 or K < world:
-        raise ValueError(f"cannot split {K} scenario chains over {world} ranks")
-    edges = [(K * r) // world for r in range(world + 1)]
+def split_chains(tree: Tree, cs: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous chain ranges [lo, hi) per rank, cut only BETWEEN the bottom-crown nodes (stage cs-1) and balanced by the
+    number of chains: the edge of rank r is the parent boundary closest to K r / world."""
+    K = int(tree.nodes_per_stage[cs])
+    if cs <= 0:
+        raise ValueError("the tree has no crown stage to cut below")
+    cum = tree.nodes_per_stage_cumul
+    par = tree.ancestor.astype(np.int64) - 1
+    heads_parent = par[cum[cs]: cum[cs] + K]
+    # chain index where each bottom-crown node's heads start (children are contiguous per parent), plus the end
+    bounds = np.concatenate([np.flatnonzero(np.diff(heads_parent, prepend=heads_parent[0] - 1)), [K]])
+    if world < 1 or bounds.size - 1 < world:
+        raise ValueError(f"cannot split {bounds.size - 1} bottom-crown subtrees over {world} ranks")
+    edges = [0]
+    for r in range(1, world):
+        target = K * r / world
+        cand = bounds[(bounds > edges[-1])]
+        cand = cand[cand <= K - (world - r)] if cand.size else cand
+        edges.append(int(cand[np.argmin(np.abs(cand - target))]))
+    edges.append(K)
+    if any(edges[r + 1] <= edges[r] for r in range(world)):
+        raise ValueError(f"cannot split the chains over {world} ranks along the bottom-crown nodes")
     return [(edges[r], edges[r + 1]) for r in range(world)]
 
 
@@ -89,7 +109,7 @@ def local_problem(problem: Problem, rank: int, world: int) -> Tuple[Problem, Par
     K = int(nps[cs])
     if K != t.K:
         raise ValueError("the chains of the tail are not the scenarios of the tree")
-    lo, hi = split_chains(K, world)[rank]
+    lo, hi = split_chains(t, cs, world)[rank]
     kl = hi - lo
     n_crown = int(cum[cs])
     # global ids of the local nodes, in local (breadth-first) order
@@ -158,44 +178,54 @@ class DistributedSolver:
         dist.barrier(group=group)
 
     def setup(self, slot: int = 0):
+        import torch.distributed as dist
         c, fc = self.global_problem.config, self.global_problem.forecast
         s = self.solver
         s.factor_step()
         s.update_state(c.current_x, c.prev_u, c.prev_demand)
         self.eliminate_coupling(fc.demand[slot], fc.prices[slot])
+        # the first solve also allocates the persistent kernel's buffers: do it once here, then line the ranks up, so that
+        # no later launch is skewed by more than the in-kernel wait budget
+        s.prepare_persistent()
+        s.sync()
+        dist.barrier(group=self.group)
 
     def eliminate_coupling(self, d_hat, alpha_hat):
         """Engine::eliminateInputDistubanceCoupling on the partition.  zeta_i = p_i dU_i - sum_children p_c dU_c
-        (calculateZeta, /root/reference/src/Utilities.cu:100-131) of a node just above the chain heads sums over children
-        on every rank: each rank's local value holds p_i dU_i minus its own children, so
-        zeta_i = sum_ranks zeta_i^r - (G - 1) p_i dU_i, summed in rank order on every rank; beta follows on the device."""
+        (calculateZeta, /root/reference/src/Utilities.cu:100-131) of a bottom-crown node sums over its children, which all
+        live on one rank (the cut is aligned to these nodes): that rank's beta row is exact and is pushed into every rank's
+        staging table over NVLink; after the barrier every rank pulls the rows it does not own.  No host copy of data."""
         import torch.distributed as dist
-        s, m, t = self.solver, self.meta, self.local.tree
+        s, m = self.solver, self.meta
         s.eliminate_coupling(d_hat, alpha_hat)
         if self.world == 1 or m.cs == 0:
-            s.sync()
             return
-        nu = self.local.network.nu
-        cum = t.nodes_per_stage_cumul
-        n0, n1 = int(cum[m.cs - 1]), int(cum[m.cs])
-        zeta = s.read("VEC_ZETA", count=n1 * nu).reshape(n1, nu)[n0:n1]
-        uhat = s.read("VEC_UHAT", count=n1 * nu).reshape(n1, nu)
-        par = t.ancestor[n0:n1].astype(np.int64) - 1
-        up = np.where(par[:, None] >= 0, uhat[np.maximum(par, 0)], s.read("VEC_PREV_UHAT")[None, :])
-        pdu = (t.prob[n0:n1, None].astype(np.float32) * (uhat[n0:n1] - up)).astype(np.float32)
-        parts = [None] * self.world
-        dist.all_gather_object(parts, zeta, group=self.group)
-        total = parts[0].astype(np.float32).copy()
-        for z in parts[1:]:
-            total += z
-        s.dist_fix_crown_beta(n0, total - np.float32(self.world - 1) * pdu)
+        s.dist_sync_crown_beta(pull=False)
+        s.sync()
+        dist.barrier(group=self.group)
+        s.dist_sync_crown_beta(pull=True)
 
-    def apg_solve(self, iterations: int, want_u0=True):
-        """Every rank must call this with the same iteration count (the in-kernel barriers span the GPUs)."""
+    def apg_solve(self, iterations: int, want_u0=True, check=True):
+        """Every rank must call this with the same iteration count (the in-kernel barriers span the GPUs).  `check`: read
+        the timeout flag of the cross-GPU waits back (a device synchronisation)."""
         u0, _ = self.solver.apg_solve(iterations, want_u0=want_u0)
-        if self.solver.dist_error():
+        if check and self.solver.dist_error():
             raise RuntimeError("a cross-GPU wait timed out: a peer rank did not reach the exchange")
         return u0
+
+    def control_action(self, x, u_prev, d_prev, d_hat, alpha_hat, iterations: int):
+        """SmpcController::controlAction(real_t*) on the partition: host buffers in on every rank, u0 (of the replicated
+        root) out on every rank."""
+        self.solver.update_state(x, u_prev, d_prev)
+        self.eliminate_coupling(d_hat, alpha_hat)
+        return self.apg_solve(iterations, want_u0=True, check=True)
+
+    def exchange_bytes_per_iteration(self) -> int:
+        """bytes this rank stores into its peers per APG iteration: S rows of its bottom-crown nodes + the prox distances"""
+        t, m, n = self.local.tree, self.meta, self.local.network
+        cum = t.nodes_per_stage_cumul
+        owned = int(np.count_nonzero(t.n_children[int(cum[m.cs - 1]): int(cum[m.cs])])) if m.cs > 0 else 0
+        return (owned * (n.nx + self.local.config.nv) * 4 + 2 * 16 + 2 * 4) * (self.world - 1)
 
     def gather(self, name: str, dim: int) -> np.ndarray:
         """A per-node buffer ([nodes][dim]) assembled in GLOBAL node order on every rank."""

@@ -4,19 +4,26 @@
 * smpc_close   : abs 0.1, or 0.1 % relative when |value| > 100
                  (/root/reference/src/test/TestSmpcController.cu:28-47)
 
-fp32 noise floor (DESIGN.md "tolerances"): the APG iteration amplifies rounding differences -- after 500 iterations
-two correct fp32 implementations that merely sum in a different order (cuBLAS vs plain loops) differ by a few 1e-4,
-and each is ~1e-4 away from the same code run in double.  So the parity bar is
-    err(ours, ref)  <  max(RTOL, KAPPA * err(ref, f64 trajectory))
-i.e. 1e-4, or -- where the reference's own rounding uncertainty is larger than that -- as close to the reference as
-the reference is to exact arithmetic (times KAPPA).  `floor_tol` computes it.  KAPPA = 8: the floor is ONE sample of a
-random quantity (two independent fp32 runs differ by sqrt(2) x that on average, with a wide spread on short vectors such
-as u0: measured on B200, C1r6 at 500 iterations: u0 error 1.7e-4 against a sampled floor of 3.6e-5).
+Parity gates for whole solves.  The APG iteration amplifies rounding differences: after 500
+iterations two correct fp32 implementations that merely sum in a different order (cuBLAS vs plain loops) differ by a
+few 1e-4, and each is about that far from the same algorithm run in double.  Agreement with the reference build is
+therefore bounded by the reference's OWN rounding uncertainty, and the gates are stated on accuracy:
+
+  accuracy_gate : err(ours, f64) <= ACC_FACTOR * err(reference, f64) + ACC_ABS          per variable
+                  (ours is at most twice as far from the double-precision trajectory as the reference itself is;
+                  ACC_ABS = 2e-6 keeps single-rounding differences at iteration 1 from being ranked)
+  u0 / iterates : err(ours, reference) <= RTOL = 1e-4 (the north-star figure) wherever the reference's floor
+                  err(reference, f64) allows it (<= RTOL / 3); otherwise the bound that follows from the accuracy gate by
+                  the triangle inequality, (1 + ACC_FACTOR) * err(reference, f64), and the case is reported as
+                  floor-limited.  `floor_tol` computes it.
+tools/parity_table.py prints all three errors per config x iteration count x variable (profiles/r02_parity_table.md).
 """
 import numpy as np
 
 RTOL = 1e-4
-KAPPA = 8.0
+ACC_FACTOR = 2.0
+ACC_ABS = 2e-6
+KAPPA = 1.0 + ACC_FACTOR
 
 
 def floor_tol(ref32, ref64, den=None, rtol=RTOL, kappa=KAPPA):
@@ -26,6 +33,17 @@ def floor_tol(ref32, ref64, den=None, rtol=RTOL, kappa=KAPPA):
     d = float(np.linalg.norm(b)) if den is None else float(den)
     floor = float(np.linalg.norm(a - b) / max(d, 1e-30))
     return max(rtol, kappa * floor), floor
+
+
+def accuracy_gate(ours, ref32, ref64, den=None, factor=ACC_FACTOR, slack=ACC_ABS):
+    """(ok, err(ours, f64), err(ref, f64)): ours is at most `factor` times as far from the double-precision trajectory as
+    the reference is (norm-wise relative; `den` overrides the denominator for differences of nearly equal iterates)"""
+    o = np.asarray(ours, dtype=np.float64).reshape(-1)
+    a = np.asarray(ref32, dtype=np.float64).reshape(-1)
+    b = np.asarray(ref64, dtype=np.float64).reshape(-1)
+    d = max(float(np.linalg.norm(b)) if den is None else float(den), 1e-30)
+    e_ours, e_ref = float(np.linalg.norm(o - b) / d), float(np.linalg.norm(a - b) / d)
+    return e_ours <= factor * e_ref + slack, e_ours, e_ref
 
 
 def engine_close(got, want, tol=1e-2):

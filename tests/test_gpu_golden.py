@@ -90,6 +90,63 @@ def test_apg_steps_golden(solver, toy):
     smpc_close(s.read("VEC_UPDATE_XI"), g["finalUpdateXi"]); smpc_close(s.read("VEC_UPDATE_PSI"), g["finalUpdatePsi"])
 
 
+def test_persistent_kernel_golden_iteration(toy):
+    """The golden step vectors through k_apg_persistent itself (rn_step dispatches to the stand-alone kernels): ONE fused
+    iteration continued from the golden y_k / y_{k-1} with the golden lambda must reproduce the extrapolation, the solve
+    step, the prox, the residual and the dual update of TestSmpcController.cu:134-398 at the reference's tolerances."""
+    prob, engine, g = toy
+    s = cabi.Solver(prob)
+    s.set_modes(cabi.SWEEP_PERSISTENT, cabi.FACTORS_FULL)
+    s.set_null_space(engine["matL"], prob.config.Lhat)
+    s.factor_step(); s.update_state()
+    s.eliminate_coupling(prob.forecast.demand[1], prob.forecast.prices[1])
+    assert s.info().sweep_mode == cabi.SWEEP_PERSISTENT
+    s.apg_init()
+    s.write("VEC_XI", g["xi"]); s.write("VEC_PSI", g["psi"])
+    s.write("VEC_UPDATE_XI", g["updateXi"]); s.write("VEC_UPDATE_PSI", g["updatePsi"])
+    th = g["theta"].astype(np.float32)
+    lam = np.float32(th[1] * (np.float32(1) / th[0] - np.float32(1)))
+    launches = s.info().kernel_launches
+    s.apg_continue(1, lambdas=[lam])
+    assert s.info().kernel_launches - launches == 5      # 3 chain-major copies + k_apg_persistent + k_finalize
+    smpc_close(s.read("VEC_ACCEL_XI"), g["acceleXi"]); smpc_close(s.read("VEC_ACCEL_PSI"), g["accelePsi"])
+    smpc_close(s.read("VEC_XI"), g["finalXi"]); smpc_close(s.read("VEC_PSI"), g["finalPsi"])     # y_{k-1} <- y_k
+    smpc_close(s.read("VEC_X"), g["X"]); smpc_close(s.read("VEC_U"), g["U"])
+    engine_close(s.read("VEC_V"), g["tempV"], tol=1e-3)
+    smpc_close(s.read("VEC_PRIMAL_XI"), g["primalX"]); smpc_close(s.read("VEC_PRIMAL_PSI"), g["primalU"])
+    smpc_close(s.read("VEC_DUAL_XI"), g["dualX"]); smpc_close(s.read("VEC_DUAL_PSI"), g["dualU"])
+    smpc_close(s.read("VEC_RESIDUAL_XI"), g["fixedPointResidualXi"])
+    smpc_close(s.read("VEC_RESIDUAL_PSI"), g["fixedPointResidualPsi"])
+    # the golden dual update starts from the golden residual and the golden w (TestSmpcController.cu:369-389), both
+    # reproduced above, so y_{k+1} = w + step * res must match finalUpdate as well
+    smpc_close(s.read("VEC_UPDATE_XI"), g["finalUpdateXi"]); smpc_close(s.read("VEC_UPDATE_PSI"), g["finalUpdatePsi"])
+    s.close()
+
+
+def test_warm_start_continues_the_iteration(toy):
+    """rn_apg_continue with the theta sequence of a longer solve continues it exactly: 30 cold iterations followed by 20
+    continued ones (with lambda_30..49) equal 50 cold iterations; warm_restart restarts theta from the final duals."""
+    prob = toy[0]
+    s = cabi.Solver(prob)
+    s.factor_step(); s.update_state(); s.eliminate_coupling(prob.forecast.demand[1], prob.forecast.prices[1])
+    s.apg_solve(50)
+    want = {k: s.read(k) for k in ("VEC_U", "VEC_X", "VEC_UPDATE_XI", "VEC_UPDATE_PSI", "VEC_XI")}
+    th0, th1, lams = np.float32(1), np.float32(1), []
+    for _ in range(50):
+        lams.append(np.float32(th1 * (np.float32(1) / th0 - np.float32(1))))
+        th0 = th1
+        th1 = np.float32(0.5 * (np.sqrt(float(th1) ** 4 + 4 * float(th1) ** 2) - float(th1) ** 2))
+    s.apg_solve(30)
+    s.apg_continue(20, lambdas=lams[30:])
+    for k, v in want.items():
+        assert np.allclose(s.read(k), v, rtol=2e-5, atol=1e-3 * max(1.0, float(np.abs(v).max()))), k
+    y = s.read("VEC_UPDATE_XI").copy()
+    s.apg_continue(1, warm_restart=True)
+    assert np.array_equal(s.read("VEC_XI"), y)           # y_{-1} = y_0 = the previous duals
+    assert np.isfinite(s.read("VEC_U")).all()
+    s.close()
+
+
 def test_cusolver_null_space(toy):
     """Default path (Engine::calculateMatLandMatLhat through cuSOLVER Dgesvd): a valid orthonormal basis of
     null(E) spanning the golden subspace, and the basis-free Lhat of the shipped config."""

@@ -1,16 +1,17 @@
 """GPU: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
 
 Tolerance (BASELINE.md section 5 / north_star): fp32 relative 1e-4, norm-wise ||a-b||/||b|| on every iterate
-(U, X, y, z, Hx) and on u0, at equal iteration counts 1, 10, 100 and 500 -- widened to KAPPA x the fp32 noise floor
-(the oracle's own distance from the same code in double, refcompare.floor_tol) where that floor exceeds 1e-4, which
-happens only at 500 iterations."""
+(U, X, y, z, Hx) and on u0, at equal iteration counts 1, 10, 100 and 500 -- where the oracle's own distance from the same
+code in double exceeds 1e-4 / 3 (only at 500 iterations) the bound is three times that distance (refcompare.floor_tol) --
+plus the accuracy gate: ours is at most twice as far from the double-precision trajectory as the fp32 oracle is.  The
+bench workloads run here at their operating point too (C2 and C3, 500 iterations)."""
 import numpy as np
 import pytest
 
 from oracle.oracle import Oracle
 from rapidnet_b200 import cabi
 from rapidnet_b200.datagen import named_problem
-from refcompare import RTOL, floor_tol, pinf_close, rel_err
+from refcompare import RTOL, accuracy_gate, floor_tol, pinf_close, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -56,6 +57,10 @@ def _compare_state(s, o, tag, o64=None):
         tol, floor = (RTOL, 0.0) if o64 is None else floor_tol(want, o64.get(oname), den=den)
         worst = max(worst, err)
         assert err < tol, f"{tag}: {gname} rel err {err:.3e} (tolerance {tol:.1e}, fp32 noise floor {floor:.1e})"
+        if o64 is not None:
+            den64 = np.linalg.norm(o64.get(scale[oname])) if oname in scale else None
+            ok, e_ours, e_ref = accuracy_gate(got, want, o64.get(oname), den=den64)
+            assert ok, f"{tag}: {gname} is {e_ours:.3e} from the double-precision trajectory, the fp32 oracle {e_ref:.3e}"
     return worst
 
 
@@ -92,8 +97,10 @@ def test_toy_iterates_match_oracle(toy_problem, sweep, factors):
 
 
 @pytest.mark.parametrize("sweep", [cabi.SWEEP_PERSISTENT, cabi.SWEEP_CHAIN], ids=["persistent", "chain"])
-@pytest.mark.parametrize("name", ["C1", "C1r6", "C1r30"])
+@pytest.mark.parametrize("name", ["C1", "C1r6", "C1r30", "C2", "C3"])
 def test_barcelona_iterates_match_oracle(name, sweep):
+    if name in ("C2", "C3") and sweep != cabi.SWEEP_PERSISTENT:
+        pytest.skip("the bench workloads are checked on the path the bench runs")
     prob = named_problem(name)
     s, o = _setup(prob, sweep, cabi.FACTORS_FULL)
     for gname, oname in (("MAT_PHI", "Phi"), ("MAT_PSI", "Psi"), ("MAT_D", "D"), ("MAT_F", "F"), ("VEC_BETA", "beta")):

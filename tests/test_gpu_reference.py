@@ -2,12 +2,15 @@
 oracle/build_ref.sh from the unmodified /root/reference/src) on identical JSON inputs.
 
 north_star parity: "the same primal/dual iterates after a fixed iteration count and the same first-stage control u0
-within a stated fp32 relative tolerance (e.g. 1e-4)".  Tolerance used here: norm-wise relative 1e-4 on every
-basis-invariant iterate (U, X, y, y_prev, z, Hx, w) and on u0, at equal iteration counts.  V and beta live in the
-null-space basis chosen by cuSOLVER and are compared only after feeding the reference's L back in.
-Where the reference's own fp32 rounding uncertainty exceeds 1e-4 (its distance from the same algorithm run in double,
-which happens at 500 iterations) the bar is KAPPA x that distance instead (refcompare.floor_tol); every case prints
-the measured floor next to our error.
+within a stated fp32 relative tolerance (e.g. 1e-4)".  Two gates per basis-invariant iterate (U, X, y, y_prev, z, Hx, w)
+and for u0, at equal iteration counts (tests/refcompare.py):
+  accuracy   ours is at most twice as far from the double-precision trajectory as the reference build itself is;
+  agreement  norm-wise relative 1e-4 against the reference build wherever the reference's own distance from the double
+             trajectory allows it (<= 1e-4 / 3); otherwise three times that distance (what the accuracy gate implies), and
+             the case prints "floor-limited".
+V and beta live in the null-space basis chosen by cuSOLVER and are compared only after feeding the
+reference's L back in.  The cases include the bench workloads at their operating point: C2 and C3 at 500 iterations.
+tools/parity_table.py prints the same three errors per variable (profiles/r02_parity_table.md).
 """
 import os
 import subprocess
@@ -19,7 +22,7 @@ from rapidnet_b200 import cabi
 from rapidnet_b200.datagen import named_problem
 from rapidnet_b200.problem import write_problem
 from oracle.oracle import Oracle
-from refcompare import RTOL, floor_tol, pinf_close, rel_err
+from refcompare import RTOL, accuracy_gate, floor_tol, pinf_close, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -52,7 +55,8 @@ def _toy_problem(toy, iters):
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ref_driver not built (needs /root/reference at build time)")
 @pytest.mark.parametrize("case,iters", [("toy", 1), ("toy", 100), ("toy", 500), ("C1", 10), ("C1", 500), ("C1r6", 200),
-                                        ("C1r30", 100), ("C2", 50)])
+                                        ("C1r6", 500), ("C1r30", 100), ("C1r30", 500), ("C2", 50), ("C2", 500), ("C3", 100),
+                                        ("C3", 500)])
 def test_iterates_match_reference_build(case, iters, toy, tmp_path):
     slot = 1 if case == "toy" else 0
     prob = _toy_problem(toy, iters) if case == "toy" else named_problem(case, max_iter=iters)
@@ -66,15 +70,24 @@ def test_iterates_match_reference_build(case, iters, toy, tmp_path):
     o64 = Oracle(prob, L=ref["L"], Lhat=ref["Lhat"], precision="f64")
     o64.factor_step(); o64.update_state(); o64.eliminate(fc.demand[slot], fc.prices[slot]); o64.apg(iters)
     worst = ("", 0.0, 0.0)
+    limited = False
     for gname, rname, oname in PAIRS:
-        err = rel_err(s.read(gname), ref[rname])
+        ours = s.read(gname)
+        err = rel_err(ours, ref[rname])
         tol, floor = floor_tol(ref[rname], o64.get(oname))
+        ok, e_ours, e_ref = accuracy_gate(ours, ref[rname], o64.get(oname))
+        limited |= tol > RTOL
         if err > worst[1]:
             worst = (gname, err, floor)
+        assert ok, (f"{case} it={iters}: {gname} is {e_ours:.3e} from the double-precision trajectory, the reference build "
+                    f"{e_ref:.3e}: more than twice as far")
         assert err < tol, (f"{case} it={iters}: {gname} rel err {err:.3e} vs the reference build "
                            f"(tolerance {tol:.1e}; the reference is {floor:.1e} from the double-precision trajectory)")
     u0_tol, u0_floor = floor_tol(ref["u0"], o64.get("U")[: u0.size])
+    ok, e_ours, e_ref = accuracy_gate(u0, ref["u0"], o64.get("U")[: u0.size])
+    assert ok, f"{case} it={iters}: u0 is {e_ours:.3e} from the double-precision trajectory, the reference build {e_ref:.3e}"
     assert rel_err(u0, ref["u0"]) < u0_tol, (rel_err(u0, ref["u0"]), u0_tol)
+    limited |= u0_tol > RTOL
     ours_vs_64 = rel_err(s.read("VEC_U"), o64.get("U"))
     o64.close()
     # vecPrimalInfs (signed value at arg-max-abs, SmpcController.cu:1487-1495)
@@ -83,7 +96,8 @@ def test_iterates_match_reference_build(case, iters, toy, tmp_path):
     # same cuSOLVER routine on the same matrix -> the same null-space basis; then V and beta must agree too
     lerr = rel_err(s.read("SYS_MAT_L"), ref["L"])
     print(f"{case} it={iters}: worst {worst[0]} {worst[1]:.2e} (reference vs double {worst[2]:.2e}); u0 {rel_err(u0, ref['u0']):.2e} "
-          f"(floor {u0_floor:.2e}); U ours vs double {ours_vs_64:.2e}; L vs ref {lerr:.2e}; {log.strip()}")
+          f"(floor {u0_floor:.2e}{', floor-limited' if limited else ''}); U ours vs double {ours_vs_64:.2e}; L vs ref {lerr:.2e}; "
+          f"{log.strip()}")
     s.close()
     s2 = cabi.Solver(prob)
     s2.set_null_space(ref["L"], ref["Lhat"])

@@ -104,6 +104,15 @@ def test_apg_steps_golden_gpu(toy, tmp_path):
 
 
 @pytest.mark.gpu
+def test_fresh_controller_factors_lazily(tmp_path):
+    """controlAction on a controller that never saw initialiseSmpcController: the reference's solveStep factors on first
+    use (SmpcController.cu:579-582); the facade does the same and gives the control of an explicitly initialised one."""
+    from rapidnet_b200.datagen import named_problem
+    cfg = write_problem(named_problem("C1", max_iter=20), str(tmp_path))
+    assert "fresh: ok" in _run("fresh", cfg)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("factors", ["full", "shared"])
 def test_closed_loop_matches_ctypes_path(tmp_path, factors):
     """main.cu's closed loop through the C++ classes == the same calls through the ctypes binding (bit-identical: both

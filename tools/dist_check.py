@@ -3,7 +3,8 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
       tools/dist_check.py --workload C1r30 --iters 1,10,100
 Every rank solves the partitioned problem; rank 0 also solves the whole tree on its GPU and compares the gathered
-iterates (expected: bit-identical -- the crown is computed from the same head tables in the same order, the chains by
+iterates (expected: bit-identical -- the cut is aligned to the bottom-crown nodes, whose head sums and beta rows are
+formed by the owning rank in the order of the single-GPU solve; the crown is computed from the same tables, the chains by
 the same code).  Prints one line per iteration count and "DIST_CHECK OK" / "DIST_CHECK FAIL"."""
 import argparse
 import os
@@ -57,11 +58,13 @@ def main():
                 err = float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
                 worst = max(worst, err)
             pinf = merge_pinf(parts)
-            pe = float(np.abs(pinf[: iters - 1] - rinf[: iters - 1]).max()) if iters > 1 else 0.0
+            pe = float(np.abs(pinf[:iters] - rinf[:iters]).max())          # every row, the last one (k_finalize) included
             same = all(np.array_equal(got[k], ref.read(k).reshape(got[k].shape)) for k in got)
             print(f"{args.workload} x{world} it={iters}: worst rel diff vs 1 GPU {worst:.2e}, bit-identical {same}, "
                   f"u0 diff {float(np.abs(u0 - ru0).max()):.2e}, pinf diff {pe:.2e}", flush=True)
-            ok = ok and worst < (1e-5 if iters <= 10 else 1e-4)   # fp32 rounding grows with the iteration count (DESIGN.md tolerances)
+            pe_ok = pe < 1e-3 * max(1.0, float(np.abs(rinf[: max(iters - 1, 1)]).max()))
+            # every exchanged sum is formed by ONE rank in the order of the single-GPU solve: bit-identical is the expectation
+            ok = ok and worst < 1e-6 and pe_ok
     if args.bench:
         dist.barrier()
         ds.apg_solve(100, want_u0=False); ds.solver.sync()
