@@ -246,7 +246,7 @@ def bench_config(name, args, local, stream, barrier, peak):
     fc = prob.forecast
     s = cabi.Solver(prob, device=local)
     s.set_stream(stream.cuda_stream)
-    s.set_modes({"persistent": cabi.SWEEP_PERSISTENT, "chain": cabi.SWEEP_CHAIN, "per_stage": cabi.SWEEP_PER_STAGE}[args.sweep],
+    s.set_modes({"persistent": cabi.SWEEP_PERSISTENT, "chain": cabi.SWEEP_CHAIN, "per_stage": cabi.SWEEP_PER_STAGE, "batched": cabi.SWEEP_BATCHED}[args.sweep],
                 {"full": cabi.FACTORS_FULL, "df": cabi.FACTORS_DF, "shared": cabi.FACTORS_SHARED}[args.factors])
     s.factor_step(); s.update_state(); s.eliminate_coupling(fc.demand[0], fc.prices[0])
     big = prob.tree.nodes > 20000
@@ -455,7 +455,7 @@ def main():
     ap.add_argument("--closed-loop-lanes", type=int, default=4, help="that leg again with this many handles per GPU side by side (1 = skip)")
     ap.add_argument("--closed-loop-steps", type=int, default=2, help="receding-horizon steps per instance in that leg")
     ap.add_argument("--closed-loop-workload", default="C1r30", help="tree of that leg (SURVEY C4: the shipped K=30 tree)")
-    ap.add_argument("--sweep", default="persistent", choices=["persistent", "chain", "per_stage"])
+    ap.add_argument("--sweep", default="persistent", choices=["persistent", "chain", "per_stage", "batched"])
     ap.add_argument("--factors", default="full", choices=["full", "df", "shared"])
     ap.add_argument("--partition-workload", default="C3", help="N > 1: the tree that is cut across the GPUs = the headline ('' = replicas only)")
     ap.add_argument("--partition-extra", default="C3b", help="N > 1: a second, larger tree cut across the GPUs ('' = skip)")
@@ -489,7 +489,7 @@ def main():
     s = cabi.Solver(prob, device=local)
     stream = torch.cuda.Stream()
     s.set_stream(stream.cuda_stream)          # torch.cuda.Event sees the stream the kernels are launched on
-    s.set_modes({"persistent": cabi.SWEEP_PERSISTENT, "chain": cabi.SWEEP_CHAIN, "per_stage": cabi.SWEEP_PER_STAGE}[args.sweep],
+    s.set_modes({"persistent": cabi.SWEEP_PERSISTENT, "chain": cabi.SWEEP_CHAIN, "per_stage": cabi.SWEEP_PER_STAGE, "batched": cabi.SWEEP_BATCHED}[args.sweep],
                 {"full": cabi.FACTORS_FULL, "df": cabi.FACTORS_DF, "shared": cabi.FACTORS_SHARED}[args.factors])
     s.factor_step()
     s.update_state()

@@ -91,9 +91,12 @@ typedef enum rn_sweep_mode {
                                 literal shape of SmpcController::solveStep (:593-741)           */
     RN_SWEEP_CHAIN = 1,      /* node-parallel factor stream, then one CTA per scenario chain below
                                 the last branching stage, per-stage launches above (CUDA graph)   */
-    RN_SWEEP_PERSISTENT = 2  /* default: the whole APG loop in ONE persistent cooperative kernel, grid
+    RN_SWEEP_PERSISTENT = 2, /* default: the whole APG loop in ONE persistent cooperative kernel, grid
                                 barrier per crown stage, chains as scans + GEMMs across their stages;
-                                falls back to RN_SWEEP_CHAIN when the problem does not fit it       */
+                                falls back to RN_SWEEP_BATCHED when the problem does not fit it     */
+    RN_SWEEP_BATCHED = 3     /* node-parallel factor stream, then the sweeps as four GEMMs ACROSS ALL NODES
+                                against the shared matrices G, OmegaBar, L, B (every Omega_i is OmegaBar / p_i)
+                                with element-wise scans over the stages in between (CUDA graph); any dimensions */
 } rn_sweep_mode;
 
 /* Which per-node factor matrices the stream kernel reads (DESIGN.md "formulations"). */

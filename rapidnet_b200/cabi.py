@@ -20,7 +20,7 @@ RN_OK = 0
 STATUS_NAMES = {0: "RN_OK", 1: "RN_ERR_INVALID", 2: "RN_ERR_CUDA", 3: "RN_ERR_STATE", 4: "RN_ERR_SINGULAR",
                 5: "RN_ERR_NOMEM"}
 
-SWEEP_PER_STAGE, SWEEP_CHAIN, SWEEP_PERSISTENT = 0, 1, 2
+SWEEP_PER_STAGE, SWEEP_CHAIN, SWEEP_PERSISTENT, SWEEP_BATCHED = 0, 1, 2, 3
 FACTORS_FULL, FACTORS_DF, FACTORS_SHARED = 0, 1, 2
 STEP_EXTRAPOLATE, STEP_SOLVE, STEP_PROX, STEP_RESIDUAL, STEP_DUAL_UPDATE = range(5)
 

@@ -35,7 +35,6 @@ constexpr int kConsumers = 512;                  // consumer threads (16 warps) 
 constexpr int kStreamThreads = kConsumers + 32;
 constexpr int kStages = 6;                       // ring depth
 constexpr int kStageFloats = 4096;               // payload per stage (16 KB)
-constexpr int kStageStride = kStageFloats + 32;  // + slack for the 16-B window, keeps stages 128-B aligned
 
 struct StreamArgs {
     const float *mat[4];       // D, F, Phi, Psi (packed per node, Engine.cu:201-207)
@@ -49,6 +48,7 @@ struct StreamArgs {
     int nodes, nx, nu, nv;
     int halves;                // 2: {D,F} and {Phi,Psi};  1: {D,F} only
     int cols_per_chunk;
+    int stage_stride;          // floats per ring stage (payload + 32 floats of slack for the 16-B window)
     int extrapolate;           // 1: w from y_k, y_{k-1};  0: w is read from w_xi / w_psi (step API)
     int dry;                   // profiling: lambda = 0, no vector writes
 };
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nx = A.nx, nu = A.nu, nv = A.nv, ny = 2 * nx + nu;
     float *stage_buf = reinterpret_cast<float *>(smem_raw);
-    float *wbuf = stage_buf + kStages * kStageStride;
+    float *wbuf = stage_buf + kStages * A.stage_stride;
     float *red = wbuf + ((ny + 31) & ~31);
     uint64_t *full = reinterpret_cast<uint64_t *>(red + kConsumers);
     uint64_t *empty = full + kStages;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
                         const uint32_t bytes = (uint32_t)(b1 - b0);
                         mbar_wait(&empty[st], ph ^ 1);
                         mbar_expect_tx(&full[st], bytes);
-                        bulk_g2s(stage_buf + st * kStageStride, reinterpret_cast<const void *>(b0), bytes, &full[st]);
+                        bulk_g2s(stage_buf + st * A.stage_stride, reinterpret_cast<const void *>(b0), bytes, &full[st]);
                         if (++st == kStages) { st = 0; ph ^= 1; }
                     }
                 }
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
                 const int cc = min(A.cols_per_chunk, ncols - c0);
                 const int off = (int)((reinterpret_cast<uintptr_t>(base + (size_t)c0 * nv) & 15) >> 2);
                 mbar_wait(&full[st], ph);
-                const float *sb = stage_buf + st * kStageStride + off;
+                const float *sb = stage_buf + st * A.stage_stride + off;
                 if (active) {
 #pragma unroll 4
                     for (int j = g; j < cc; j += G) {
@@ -184,9 +184,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
     }
 }
 
+// ring stage payload: 16 KB; 32 KB for wide matrices (nv > 128: a 16 KB stage would hold ten columns of the 4 x network)
+static int stream_stage_floats(const Handle *h) { return h->d.nv > 128 ? 2 * kStageFloats : kStageFloats; }
 static size_t stream_smem_bytes(const Handle *h) {
     const int ny = 2 * h->d.nx + h->d.nu;
-    return (size_t)kStages * kStageStride * 4 + (size_t)((ny + 31) & ~31) * 4 + kConsumers * 4 + 2 * kStages * 8 + 64;
+    return (size_t)kStages * (stream_stage_floats(h) + 32) * 4 + (size_t)((ny + 31) & ~31) * 4 + kConsumers * 4 + 2 * kStages * 8 + 64;
 }
 
 // ============================================================================================
@@ -708,8 +710,9 @@ static rn_status launch_stream(Handle *h, cudaStream_t st, bool extrapolate, boo
     A.lambda_tab = h->lambda_tab; A.iter = h->iter_dev;
     A.nodes = d.nodes; A.nx = d.nx; A.nu = d.nu; A.nv = d.nv;
     A.halves = h->factor_mode == RN_FACTORS_FULL ? 2 : 1;
-    A.cols_per_chunk = kStageFloats / d.nv;
-    if (A.cols_per_chunk < 1) return fail(h, RN_ERR_INVALID, "nv = %d exceeds the stream kernel's stage (%d floats)", d.nv, kStageFloats);
+    A.cols_per_chunk = stream_stage_floats(h) / d.nv;
+    A.stage_stride = stream_stage_floats(h) + 32;
+    if (A.cols_per_chunk < 1) return fail(h, RN_ERR_INVALID, "nv = %d exceeds the stream kernel's stage (%d floats)", d.nv, stream_stage_floats(h));
     A.extrapolate = extrapolate ? 1 : 0;
     A.dry = dry ? 1 : 0;
     const size_t smem = stream_smem_bytes(h);
@@ -733,8 +736,18 @@ static rn_status launch_stream(Handle *h, cudaStream_t st, bool extrapolate, boo
 }
 
 // the tree sweeps of solveStep; returns the number of kernels launched and the number of distance slots written
+// RN_SWEEP_BATCHED, and what RN_SWEEP_PERSISTENT / RN_SWEEP_CHAIN fall back to when the problem does not fit their shared memory
+bool use_batched(const Handle *h) {
+    if (h->factor_mode == RN_FACTORS_SHARED) return false;
+    if (h->sweep_mode == RN_SWEEP_BATCHED) return true;
+    if (h->sweep_mode == RN_SWEEP_PERSISTENT) return !persistent_supported(h);
+    if (h->sweep_mode == RN_SWEEP_CHAIN) return !chain_fits(h);
+    return false;
+}
+
 static rn_status launch_sweeps(Handle *h, cudaStream_t st, bool fuse_prox, int *n_launch, int *n_slots, cudaEvent_t mid = nullptr) {
     const rn_dims &d = h->d;
+    if (use_batched(h)) return launch_sweeps_batched(h, st, fuse_prox, n_launch, n_slots, mid);
     const bool chains = h->sweep_mode != RN_SWEEP_PER_STAGE && chain_fits(h);
     const int cs = chains ? h->chain_stage : d.N;   // stages [0, cs) go stage by stage, [cs, N) as chains
     SweepArgs S = make_sweep_args(h, fuse_prox);
@@ -872,6 +885,7 @@ rn_status profile_kernels(Handle *h, int iterations, float *ms_out) {
         ms_out[RN_PROF_FINALIZE] = (float)((rest > 0 ? rest : 0) / iterations);   // launch + the one k_finalize
         return RN_OK;
     }
+    if (use_batched(h)) RN_CHECK(batched_prepare(h));
     std::vector<cudaEvent_t> ev((size_t)iterations * 5);
     for (auto &e : ev) RN_CUDA(h, cudaEventCreate(&e));
     long long per_iter = 0;
@@ -922,6 +936,7 @@ rn_status apg_enqueue(Handle *h, int iterations) {
     RN_CHECK(ensure_lambda(h, iterations));
     RN_CHECK(apg_init(h));
     if (use_persistent(h)) return enqueue_persistent(h, iterations);
+    if (use_batched(h)) RN_CHECK(batched_prepare(h));
     if (h->factor_mode == RN_FACTORS_SHARED)
         return fail(h, RN_ERR_INVALID, "RN_FACTORS_SHARED needs the persistent sweep (RN_SWEEP_PERSISTENT on a tree it supports)");
     static const bool no_graph = getenv("RN_NO_GRAPH") != nullptr;
@@ -1007,6 +1022,7 @@ rn_status apg_step(Handle *h, rn_step_kind kind, float lambda) {
         }
         case RN_STEP_SOLVE: {
             int nl = 0, slots = 0;
+            if (use_batched(h)) RN_CHECK(batched_prepare(h));
             RN_CHECK(launch_stream(h, h->stream, false, false, h->upd_xi, h->upd_psi, h->xi, h->psi));
             RN_CHECK(launch_sweeps(h, h->stream, false, &nl, &slots));
             h->launches += 1 + nl;

@@ -255,7 +255,7 @@ rn_status rn_sync(rn_handle *hh) {
 rn_status rn_set_modes(rn_handle *hh, rn_sweep_mode sweep, rn_factor_mode factors) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (!h) return RN_ERR_INVALID;
-    if ((sweep != RN_SWEEP_PER_STAGE && sweep != RN_SWEEP_CHAIN && sweep != RN_SWEEP_PERSISTENT) || (factors != RN_FACTORS_FULL && factors != RN_FACTORS_DF && factors != RN_FACTORS_SHARED))
+    if ((sweep != RN_SWEEP_PER_STAGE && sweep != RN_SWEEP_CHAIN && sweep != RN_SWEEP_PERSISTENT && sweep != RN_SWEEP_BATCHED) || (factors != RN_FACTORS_FULL && factors != RN_FACTORS_DF && factors != RN_FACTORS_SHARED))
         return rn::fail(h, RN_ERR_INVALID, "rn_set_modes: unknown mode");
     h->sweep_mode = sweep;
     h->factor_mode = factors;

@@ -108,6 +108,7 @@ struct Handle {
     bool xchg_opened[8] = {false, false, false, false, false, false, false, false};
     unsigned int xepoch = 0;
     float *pinf4 = nullptr;
+    float *bat_y = nullptr, *bat_y3 = nullptr, *bat_x = nullptr;   // RN_SWEEP_BATCHED scratch: GEMM outputs, X = -1/2 (sigma + G q_bar)
     float *head_q = nullptr, *head_r = nullptr;    // q / r of this rank's chain heads (persistent kernel)
     int pinf4_cap = 0;
     float *cm_c = nullptr, *cm_lv = nullptr, *cm_beta = nullptr, *cm_uhat = nullptr, *cm_e = nullptr;   // chain-major arrays
@@ -202,6 +203,9 @@ rn_status ensure_xchg(Handle *h);
 size_t xchg_err_offset(const Handle *h);
 rn_status dist_crown_beta(Handle *h, int pull);
 rn_status persistent_launch(Handle *h, cudaStream_t st, int iters);
+rn_status batched_prepare(Handle *h);
+rn_status launch_sweeps_batched(Handle *h, cudaStream_t st, bool fuse_prox, int *n_launch, int *n_slots, cudaEvent_t mid);
+bool use_batched(const Handle *h);
 rn_status clamp_control(Handle *h);
 rn_status move_forward(Handle *h);
 void fill_lambda_table(std::vector<float> &tab, int iters);

@@ -56,7 +56,8 @@ constexpr int kMaxCs = 8;                       // deepest crown supported (stag
 constexpr int kDimMax = 128;                    // max(2nx, nu, nv) supported by this kernel
 constexpr int kMaxRanks = 8;                    // GPUs of one node
 constexpr double kL2KeepDefault = 0.1;          // RN_L2_KEEP default: share of the L2 given to evict_last factor matrices
-constexpr double kL2PrefDefault = 0.4;          // RN_L2_PREFETCH default: share of the L2 refilled with the next iteration's matrices during the sweeps
+constexpr double kL2PrefDefault = 0.0;          // RN_L2_PREFETCH default (share of the L2 refilled with the next iteration's matrices during the
+                                                // sweeps): off -- measured on C2/C3/C1r30, phase S does not get faster with up to 18 % L2 hits
 
 struct PArgs {
     const int *parent, *child_first, *child_count, *omega_idx, *cum, *stages;
@@ -93,7 +94,7 @@ struct PArgs {
     float *Sq_peer[kMaxRanks], *Sr_peer[kMaxRanks];
     unsigned int *par_ctr;                      // [n_crown] local: chains of a bottom-crown node whose head q, r are in hq / hr (cumulative)
     unsigned int *s_ctr;                        // local, one GPU: bottom-crown nodes whose S row is published (cumulative)
-    int bottom0, n_bottom, n_owned;             // bottom-crown nodes: first id, count, how many of them have their chains on this rank
+    int bottom0, n_bottom, n_owned, own_lo;     // bottom-crown nodes: first id, count; those with their chains on this rank: count, first id (contiguous)
     double *dslot_peer[kMaxRanks];              // [kMaxRanks][2] squared prox distances of each rank, on each rank
     unsigned int *xflag_peer[kMaxRanks];        // [kMaxRanks] arrival epochs, on each rank
     int *xerr;                                  // local: set when a cross-GPU wait timed out
@@ -959,13 +960,13 @@ __device__ __noinline__ void parent_sum(const PArgs &P, int p, int it) {
 
 // `wait_s`: single GPU -- the S rows of the bottom-crown nodes are awaited here (a counter parent_sum bumps), after the
 // first column's sums over its crown descendants, so that the crown overlaps the chains' backward sweep
-__device__ __noinline__ void crown_sums(const PArgs &P, int i0, int ncols, unsigned int wait_s, uint32_t mpar) {
+__device__ __noinline__ void crown_sums(const PArgs &P, int ncols, unsigned int wait_s, uint32_t mpar) {
     const SweepSmem S = sweep_smem(P);
     const int t = threadIdx.x, g = t >> 6, role = (t >> 5) & 1, c4 = t & 31, nx = P.nx, nv = P.nv, cs = P.cs, nxp = P.nxp, nvp = P.nvp;
     static_assert(8 * 3 * 128 <= 128 * kTP, "partial sums of the row groups fit the split-K scratch");
 #pragma unroll 1
     for (int col = 0; col < ncols; col++) {
-        const int i = i0 + col, si = __ldg(P.stages + i);
+        const int i = S.colid[col], si = __ldg(P.stages + i);
         const int *rng = P.crown_rng + (size_t)i * (kMaxCs + 1) * 2;
         F4 acc{0.f, 0.f, 0.f, 0.f}, accw{0.f, 0.f, 0.f, 0.f};   // even warps: q_bar, QS; odd warps: sums of beta + D xi + F psi and of r
 #pragma unroll 1
@@ -1035,16 +1036,21 @@ __device__ __noinline__ void crown_sigma(const PArgs &P, int ncols) {
     }
 }
 
-__device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, uint32_t mpar, StagePhase &ph, unsigned int wait_heads) {
+// crown nodes in the order of the second crown pass: the upper crown, then the bottom-crown nodes whose chains live on
+// OTHER ranks (the owned ones, one contiguous id range, were done in the first pass)
+__device__ __forceinline__ int crown_pass2_id(const PArgs &P, int k) { return k < P.own_lo ? k : k + P.n_owned; }
+
+// `mapped`: columns are entries i0 .. i0 + ncols - 1 of the second-pass order; otherwise node ids
+__device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, uint32_t mpar, StagePhase &ph, unsigned int wait_heads, bool mapped) {
     const SweepSmem S = sweep_smem(P);
     const int t = threadIdx.x;
     if (t < kTP) {
-        const int node = t < ncols ? i0 + t : 0;
+        const int node = t < ncols ? (mapped ? crown_pass2_id(P, i0 + t) : i0 + t) : 0;
         S.colnode[t] = node; S.colid[t] = node;
         S.colp[t] = t < ncols ? 1.f / __ldg(P.prob + __ldg(P.omega_idx + node)) : 1.f;
     }
     cbar();
-    crown_sums(P, i0, ncols, wait_heads, mpar);
+    crown_sums(P, ncols, wait_heads, mpar);
     dstamp(P, 11);
     mbar_wait(&S.mfull[0], mpar);
     if (ncols == 1) tile_gemv2(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2, 0, 12);
@@ -1694,6 +1700,7 @@ __device__ __noinline__ void pinf_merge(const PArgs &P, int it) {
     }
 }
 
+__device__ __noinline__ bool cta_sweeps_backward(const PArgs &P);
 // first half of iteration `it`: global distances of the previous prox, phase S, infeasibility log of iteration it-1
 __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
     double *dsh = reinterpret_cast<double *>(smem_f(kOffDsh));      // 2 * 16 doubles
@@ -1756,7 +1763,7 @@ __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
         P.cta_ns[2 * blockIdx.x] += globaltimer() - t_in;   // load balance of phase S (rn_cta_times)
         __threadfence();
         atomicAdd(P.bar, 1u);
-        issue_matrix_loads(P);
+        if (cta_sweeps_backward(P)) issue_matrix_loads(P);
     }
     dstamp(P, 0);
     if (tid == 0) {
@@ -1770,16 +1777,40 @@ __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
     if (it > 0 && (int)blockIdx.x == pcta && warp == 0) pinf_merge(P, it);
 }
 
-// second half of iteration `it`: the sweeps (phases B, C, F), this CTA's share of the prox distances, closing barrier.
-// Three functions, each with little state of its own, so that the sweep steps below them keep their register budget.
+// Crown work is dealt from the last CTA down (those have the fewest chains): first the tiles of the second crown pass (the upper
+// crown is the critical path), then the bottom-crown nodes of the first pass.  Item q goes to the CTA with slot = q mod grid.
+struct CrownDeal { int n2, tile_w, n_tiles2, n_items; };
+__device__ __forceinline__ CrownDeal crown_deal(const PArgs &P) {
+    CrownDeal C;
+    C.n2 = P.n_crown - P.n_owned;
+    C.tile_w = min(kTP / 2, max(1, (C.n2 + (int)gridDim.x - 1) / (int)gridDim.x));
+    C.n_tiles2 = (C.n2 + C.tile_w - 1) / C.tile_w;
+    C.n_items = C.n_tiles2 + P.n_bottom;
+    return C;
+}
+// does this CTA sweep anything backward / forward?  CTAs that do not leave the shared matrices where they are: no bulk copy
+// without a waiter, less L2 traffic
+__device__ __noinline__ bool cta_sweeps_backward(const PArgs &P) {
+    if ((int)blockIdx.x < P.K) return true;
+    if (P.n_crown == 0) return false;
+    const CrownDeal C = crown_deal(P);
+    for (int q = (int)gridDim.x - 1 - (int)blockIdx.x; q < C.n_items; q += (int)gridDim.x)
+        if (q < C.n_tiles2 || __ldg(P.child_count + P.bottom0 + q - C.n_tiles2) > 0) return true;
+    return false;
+}
 struct CrownTiles { int tile_w, n_tiles; };
-__device__ __forceinline__ CrownTiles crown_tiles(const PArgs &P) {   // as narrow as the grid allows (every CTA is free during phase C)
+__device__ __forceinline__ CrownTiles crown_tiles(const PArgs &P) {   // forward: as narrow as the grid allows
     CrownTiles C;
     C.tile_w = min(kTP / 2, max(1, (P.n_crown + (int)gridDim.x - 1) / (int)gridDim.x));
     C.n_tiles = (P.n_crown + C.tile_w - 1) / C.tile_w;
     return C;
 }
+__device__ __forceinline__ bool cta_sweeps_forward(const PArgs &P) {
+    return (int)blockIdx.x < P.K || (P.n_crown > 0 && (int)gridDim.x - 1 - (int)blockIdx.x < crown_tiles(P).n_tiles);
+}
 
+// second half of iteration `it`: the sweeps (phases B, C, F), this CTA's share of the prox distances, closing barrier.
+// Three functions, each with little state of its own, so that the sweep steps below them keep their register budget.
 __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
     const uint32_t mpar = (uint32_t)(it & 1);
     const int grid = (int)gridDim.x, j0 = (int)blockIdx.x, nK = P.K;
@@ -1796,22 +1827,29 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
         // table (chain_qscan / chain_rscan), and this barrier spans the GPUs.  On one GPU only the CTAs that own crown
         // tiles wait, and only for the heads (a counter the chains bump after their r-scan): the crown overlaps the
         // rest of the chains' backward sweep
-        const CrownTiles C = crown_tiles(P);
-        const int n_crown = P.n_crown;
-        // near-root contributions: the S rows of the bottom-crown nodes whose chains live on this rank, dealt from the last
-        // CTA down like the crown tiles
+        const CrownDeal C = crown_deal(P);
+        const int slot = grid - 1 - j0;
+        // Pass 1 -- the bottom-crown nodes whose chains live on this rank: S_p (the sum over p's chain heads; awaits only p's
+        // chains) goes to every rank's table, then p's own backward step follows at once.
 #pragma unroll 1
-        for (int pb = grid - 1 - j0; pb < P.n_bottom; pb += grid) {
-            const int p = P.bottom0 + pb;
-            if (__ldg(P.child_count + p) > 0) parent_sum(P, p, it);
+        for (int q = slot; q < C.n_items; q += grid) {
+            if (q < C.n_tiles2) continue;
+            const int p = P.bottom0 + q - C.n_tiles2;
+            if (__ldg(P.child_count + p) > 0) {
+                parent_sum(P, p, it);
+                crown_backward(P, p, 1, mpar, K.SP, 0u, false);
+            }
         }
+        // Pass 2 -- everything else of the crown needs every S row: with several GPUs they were stored into every rank's table
+        // and this barrier spans the GPUs; on one GPU only the CTAs that own tiles wait, for a counter parent_sum bumps, so
+        // the crown overlaps the rest of the chains' backward sweep
         if (P.n_ranks > 1) grid_sync_cross(P, bar_count(P, it, 1), P.epoch0 + 2u * (unsigned)it + 1u, -1);
-        unsigned int wait_heads = P.n_ranks > 1 ? 0u : (unsigned)P.n_owned * (unsigned)(it + 1);   // counter value once every S row is in
+        unsigned int wait_s = P.n_ranks > 1 ? 0u : (unsigned)P.n_owned * (unsigned)(it + 1);   // counter value once every S row is in
         dstamp(P, 20);
 #pragma unroll 1
-        for (int tl = grid - 1 - j0; tl < C.n_tiles; tl += grid) {
-            crown_backward(P, tl * C.tile_w, min(C.tile_w, n_crown - tl * C.tile_w), mpar, K.SP, wait_heads);
-            wait_heads = 0u;   // awaited once
+        for (int tl = slot; tl < C.n_tiles2; tl += grid) {
+            crown_backward(P, tl * C.tile_w, min(C.tile_w, C.n2 - tl * C.tile_w), mpar, K.SP, wait_s, true);
+            wait_s = 0u;   // awaited once
         }
         dstamp(P, 21);
     }
@@ -1822,14 +1860,14 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(P.bar, 1u);
-            issue_b_load(P);
+            if (cta_sweeps_forward(P)) issue_b_load(P);
             if (j0 < nK) issue_chain_forward_loads(P, j0, 1);   // the staging area is free: this CTA's sweeps are done
             const unsigned int target = bar_count(P, it, P.n_ranks > 1 ? 2 : 1);
             while (ld_acquire_u32(P.bar) < target) {}
         }
         cbar();
         dstamp(P, 22);
-    } else if (threadIdx.x == 0) issue_b_load(P);
+    } else if (threadIdx.x == 0 && cta_sweeps_forward(P)) issue_b_load(P);
 }
 
 // ---- phase F: forward sweep + prox boxes; leaves this CTA's sums of squared distances in K.s1, K.s2
@@ -2280,8 +2318,11 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
         P.hq = h->head_q; P.hr = h->head_r;
         const int cs_ = h->chain_stage;
         P.bottom0 = cs_ > 0 ? h->h_cum[cs_ - 1] : 0; P.n_bottom = cs_ > 0 ? h->h_cum[cs_] - h->h_cum[cs_ - 1] : 0;
-        P.n_owned = 0;
-        for (int b = 0; b < P.n_bottom; b++) P.n_owned += h->h_child_count[P.bottom0 + b] > 0 ? 1 : 0;
+        P.n_owned = 0; P.own_lo = P.bottom0;
+        for (int b = 0; b < P.n_bottom; b++)
+            if (h->h_child_count[P.bottom0 + b] > 0) { if (P.n_owned == 0) P.own_lo = P.bottom0 + b; P.n_owned++; }
+        for (int b = 0; b < P.n_owned; b++)   // the owned bottom-crown nodes are one contiguous id range (contiguous chain ranges)
+            if (h->h_child_count[P.own_lo + b] == 0) return fail(h, RN_ERR_INVALID, "the bottom-crown nodes with local chains are not contiguous");
         RN_CUDA(h, cudaMemsetAsync(own + X.err, 0, sizeof(int), st));   // a timed-out wait of an earlier launch does not poison this one
         P.epoch0 = h->xepoch;
         h->xepoch += 2u * (unsigned)iters + 2u;   // every rank runs the same launches: the epochs stay aligned

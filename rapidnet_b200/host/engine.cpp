@@ -78,6 +78,13 @@ Engine::Engine(SmpcConfiguration *smpcConfig) {
         else if (v != "persistent") { std::cerr << "rapidnet_b200: RAPIDNET_SWEEP=" << v << " is not persistent|chain|per_stage" << std::endl; std::exit(EXIT_FAILURE); }
     }
     check(rn_set_modes(h, sm, fm), "rn_set_modes");
+    // RAPIDNET_NULL_SPACE=config: use the null-space basis matL / matLhat that the controller configuration ships (the
+    // reference parses them and then recomputes its own through cuSOLVER, Engine.cu:466-669; golden vectors produced with
+    // another SVD -- the reference's engineTest.json comes from MATLAB -- only match in the basis of the file)
+    if (const char *e = std::getenv("RAPIDNET_NULL_SPACE")) {
+        if (std::string(e) == "config") check(rn_set_null_space(h, smpcConfig->getMatL(), smpcConfig->getMatLhat()), "rn_set_null_space");
+        else if (std::string(e) != "svd") { std::cerr << "rapidnet_b200: RAPIDNET_NULL_SPACE=" << e << " is not config|svd" << std::endl; std::exit(EXIT_FAILURE); }
+    }
     // RAPIDNET_GRID_LIMIT: share of the SMs for this Engine's persistent kernel when several controllers run side by side
     if (const char *e = std::getenv("RAPIDNET_GRID_LIMIT")) check(rn_set_grid_limit(h, std::atoi(e)), "rn_set_grid_limit");
 }
@@ -92,12 +99,13 @@ cublasHandle_t Engine::getCublasHandle() {
     return cublasHandle;
 }
 
+// Ownership follows the reference: ~Engine releases the device memory and the cuBLAS handle but leaves the DwnNetwork and the
+// ScenarioTree it created to the caller (Engine.cu:1431-1436 has those deletes commented out; the reference's tests delete the
+// two objects themselves, Testing.cu:520-524, and would free them twice otherwise).
 Engine::~Engine() {
     if (cublasHandle) cublasDestroy(cublasHandle);
     for (void *p : ownedDevice) cudaFree(p);
     if (h) rn_destroy(h);
-    delete ptrMyNetwork;
-    delete ptrMyScenarioTree;
 }
 
 void *Engine::toDevice(const void *host, size_t bytes) {
@@ -212,6 +220,12 @@ void SmpcController::check(rn_status rc, const char *what) {
     std::exit(EXIT_FAILURE);
 }
 
+void SmpcController::outOfScope(const char *what) {
+    std::cerr << "rapidnet_b200: SmpcController::" << what << " belongs to the FBE / NAMA solvers of the reference, which this build "
+                 "does not contain (controlAction always runs APG, SmpcController.cu:1617, 1646)" << std::endl;
+    std::exit(EXIT_FAILURE);
+}
+
 void SmpcController::construct() {
     stepSize = ptrMySmpcConfig->getStepSize();
     factorStepFlag = false;
@@ -235,16 +249,25 @@ SmpcController::SmpcController(std::string pathToConfigFile) {
     ptrMySmpcConfig = new SmpcConfiguration(pathToConfigFile);
     ptrMyForecaster = new Forecaster(ptrMySmpcConfig->getPathToForecaster());
     ptrMyEngine = new Engine(ptrMySmpcConfig);
-    ownsObjects = true;   // the reference never deletes them (SmpcController.cu:2091-2102); this build does
+    ownsObjects = true;   // released by releaseObjects(), or by the caller as in the reference's tests
     construct();
 }
 
-SmpcController::~SmpcController() {
-    if (ownsObjects) {
-        delete ptrMyEngine;
-        delete ptrMyForecaster;
-        delete ptrMySmpcConfig;
-    }
+// Like the reference (SmpcController.cu:2091-2102 frees its own buffers only), the controller does not delete the configuration,
+// the forecaster and the engine -- not even the ones SmpcController(string) created (:78-82): its callers do
+// (Testing.cu:520-526 deletes every one of them BEFORE the controller; nothing here may touch them).
+// releaseObjects() is the one-call version of those deletes for callers written against this library.
+SmpcController::~SmpcController() {}
+
+void SmpcController::releaseObjects() {
+    if (!ownsObjects) return;
+    DwnNetwork *n = ptrMyEngine ? ptrMyEngine->getDwnNetwork() : nullptr;
+    ScenarioTree *t = ptrMyEngine ? ptrMyEngine->getScenarioTree() : nullptr;
+    delete ptrMyEngine; delete n; delete t;
+    delete ptrMyForecaster;
+    delete ptrMySmpcConfig;
+    ptrMyEngine = nullptr; ptrMyForecaster = nullptr; ptrMySmpcConfig = nullptr;
+    ownsObjects = false;
 }
 
 void SmpcController::refreshDevicePointers() {
@@ -263,6 +286,8 @@ void SmpcController::refreshDevicePointers() {
     devVecUpdateXi = get(RN_BUF_VEC_UPDATE_XI); devVecUpdatePsi = get(RN_BUF_VEC_UPDATE_PSI);
     devVecFixedPointResidualXi = get(RN_BUF_VEC_RESIDUAL_XI); devVecFixedPointResidualPsi = get(RN_BUF_VEC_RESIDUAL_PSI);
     devControlAction = get(RN_BUF_CONTROL_ACTION); devStateUpdate = get(RN_BUF_STATE_UPDATE);
+    proximalSlots[0] = devVecAcceleratedXi; proximalSlots[1] = devVecAcceleratedPsi;   // SmpcController.cu:510-511
+    ptrProximalXi = &proximalSlots[0]; ptrProximalPsi = &proximalSlots[1];
 }
 
 void SmpcController::initialiseSmpcController() {

@@ -352,6 +352,7 @@ static int closed_loop(const std::string &cfgPath, int steps, const std::string 
     }
     out << "], \"economic_kpi\": " << ctl->getEconomicKpi(steps) << ", \"smooth_kpi\": " << ctl->getSmoothKpi(steps)
         << ", \"safety_kpi\": " << ctl->getSafetyKpi(steps) << ", \"network_kpi\": " << ctl->getNetworkKpi(steps) << "}" << std::endl;
+    ctl->releaseObjects();
     delete ctl;
     return 0;
 }
@@ -398,7 +399,7 @@ static int closed_loop_lanes(const std::string &cfgPath, int steps, int lanes, c
     const int ref = lanes > 1 ? 1 : 0;
     for (size_t i = 0; i < u0[ref].size(); i++) out << (i ? ", " : "") << u0[ref][i];
     out << "]}" << std::endl;
-    for (auto *c : ctl) delete c;
+    for (auto *c : ctl) { c->releaseObjects(); delete c; }
     T_ASSERT(same == 1);
     std::cout << "host_tests lanes: ok (" << lanes << " lanes, " << steps / (one_ms * 1e-3) << " -> " << (double)lanes * steps / (all_ms * 1e-3)
               << " solves/s)" << std::endl;
@@ -414,6 +415,7 @@ static int fresh_controller(const std::string &cfgPath) {
     eager.initialiseSmpcController();
     T_ASSERT(eager.controlAction(b.data()) == 1);
     T_ASSERT(std::memcmp(a.data(), b.data(), nu * sizeof(real_t)) == 0);
+    lazy.releaseObjects(); eager.releaseObjects();
     std::cout << "host_tests fresh: ok" << std::endl;
     return 0;
 }

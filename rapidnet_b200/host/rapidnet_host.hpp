@@ -251,6 +251,7 @@ public:
     SmpcController(Forecaster *myForecaster, Engine *myEngine, SmpcConfiguration *mySmpcConfig);
     explicit SmpcController(std::string pathToConfigFile);
     virtual ~SmpcController();
+    void releaseObjects();   // not in the reference: deletes what SmpcController(string) created (the reference leaves that to its callers)
     void initialiseSmpcController();                       // SmpcController.cu:476-487
     void controllerSmpc();                                 // :1593-1599
     uint_t controlAction(real_t *u);                       // :1607-1625   1 = success
@@ -287,6 +288,28 @@ protected:
     real_t *devVecUpdateXi = nullptr, *devVecUpdatePsi = nullptr;
     real_t *devVecFixedPointResidualXi = nullptr, *devVecFixedPointResidualPsi = nullptr;
     real_t *devControlAction = nullptr, *devStateUpdate = nullptr;
+    // where the prox reads its argument (SmpcController.cuh:429-433): entry 0 is the accelerated dual w in APG mode (:510-511)
+    real_t **ptrProximalXi = nullptr, **ptrProximalPsi = nullptr;
+    // ---- members of the solvers that are OUT OF SCOPE here (global FBE, NAMA, L-BFGS: SmpcController.cuh:203-300, 417-627;
+    // never reached from controlAction).  They are declared so that code written against the
+    // reference's class -- its own TestSmpcController among it -- compiles; the buffers stay null and the methods stop the
+    // program with a message, like every error of the reference does.
+    void computeHessianOracalGlobalFbe() { outOfScope("computeHessianOracalGlobalFbe"); }
+    void computeGradientFbe() { outOfScope("computeGradientFbe"); }
+    void computeLbfgsDirection() { outOfScope("computeLbfgsDirection"); }
+    real_t computeLineSearchLbfgsUpdate(real_t) { outOfScope("computeLineSearchLbfgsUpdate"); return 0; }
+    real_t computeLineSearchAmeLbfgsUpdate(real_t) { outOfScope("computeLineSearchAmeLbfgsUpdate"); return 0; }
+    real_t computeValueFbe() { outOfScope("computeValueFbe"); return 0; }
+    void updateFixedPointResidualNamaAlgorithm() { outOfScope("updateFixedPointResidualNamaAlgorithm"); }
+    real_t *devVecResidual = nullptr, *devVecGradientFbeXi = nullptr, *devVecGradientFbePsi = nullptr;
+    real_t **devPtrVecHessianOracleXi = nullptr, **devPtrVecHessianOraclePsi = nullptr;
+    real_t *devVecXdir = nullptr, *devVecUdir = nullptr, *devVecPrevXi = nullptr, *devVecPrevPsi = nullptr;
+    real_t *devVecLbfgsDirXi = nullptr, *devVecLbfgsDirPsi = nullptr;
+    real_t **ptrLbfgsCurrentYvecXi = nullptr, **ptrLbfgsCurrentYvecPsi = nullptr, **ptrLbfgsPreviousYvecXi = nullptr,
+           **ptrLbfgsPreviousYvecPsi = nullptr;
+    real_t *devLbfgsBufferMatS = nullptr, *devLbfgsBufferMatY = nullptr, *lbfgsBufferRho = nullptr;
+    uint_t lbfgsBufferCol = 0, lbfgsBufferMemory = 0;
+    real_t lbfgsBufferHessian = 0;
     Forecaster *ptrMyForecaster = nullptr;
     Engine *ptrMyEngine = nullptr;
     SmpcConfiguration *ptrMySmpcConfig = nullptr;
@@ -299,6 +322,8 @@ private:
     void construct();
     void check(rn_status rc, const char *what);
     void step(rn_step_kind kind, real_t lambda, const char *what);
+    [[noreturn]] void outOfScope(const char *what);
+    real_t *proximalSlots[2] = {nullptr, nullptr};
     bool ownsObjects = false;
 };
 

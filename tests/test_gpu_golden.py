@@ -11,8 +11,8 @@ from refcompare import engine_close, smpc_close
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=[cabi.SWEEP_PERSISTENT, cabi.SWEEP_CHAIN, cabi.SWEEP_PER_STAGE],
-                ids=["persistent", "chain", "per_stage"])
+@pytest.fixture(scope="module", params=[cabi.SWEEP_PERSISTENT, cabi.SWEEP_CHAIN, cabi.SWEEP_PER_STAGE, cabi.SWEEP_BATCHED],
+                ids=["persistent", "chain", "per_stage", "batched"])
 def solver(request, toy):
     prob, engine, _ = toy
     s = cabi.Solver(prob)

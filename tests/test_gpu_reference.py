@@ -4,9 +4,10 @@ oracle/build_ref.sh from the unmodified /root/reference/src) on identical JSON i
 north_star parity: "the same primal/dual iterates after a fixed iteration count and the same first-stage control u0
 within a stated fp32 relative tolerance (e.g. 1e-4)".  Two gates per basis-invariant iterate (U, X, y, y_prev, z, Hx, w)
 and for u0, at equal iteration counts (tests/refcompare.py):
-  accuracy   ours is at most twice as far from the double-precision trajectory as the reference build itself is;
+  accuracy   ours is at most three times as far from the double-precision trajectory as the reference build itself is
+             (both are single samples of amplified rounding noise; measured spread in tests/refcompare.py);
   agreement  norm-wise relative 1e-4 against the reference build wherever the reference's own distance from the double
-             trajectory allows it (<= 1e-4 / 3); otherwise three times that distance (what the accuracy gate implies), and
+             trajectory allows it (<= 1e-4 / 4); otherwise four times that distance (what the accuracy gate implies), and
              the case prints "floor-limited".
 V and beta live in the null-space basis chosen by cuSOLVER and are compared only after feeding the
 reference's L back in.  The cases include the bench workloads at their operating point: C2 and C3 at 500 iterations.
@@ -80,7 +81,7 @@ def test_iterates_match_reference_build(case, iters, toy, tmp_path):
         if err > worst[1]:
             worst = (gname, err, floor)
         assert ok, (f"{case} it={iters}: {gname} is {e_ours:.3e} from the double-precision trajectory, the reference build "
-                    f"{e_ref:.3e}: more than twice as far")
+                    f"{e_ref:.3e}: more than ACC_FACTOR times as far")
         assert err < tol, (f"{case} it={iters}: {gname} rel err {err:.3e} vs the reference build "
                            f"(tolerance {tol:.1e}; the reference is {floor:.1e} from the double-precision trajectory)")
     u0_tol, u0_floor = floor_tol(ref["u0"], o64.get("U")[: u0.size])

@@ -9,6 +9,6 @@ HOSTCXX="${HOSTCXX:-/usr/bin/g++}"
 FLAGS=(-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -ccbin "$HOSTCXX"
        -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v --shared
        -I"$ROOT/include")
-"$NVCC" "${FLAGS[@]}" -o "$OUT" "$SRC/rn_api.cu" "$SRC/rn_factor.cu" "$SRC/rn_affine.cu" "$SRC/rn_apg.cu" "$SRC/rn_persist.cu" \
+"$NVCC" "${FLAGS[@]}" -o "$OUT" "$SRC/rn_api.cu" "$SRC/rn_factor.cu" "$SRC/rn_affine.cu" "$SRC/rn_apg.cu" "$SRC/rn_batched.cu" "$SRC/rn_persist.cu" \
     -lcusolver -lcudart "$@"
 echo "built $OUT"

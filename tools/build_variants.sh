@@ -16,7 +16,7 @@ mkdir -p "$ROOT/ab_libs"
 for f in "${FLAGS_ALL[@]}"; do
   out="$ROOT/ab_libs/$(echo "$f" | tr 'A-Z' 'a-z' | sed 's/^rn_exp_//').so"
   "$NVCC" -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -Xcompiler -fPIC --shared \
-      -D"$f" -I"$ROOT/include" -o "$out" "$SRC/rn_api.cu" "$SRC/rn_factor.cu" "$SRC/rn_affine.cu" "$SRC/rn_apg.cu" "$SRC/rn_persist.cu" \
+      -D"$f" -I"$ROOT/include" -o "$out" "$SRC/rn_api.cu" "$SRC/rn_factor.cu" "$SRC/rn_affine.cu" "$SRC/rn_apg.cu" "$SRC/rn_batched.cu" "$SRC/rn_persist.cu" \
       -lcusolver -lcudart
   echo "built $out"
 done
