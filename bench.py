@@ -202,13 +202,13 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def measure_handle(s, prob, iters, steps, warmup, stream, barrier):
+def measure_handle(s, prob, iters, steps, warmup, stream, barrier, min_warmup=3):
     """One factored handle: `steps` cold-started solves with device-resident inputs (CUDA events on the launching stream),
     then the same through rn_control_action with host buffers.  Returns this rank's figures (ms over all steps)."""
     import torch
     c, fc = prob.config, prob.forecast
     with torch.cuda.stream(stream):
-        for _ in range(max(warmup, 3)):
+        for _ in range(max(warmup, min_warmup)):
             s.apg_solve(iters, want_u0=False)
         barrier()
         l0 = s.info().kernel_launches
@@ -223,7 +223,7 @@ def measure_handle(s, prob, iters, steps, warmup, stream, barrier):
         host_in = [np.ascontiguousarray(a, dtype=np.float32) for a in
                    (c.current_x, c.prev_u, c.prev_demand, fc.demand[0], fc.prices[0])]
         u0 = np.zeros(prob.network.nu, dtype=np.float32)
-        for _ in range(2):
+        for _ in range(min(2, min_warmup)):
             s.control_action(*host_in, iters, out=u0)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -249,15 +249,18 @@ def bench_config(name, args, local, stream, barrier, peak):
     s.set_modes({"persistent": cabi.SWEEP_PERSISTENT, "chain": cabi.SWEEP_CHAIN, "per_stage": cabi.SWEEP_PER_STAGE, "batched": cabi.SWEEP_BATCHED}[args.sweep],
                 {"full": cabi.FACTORS_FULL, "df": cabi.FACTORS_DF, "shared": cabi.FACTORS_SHARED}[args.factors])
     s.factor_step(); s.update_state(); s.eliminate_coupling(fc.demand[0], fc.prices[0])
-    big = prob.tree.nodes > 20000
+    info = s.info()
+    big = info.factor_bytes > 4e9            # seconds per solve: fewer repetitions
     steps = max(1, min(args.steps, 2 if big else 5))
-    m = measure_handle(s, prob, args.iters, steps, 1 if big else 3, stream, barrier)
+    m = measure_handle(s, prob, args.iters, steps, 1 if big else 3, stream, barrier, min_warmup=1 if big else 3)
     info = s.info()
     it_s = m["ms_dev"] / steps / args.iters * 1e-3
     out = {"workload": describe(name, prob), "scenarios": int(prob.tree.K), "nodes": int(prob.tree.nodes), "steps": steps,
            "value": steps * args.iters / (m["ms_dev"] * 1e-3), "unit": UNIT, "ms_per_solve": m["ms_dev"] / steps,
            "e2e": {"value": steps * args.iters / (m["ms_e2e"] * 1e-3), "ms_per_solve": m["ms_e2e"] / steps},
            "persistent_kernel": bool(info.launches_per_iteration == 0),
+           "launches_per_iteration": int(info.launches_per_iteration),
+           "path": "k_apg_persistent" if info.launches_per_iteration == 0 else "k_stream + batched sweeps (GEMMs across all nodes) + k_finalize, CUDA graph per iteration",
            "factor_mb": info.factor_bytes / 1e6,
            "roofline": {"bytes_per_iteration": info.apg_bytes_per_iteration,
                         "achieved": info.apg_bytes_per_iteration / it_s / 1e9, "unit": "GB/s",
@@ -346,6 +349,15 @@ def bench_partition(args, rank, world, local, stream, workload):
                              "note": "the same tree solved on ONE GPU of this box in the same run (rank 0)"}}
         ref.close()
     dist.barrier()
+    # phase clock of the partitioned kernel (every rank runs the same solve: the in-kernel barriers span the GPUs)
+    phases, prof = None, None
+    try:
+        with torch.cuda.stream(stream):
+            prof = ds.solver.profile_kernels(min(iters, 100))
+            phases = {k: round(v) for k, v in ds.solver.phase_times().items() if not k.startswith("cyc.")}
+    except Exception as ex:   # noqa: BLE001
+        phases = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+    dist.barrier()
     d = prob.dims
     info = ds.solver.info()
     out = {"workload": describe(workload, prob), "n_gpus": world, "scaling": "strong", "steps": steps,
@@ -358,6 +370,7 @@ def bench_partition(args, rank, world, local, stream, workload):
            "exchange_bytes_per_iteration_per_rank": int(ds.exchange_bytes_per_iteration()),
            "exchange": "in-kernel stores to peer memory (CUDA IPC over NVLink) + flag barriers; no NCCL on the data path",
            "bytes_per_iteration_per_rank": info.apg_bytes_per_iteration,
+           "iteration_ms_by_phase_rank0": prof, "phase_clock_ns_per_iteration_rank0": phases,
            "check_vs_one_gpu": check}
     ds.close()
     return out
@@ -450,7 +463,7 @@ def main():
     ap.add_argument("--ref-max-steps", type=int, default=5, help="--impl reference: most timed solves (seconds each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the legs of the two reformulations (D, F only; shared factors)")
-    ap.add_argument("--by-config", default="C1,C1r6,C1r30,C3,C3b", help="N = 1: other scenario counts measured next to the headline ('' = skip)")
+    ap.add_argument("--by-config", default="C1,C1r6,C1r30,C3,C3b,C5", help="N = 1: other scenario counts measured next to the headline ('' = skip)")
     ap.add_argument("--closed-loop-instances", type=int, default=4, help="closed-loop Monte-Carlo leg: instances PER RANK (0 = skip)")
     ap.add_argument("--closed-loop-lanes", type=int, default=4, help="that leg again with this many handles per GPU side by side (1 = skip)")
     ap.add_argument("--closed-loop-steps", type=int, default=2, help="receding-horizon steps per instance in that leg")

@@ -248,6 +248,11 @@ rn_status rn_apg_solve(rn_handle *h, int iterations, float *u0_host, float *prim
  *   warm_restart != 0: warm start of a closed-loop step: y_0 = y_{-1} = the duals the previous solve left, theta restarts
  *                      at 1 (lambda_host ignored). */
 rn_status rn_apg_continue(rn_handle *h, int iterations, const float *lambda_host, int warm_restart);
+/* Opt-in: from the second solve on, rn_apg_solve / rn_control_action start from the duals the previous solve left (theta
+ * restarted) instead of zeroing them -- for receding-horizon loops, where consecutive problems differ little.  Off by default:
+ * the reference cold-starts every solve (:420-450, :1509) and parity is defined on that.  Persistent sweep only; a factor step
+ * or switching it off drops the stored duals. */
+rn_status rn_set_warm_start(rn_handle *h, int on);
 /* SmpcController::controlAction(real_t* u) (:1607-1625) when clamp == 0;
  * SmpcController::controlAction(fstream&) control vector (:1633-1667) when clamp != 0 (u0 clamped with
  * the node-0 preconditioned bounds).  Host buffers in, u0 (nu floats) out; blocking. */

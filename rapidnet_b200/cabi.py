@@ -41,7 +41,7 @@ EXPORTS = [
     "rn_set_uncertainty", "rn_apg_init", "rn_step", "rn_apg_solve", "rn_control_action", "rn_move_forward",
     "rn_buffer", "rn_read_buffer", "rn_write_buffer", "rn_profile_stream", "rn_profile_kernels", "rn_phase_times", "rn_cta_times",
     "rn_dist_prepare", "rn_dist_connect", "rn_dist_fix_crown_beta", "rn_read_pinf_parts", "rn_dist_error",
-    "rn_set_grid_limit", "rn_apg_continue", "rn_dist_sync_crown_beta", "rn_prepare",
+    "rn_set_grid_limit", "rn_apg_continue", "rn_dist_sync_crown_beta", "rn_prepare", "rn_set_warm_start",
 ]
 
 
@@ -123,6 +123,7 @@ def load():
     lib.rn_dist_error.argtypes = [H, IP]
     lib.rn_dist_sync_crown_beta.argtypes = [H, C.c_int]
     lib.rn_prepare.argtypes = [H]
+    lib.rn_set_warm_start.argtypes = [H, C.c_int]
     for name in EXPORTS:
         if name != "rn_last_error":
             getattr(lib, name).restype = C.c_int
@@ -248,6 +249,10 @@ class Solver:
         self._check(load().rn_apg_solve(self.h, int(iterations), _fp(u0) if want_u0 else None,
                                         _fp(infs) if want_infs else None), "rn_apg_solve")
         return u0, (infs[:iterations] if want_infs else None)
+
+    def set_warm_start(self, on: bool = True):
+        """opt-in: later solves start from the duals of the previous one (the reference cold-starts)"""
+        self._check(load().rn_set_warm_start(self.h, int(bool(on))), "rn_set_warm_start")
 
     def apg_continue(self, iterations: int, lambdas=None, warm_restart=False):
         """Iterations that continue from the duals in place (UPDATE = y_k, XI/PSI = y_{k-1}); `lambdas` replaces the theta

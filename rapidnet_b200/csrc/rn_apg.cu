@@ -927,12 +927,15 @@ static rn_status enqueue_persistent(Handle *h, int iterations) {
     }
     h->launches_per_iter = 0;
     if (iterations & 1) { std::swap(h->upd_xi, h->xi); std::swap(h->upd_psi, h->psi); }
+    if (iterations > 0) h->have_duals = true;
     return RN_OK;
 }
 
 bool use_persistent(const Handle *h) { return h->sweep_mode == RN_SWEEP_PERSISTENT && persistent_supported(h); }
 
 rn_status apg_enqueue(Handle *h, int iterations) {
+    // opt-in warm start (rn_set_warm_start): from the second solve on, start from the duals the previous solve left
+    if (h->warm_start && h->have_duals && iterations > 0 && use_persistent(h)) return apg_warm(h, iterations);
     RN_CHECK(ensure_lambda(h, iterations));
     RN_CHECK(apg_init(h));
     if (use_persistent(h)) return enqueue_persistent(h, iterations);

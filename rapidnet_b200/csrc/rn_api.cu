@@ -271,6 +271,14 @@ rn_status rn_set_grid_limit(rn_handle *hh, int max_ctas) {
     return RN_OK;
 }
 
+rn_status rn_set_warm_start(rn_handle *hh, int on) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return RN_ERR_INVALID;
+    h->warm_start = on != 0;
+    if (!on) h->have_duals = false;
+    return RN_OK;
+}
+
 rn_status rn_get_info(rn_handle *hh, rn_info *info) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (!h || !info) return RN_ERR_INVALID;

@@ -245,7 +245,7 @@ rn_status factor_step(Handle *h) {
     RN_CUDA(h, cudaStreamSynchronize(h->stream));   // host vectors above go out of scope
     h->factored = true;
     h->pack_dirty = true;   // the persistent kernel's copy of G, OmegaBar, L, B, L' (rn_persist.cu: refresh_pack)
-    h->state_set = false; h->eliminated = false;
+    h->state_set = false; h->eliminated = false; h->have_duals = false;
     return RN_OK;
 }
 

@@ -117,6 +117,7 @@ struct Handle {
     unsigned long long *phase_ns = nullptr, *cta_ns = nullptr;
     std::vector<unsigned long long> last_cta_ns;
     bool persist_ready = false;
+    bool warm_start = false, have_duals = false;   // rn_set_warm_start; a solve has left duals to start from
     bool pack_dirty = true;          // the sweep pack must be re-copied from the factor-step outputs before the next launch
     unsigned long long last_phase_ns[32] = {0};
     int last_phase_iters = 0;

@@ -534,27 +534,23 @@ __device__ __noinline__ void tile_gemm(const float *M, int m, int K, const float
 
 
 // The same product for two columns c0, c1 only (a crown tile of one node: the 24-column GEMM would spend 3 us on 1-2
-// useful columns).  Thread = (row r = t & 127, quarter of k = t >> 7); the quarters are summed through scr2 in a fixed
-// order.  All kPC threads call; ends with a CTA barrier.
+// useful columns).  Thread = (row r = t & 127, half of k = (t >> 7) & 1, column = t >> 8); the halves of k are the ones of
+// tile_gemm and are added in the same order, so a crown node gets the same bits whether it is swept alone or inside a wider
+// tile -- the crown is replicated across the GPUs of a partition, and the ranks tile it differently.
+// All kPC threads call; ends with a CTA barrier.
 __device__ __noinline__ void tile_gemv2(const float *M, int m, int K, const float *X, float *Y, float *scr2, int c0, int c1) {
-    const int t = threadIdx.x, r = t & 127, kq = t >> 7;
-    const int kn = (K + 3) >> 2, k0 = kq * kn, k1 = min(K, k0 + kn);
-    float a0 = 0.f, a1 = 0.f;
+    const int t = threadIdx.x, r = t & 127, h = (t >> 7) & 1, c = t >> 8;
+    const int kh = (K + 1) >> 1, k0 = h ? kh : 0, k1 = h ? K : kh;
+    const int col = c ? c1 : c0;
+    float a = 0.f;
     if (r < m) {
-        const float *mp = M + (size_t)k0 * m + r, *x0 = X + c0, *x1 = X + c1;
+        const float *mp = M + (size_t)k0 * m + r, *x = X + col;
 #pragma unroll 4
-        for (int k = k0; k < k1; k++, mp += m) {
-            const float mv = *mp;
-            a0 = fmaf(mv, x0[k * kTP], a0);
-            a1 = fmaf(mv, x1[k * kTP], a1);
-        }
+        for (int k = k0; k < k1; k++, mp += m) a = fmaf(*mp, x[k * kTP], a);
     }
-    scr2[kq * 256 + r] = a0; scr2[kq * 256 + 128 + r] = a1;
+    scr2[h * 256 + c * 128 + r] = a;
     cbar();
-    if (kq == 0 && r < m) {
-        Y[r * kTP + c0] = ((scr2[r] + scr2[256 + r]) + scr2[512 + r]) + scr2[768 + r];
-        Y[r * kTP + c1] = ((scr2[128 + r] + scr2[384 + r]) + scr2[640 + r]) + scr2[896 + r];
-    }
+    if (h == 0 && r < m) Y[r * kTP + col] = scr2[c * 128 + r] + scr2[256 + c * 128 + r];
     cbar();
 }
 

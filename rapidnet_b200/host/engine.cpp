@@ -104,6 +104,7 @@ cublasHandle_t Engine::getCublasHandle() {
 // two objects themselves, Testing.cu:520-524, and would free them twice otherwise).
 Engine::~Engine() {
     if (cublasHandle) cublasDestroy(cublasHandle);
+    if (devMatGCopies) cudaFree(devMatGCopies);
     for (void *p : ownedDevice) cudaFree(p);
     if (h) rn_destroy(h);
 }
@@ -144,7 +145,7 @@ real_t **Engine::ptrTable(PtrTableId id) {
         case PT_SIGMA: per_node(getMatSigma(), nv); break;
         case PT_OMEGA: aliased(getMatOmega(), nv * nv); break;
         case PT_THETA: aliased(getMatTheta(), nx * nv); break;
-        case PT_G: shared(getMatG()); break;
+        case PT_G: per_node(getMatG(), nv * nx); break;
         case PT_SYS_B: shared(getSysMatB()); break;
         case PT_SYS_L: shared(getSysMatL()); break;
         case PT_SYS_LHAT: shared(getSysMatLhat()); break;
@@ -191,7 +192,24 @@ real_t *Engine::buf(rn_buffer_id id) {
 
 // The reference runs on the legacy default stream, so a cudaMemcpy issued by the caller right after any of these
 // methods sees their results; the library's stream is non-blocking, hence the explicit rn_sync.
-void Engine::factorStep() { check(rn_factor_step(h), "Engine::factorStep"); check(rn_sync(h), "rn_sync"); }
+void Engine::factorStep() {
+    check(rn_factor_step(h), "Engine::factorStep");
+    check(rn_sync(h), "rn_sync");
+    if (devMatGCopies) { cudaFree(devMatGCopies); devMatGCopies = nullptr; }   // G follows the null-space basis
+    devPtrTables[PT_G] = nullptr;
+}
+
+// The library keeps ONE G = Bbar' (every scenario's copy is the same matrix, Engine.cu:736-747); callers of the reference index
+// devMatG by scenario (its tests read copy `node - 1`, Testing.cu:437-440), so the getter hands out K copies, built on request.
+real_t *Engine::getMatG() {
+    if (devMatGCopies) return devMatGCopies;
+    const size_t K = ptrMyScenarioTree->getNumScenarios(), sz = (size_t)ptrMySmpcConfig->getNV() * ptrMySmpcConfig->getNX();
+    real_t *one = buf(RN_BUF_MAT_G);
+    if (cudaMalloc(&devMatGCopies, K * sz * sizeof(real_t)) != cudaSuccess) { std::cerr << "rapidnet_b200: Engine::getMatG: out of device memory" << std::endl; std::exit(EXIT_FAILURE); }
+    for (size_t k = 0; k < K; k++)
+        if (cudaMemcpy(devMatGCopies + k * sz, one, sz * sizeof(real_t), cudaMemcpyDeviceToDevice) != cudaSuccess) { std::cerr << "rapidnet_b200: Engine::getMatG: copy failed" << std::endl; std::exit(EXIT_FAILURE); }
+    return devMatGCopies;
+}
 
 void Engine::updateStateControl(real_t *currentX, real_t *prevU, real_t *prevDemand) {
     check(rn_update_state(h, currentX, prevU, prevDemand), "Engine::updateStateControl");

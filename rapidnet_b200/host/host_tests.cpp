@@ -280,7 +280,7 @@ int TestSmpcController::testSurface() {
         T_ASSERT(sb[i] == e->getSysMatB() && sl[i] == e->getSysMatL() && slh[i] == e->getSysMatLhat());
         T_ASSERT(sf[i] == e->getSysMatF() + i * 2 * nx * nx && sgg[i] == e->getSysMatG() + i * nu * nu);
     }
-    for (size_t k = 0; k < K; k++) T_ASSERT(g[k] == e->getMatG());
+    for (size_t k = 0; k < K; k++) T_ASSERT(g[k] == e->getMatG() + k * nv * nx);   // one copy per scenario, like the reference
     for (size_t s = 0; s < N; s++)
         for (size_t j = 0; j < (size_t)tree->getNodesPerStage()[s]; j++) {
             const size_t c0 = tree->getNodesPerStageCumul()[s], cur = fb <= c0 ? fb - K + j : c0 + j;   // Engine.cu:210-221
@@ -345,6 +345,8 @@ static int closed_loop(const std::string &cfgPath, int steps, const std::string 
         ctl->moveForewardInTime();
         out << (t ? ", " : "") << "{\"ms\": " << ms << ", \"u0\": [";
         for (uint_t i = 0; i < nu; i++) out << (i ? ", " : "") << u[i];
+        out << "], \"u_applied\": [";
+        for (uint_t i = 0; i < nu; i++) out << (i ? ", " : "") << ctl->getSmpcConfiguration()->getPrevU()[i];
         out << "], \"x_next\": [";
         for (uint_t i = 0; i < nx; i++) out << (i ? ", " : "") << ctl->getSmpcConfiguration()->getCurrentX()[i];
         out << "]}";

@@ -13,8 +13,27 @@
 #include <iostream>
 #include <stdexcept>
 
+// rapidjson is header-only: its inline template members would otherwise be exported from this library and interposed by the
+// copies of a program compiled against ANOTHER rapidjson release (the reference vendors v1.1) -- different layouts, a crash
+// (the system headers rapidjson pulls in come first, so that only rapidjson's own declarations are hidden)
+#include <cassert>
+#include <cinttypes>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <iterator>
+#include <limits>
+#include <memory>
+#include <new>
+#include <utility>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#pragma GCC visibility push(hidden)
 #include "rapidjson/document.h"
 #include "rapidjson/filereadstream.h"
+#pragma GCC visibility pop
 
 #include "rapidnet_host.hpp"
 

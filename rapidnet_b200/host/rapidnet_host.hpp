@@ -172,7 +172,7 @@ public:
     real_t *getMatSigma() { return buf(RN_BUF_MAT_SIGMA); }
     real_t *getMatD() { return buf(RN_BUF_MAT_D); }
     real_t *getMatF() { return buf(RN_BUF_MAT_F); }
-    real_t *getMatG() { return buf(RN_BUF_MAT_G); }
+    real_t *getMatG();   // K identical copies of G = Bbar', as the reference lays it out (Engine.cu:173, 204-207: one per scenario)
     real_t *getVecUhat() { return buf(RN_BUF_VEC_UHAT); }
     real_t *getVecBeta() { return buf(RN_BUF_VEC_BETA); }
     real_t *getVecE() { return buf(RN_BUF_VEC_E); }
@@ -231,6 +231,7 @@ private:
     uint_t *treeU(int which);
     real_t *treeF(int which);
     void *toDevice(const void *host, size_t bytes);
+    real_t *devMatGCopies = nullptr;   // getMatG(): rebuilt after every factor step
     real_t **devPtrTables[PT_COUNT_] = {};
     uint_t *devTreeU[7] = {};
     real_t *devTreeF[3] = {};

@@ -122,6 +122,30 @@ def test_shim_headers_carry_the_reference_names():
         assert f'#define {macro} "{key}"' in keys
 
 
+def _shim_data(toy, tmp_path):
+    prob, engine, smpc = toy
+    data = tmp_path / "test" / "testDataFiles"
+    data.mkdir(parents=True)
+    (tmp_path / "Debug").mkdir()
+    write_problem(prob, str(data))
+    _golden_json(data / "engineTest.json", engine)
+    _golden_json(data / "smpcTest.json", smpc)
+    return str(tmp_path / "Debug")
+
+
+@pytest.mark.skipif(not os.path.exists(SHIM), reason="oracle/_ref/ref_shim_tests not built (needs /root/reference at build time)")
+def test_reference_loader_tests_pass_against_the_facade_cpu(toy, tmp_path):
+    """No GPU needed for the first four tests of the reference's main(): its own testNetwork, testScenarioTree, testForecaster
+    and testControllerConfig (unchanged sources) pass against the facade's loaders; without a device the run then stops at
+    Engine construction with the library's 'no CUDA device' error (exit 1, no CPU fallback)."""
+    out = subprocess.run([SHIM], cwd=_shim_data(toy, tmp_path), capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, RAPIDNET_NULL_SPACE="config"))
+    for line in ("Completed testing of the DWN network", "Completed testing of the scenario tree", "Completed testing of the Forecaster",
+                 "Completed testing the SmpcConfiguration"):
+        assert line in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
+    assert out.returncode == 0 or "no CUDA device" in out.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(SHIM), reason="oracle/_ref/ref_shim_tests not built (needs /root/reference at build time)")
 def test_reference_test_sources_pass_against_the_facade(toy, tmp_path):
@@ -130,14 +154,7 @@ def test_reference_test_sources_pass_against_the_facade(toy, tmp_path):
     the reference's main(): the four loader tests, testEngineTesting and testSmpcController (extrapolation, solve step,
     prox, residual, dual update against the reference's golden vectors at the reference's tolerances).  The binary opens
     ../test/testDataFiles/*.json like the reference does; the files are re-created here from tests/golden/toy.npz."""
-    prob, engine, smpc = toy
-    data = tmp_path / "test" / "testDataFiles"
-    data.mkdir(parents=True)
-    (tmp_path / "Debug").mkdir()
-    write_problem(prob, str(data))
-    _golden_json(data / "engineTest.json", engine)
-    _golden_json(data / "smpcTest.json", smpc)
-    out = subprocess.run([SHIM], cwd=str(tmp_path / "Debug"), capture_output=True, text=True, timeout=600,
+    out = subprocess.run([SHIM], cwd=_shim_data(toy, tmp_path), capture_output=True, text=True, timeout=600,
                          env=dict(os.environ, RAPIDNET_NULL_SPACE="config"))
     assert out.returncode == 0 and "tests pass against rapidnet-b200" in out.stdout, (out.stdout[-2500:], out.stderr[-1500:])
 
@@ -178,6 +195,38 @@ def test_closed_loop_matches_ctypes_path(tmp_path, factors):
         x, up, dp = xn, ua, fc.demand[t][: prob.network.nd].astype(np.float32)
     assert np.isfinite(res["economic_kpi"]) and res["steps"][0]["ms"] > 0
     s.close()
+
+
+REF_LOOP = os.path.join(ROOT, "oracle", "_ref", "ref_loop")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF_LOOP), reason="oracle/_ref/ref_loop not built (needs /root/reference at build time)")
+def test_closed_loop_and_kpis_match_reference_build(tmp_path):
+    """The reference's own closed loop (oracle/ref_loop.cu = src/main.cu:27-63 on the unmodified sources: controlAction(fstream&),
+    moveForewardInTime, the four KPIs of SmpcController.cu:1778-1859) against the same loop through the facade, on identical
+    JSON inputs: applied controls and next states per step within the fp32 agreement of 200-iteration solves (norm-wise
+    2e-4), KPIs within 1e-3 relative."""
+    from rapidnet_b200.datagen import named_problem
+    steps, iters = 3, 200
+    cfg = write_problem(named_problem("C1r6", max_iter=iters), str(tmp_path))
+    ref_out, our_out = tmp_path / "ref.json", tmp_path / "ours.json"
+    r = subprocess.run([REF_LOOP, cfg, str(steps), str(ref_out)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    _run("closedloop", cfg, steps, our_out)
+    ref, ours = json.load(open(ref_out)), json.load(open(our_out))
+
+    def rel(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+    for t in range(steps):
+        eu, ex = rel(ours["steps"][t]["u_applied"], ref["steps"][t]["u_applied"]), rel(ours["steps"][t]["x_next"], ref["steps"][t]["x_next"])
+        print(f"closed-loop step {t}: u_applied {eu:.2e}, x_next {ex:.2e}")
+        assert eu < 2e-4 and ex < 2e-4, (t, eu, ex)
+    for k in ("economic_kpi", "smooth_kpi", "safety_kpi", "network_kpi"):
+        print(k, ours[k], ref[k])
+        assert abs(ours[k] - ref[k]) <= 1e-3 * max(abs(ref[k]), 1e-12), (k, ours[k], ref[k])
 
 
 @pytest.mark.gpu

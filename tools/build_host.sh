@@ -14,7 +14,9 @@ for d in "$RJ" "$SITE/tilelang/3rdparty/composable_kernel/include" /usr/include 
 done
 if [ -z "$RJ" ] || [ ! -f "$RJ/rapidjson/document.h" ]; then echo "build_host: no rapidjson headers found (set RAPIDJSON_INCLUDE)"; exit 1; fi
 FLAGS=(-std=c++17 -O2 -fPIC -Wall -Wno-class-memaccess -I"$ROOT/include" -isystem "$RJ" -I"$CUDA/include")
-"$CXX" "${FLAGS[@]}" -shared -o "$SRC/librapidnet_host.so" "$SRC/loaders.cpp" "$SRC/engine.cpp" \
+# hidden inlines + hidden rapidjson (loaders.cpp): the library keeps ITS rapidjson (header-only, inline templates) even when the program
+# that loads it was compiled against another rapidjson release (the reference vendors v1.1; interposed inline symbols would crash)
+"$CXX" "${FLAGS[@]}" -fvisibility-inlines-hidden -shared -o "$SRC/librapidnet_host.so" "$SRC/loaders.cpp" "$SRC/engine.cpp" \
     -L"$ROOT/rapidnet_b200" -lrapidnet_b200 -L"$CUDA/lib64" -lcublas -lcudart -Wl,-rpath,'$ORIGIN/..'
 "$CXX" "${FLAGS[@]}" -o "$SRC/host_tests" "$SRC/host_tests.cpp" -L"$SRC" -lrapidnet_host -L"$ROOT/rapidnet_b200" -lrapidnet_b200 \
     -L"$CUDA/lib64" -lcudart -pthread -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/..'

@@ -10,7 +10,7 @@ set -euo pipefail
 ROOT="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 SRC="$ROOT/rapidnet_b200/csrc"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-FLAGS_ALL=(RN_EXP_GEMM_4X12 RN_EXP_GEMM_FFMA2 RN_EXP_RANGESUM16)
+FLAGS_ALL=()
 if [ $# -gt 0 ]; then FLAGS_ALL=("$@"); fi
 mkdir -p "$ROOT/ab_libs"
 for f in "${FLAGS_ALL[@]}"; do

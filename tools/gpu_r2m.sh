@@ -30,6 +30,7 @@ try:
     print("HEAD", d["n_gpus"], "gpus", d["scaling"], round(d["value"]), "iter/s  e2e", round(d["e2e"]["value"]), "frac", round(d["roofline"]["frac"],3))
     print("  partition", {k:p.get(k) for k in ("value","ms_per_solve","exchange_bytes_per_iteration_per_rank","nodes_per_rank","error")})
     print("  check", p.get("check_vs_one_gpu"))
+    print("  phases", p.get("iteration_ms_by_phase_rank0"), p.get("phase_clock_ns_per_iteration_rank0"))
     x=d.get("tree_partition_extra")
     if x: print("  extra", {k:x.get(k) for k in ("workload","value","ms_per_solve","error")}, x.get("check_vs_one_gpu"))
     r=d.get("replicas",{})
