@@ -354,7 +354,9 @@ rn_status rn_apg_init(rn_handle *hh) {
 rn_status rn_step(rn_handle *hh, rn_step_kind kind, float lambda) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     if (!h) return RN_ERR_INVALID;
-    if (!h->factored) return rn::fail(h, RN_ERR_STATE, "rn_step before rn_factor_step");
+    // extrapolation, residual and dual update only touch the dual vectors (the reference's tests run the extrapolation on a
+    // controller that has not been factored yet, TestSmpcController.cu:114-165); the solve step and the prox need the factor step
+    if (!h->factored && (kind == RN_STEP_SOLVE || kind == RN_STEP_PROX)) return rn::fail(h, RN_ERR_STATE, "rn_step before rn_factor_step");
     if (kind == RN_STEP_SOLVE && !h->eliminated) return rn::fail(h, RN_ERR_STATE, "solve step before rn_eliminate_coupling");
     RN_CUDA(h, cudaSetDevice(h->device));
     return rn::apg_step(h, kind, lambda);

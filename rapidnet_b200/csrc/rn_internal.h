@@ -107,6 +107,7 @@ struct Handle {
     void *xchg_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool xchg_opened[8] = {false, false, false, false, false, false, false, false};
     unsigned int xepoch = 0;
+    unsigned int s_total = 0;                      // S rows every rank's table has received in all launches so far (the in-kernel counter's base)
     float *pinf4 = nullptr;
     float *bat_y = nullptr, *bat_y3 = nullptr, *bat_x = nullptr;   // RN_SWEEP_BATCHED scratch: GEMM outputs, X = -1/2 (sigma + G q_bar)
     float *head_q = nullptr, *head_r = nullptr;    // q / r of this rank's chain heads (persistent kernel)

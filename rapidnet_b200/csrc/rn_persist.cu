@@ -93,8 +93,11 @@ struct PArgs {
     // table, indexed by crown node id: [n_crown*nx], [n_crown*nv].  solveSumChildren (Utilities.cu:168-201) one level up.
     float *Sq_peer[kMaxRanks], *Sr_peer[kMaxRanks];
     unsigned int *par_ctr;                      // [n_crown] local: chains of a bottom-crown node whose head q, r are in hq / hr (cumulative)
-    unsigned int *s_ctr;                        // local, one GPU: bottom-crown nodes whose S row is published (cumulative)
+    unsigned int *s_ctr_peer[kMaxRanks];        // on every rank: bottom-crown nodes whose S row has arrived there (cumulative over launches);
+                                                // the owner of a row bumps every rank's counter after storing the row (NVLink atomics)
+    unsigned int s_base;                        // value of the counters when this launch starts
     int bottom0, n_bottom, n_owned, own_lo;     // bottom-crown nodes: first id, count; those with their chains on this rank: count, first id (contiguous)
+    int n_bottom_active;                        // bottom-crown nodes that have chains on SOME rank (= rows every S table receives per iteration)
     double *dslot_peer[kMaxRanks];              // [kMaxRanks][2] squared prox distances of each rank, on each rank
     unsigned int *xflag_peer[kMaxRanks];        // [kMaxRanks] arrival epochs, on each rank
     int *xerr;                                  // local: set when a cross-GPU wait timed out
@@ -158,7 +161,7 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
 // Every grid barrier of the launch has a fixed ordinal (iteration x barriers per iteration + position), so its arrival
 // count is known without per-thread state and any thread can be the one that arrives and polls.
 __device__ __forceinline__ unsigned int bar_count(const PArgs &P, int it, int pos) {
-    const int per_it = (P.n_crown > 0 ? 3 : 2) + (P.n_ranks > 1 && P.n_crown > 0 ? 1 : 0);
+    const int per_it = P.n_crown > 0 ? 3 : 2;
     return (unsigned)(it * per_it + pos + 1) * gridDim.x;
 }
 __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
@@ -188,7 +191,10 @@ __device__ __forceinline__ void wait_sys(const unsigned int *p, unsigned int wan
 // peer's signal, then releases the local CTAs.  Peer data written by any thread of this GPU before the barrier is
 // ordered before the signal by the CTA barriers + the system-scope fence (cumulativity), like cooperative_groups'
 // grid sync does at device scope.
-__device__ __noinline__ void grid_sync_cross(const PArgs &P, unsigned int target, unsigned int ep, int publish_it) {
+// The barrier comes in two halves so that work that needs no other CTA can sit between them: `cross_arrive` (CTA barrier, this
+// CTA's arrival, and on CTA 0 the wait for the local arrivals + the signal to the peers) and `cross_wait` (poll the peers'
+// flags, CTA barrier).
+__device__ __noinline__ void cross_arrive(const PArgs &P, unsigned int target, unsigned int ep, int publish_it) {
     cbar();
     if (threadIdx.x < 32) {   // one warp; lane r talks to peer r
         const int lane = threadIdx.x;
@@ -208,14 +214,17 @@ __device__ __noinline__ void grid_sync_cross(const PArgs &P, unsigned int target
             __threadfence_system();   // lane 0's acquire of the local arrivals + every lane's own stores, before its flag store
             if (lane < P.n_ranks) st_release_sys_u32(P.xflag_peer[lane] + P.rank, ep);
         }
+    }
+}
+__device__ __noinline__ void cross_wait(const PArgs &P, unsigned int ep) {
+    if (threadIdx.x < 32) {
         // every CTA polls the arrival flags itself (they live in this GPU's memory): no second hop through a release word
-        if (lane < P.n_ranks) wait_sys(P.xflag_peer[P.rank] + lane, ep, P.xerr);
+        if ((int)threadIdx.x < P.n_ranks) wait_sys(P.xflag_peer[P.rank] + threadIdx.x, ep, P.xerr);
         __syncwarp();
         __threadfence();
     }
     cbar();
 }
-
 // shared-memory layout (float offsets from the dynamic shared-memory base).  The small persistent area comes first;
 // the phase-S region and the sweep region (runtime offsets in PArgs, they depend on nx/nu/nv) overlay each other
 // behind it.  Phase-S offsets are compile-time constants so that every access there is an LDS/STS with an immediate
@@ -226,7 +235,8 @@ constexpr int kOffCsh = kOffDsh + 2 * 2 * (kPC / 32);                   // 2 x 1
 constexpr int kOffSd = kOffCsh + 3 * 2 * (kPC / 32);                    // d1, d2
 constexpr int kOffMisc = kOffSd + 4;                                    // 4 x kTP words: column -> row / node maps etc.
 constexpr int kOffMeta = kOffMisc + 4 * kTP;                             // 64 words: column maps of this CTA's first chain (cache)
-constexpr int kOffFix = kOffMeta + 64;                                  // u_prev | uhat_prev | x_cur, kVStride floats each (per launch)
+constexpr int kOffSegs = kOffMeta + 64;                                 // 64 words: row ranges of the crown node being summed (CrownSegs)
+constexpr int kOffFix = kOffSegs + 64;                                  // u_prev | uhat_prev | x_cur, kVStride floats each (per launch)
 constexpr int kOffClk = (kOffFix + 3 * kVStride + 1) & ~1;                   // 34 x u64: phase clock accumulators, t_prev, enabled
 constexpr int kOffPArgs = kOffClk + 2 * 34;                            // a copy of the kernel arguments (see k_apg_persistent)
 constexpr int kPArgsWords = 288;
@@ -883,43 +893,52 @@ __device__ __noinline__ void chain_forward(const PArgs &P, int j, int next_chain
 //   QS_i    = sum_{crown j below i} q_bar_j = sum_{crown j below i} (s_j - s_i - 1) c_j + (cs - 1 - s_i) sum_{heads} q_h
 // (the descendants of a node are one contiguous id range per stage: children are contiguous, Utilities.cu:184-199).
 // X1 q-rows: columns 0..n-1 = QS_i, columns 12..12+n-1 = q_bar_i (one G GEMM gives both products); V rows = base_i
-// Sums over the rows [lo, hi) of chain-major arrays, as float4 columns.  The CTA is 8 row groups of two warps: the even warp of
-// a pair adds rows of A (row length ldA: c or S_q), the odd warp rows of B0 (+ B1 + B2: beta + D xi + F psi, or S_r); lane =
-// float4 column.  Group g takes rows lo + g, lo + g + 8, ...; kRows of them in flight per trip, added in ascending order.
-// acc += sum, accw += w * sum (even warps only; w = how many times the rows count in QS).
+// Sums over rows of chain-major arrays, as float4 columns, for ONE crown node: all row ranges that enter the node's sums --
+// its crown descendants stage by stage, then the S rows of the bottom-crown nodes below it -- form one virtual row list, so that
+// every load of the node is in flight together (a call per range cost a round trip to L2 each).  The CTA is 8 row groups of two
+// warps: the even warp of a pair adds rows of c / S_q (row length nxp), the odd warp rows of beta + D xi + F psi / S_r (nvp);
+// lane = float4 column.  Group g takes virtual rows g, g + 8, ...; kRows of them in flight per trip, added in ascending order.
+// acc += row, accw += w(range) * row (even warps: w = how many times the range counts in QS).
 struct F4 { float x, y, z, w; };
-__device__ __forceinline__ void f4_add(F4 &a, const float4 &v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
-__device__ __noinline__ void range_sum(const float *__restrict__ A, int ldA, int dimA, const float *__restrict__ B0, const float *__restrict__ B1,
-                                       const float *__restrict__ B2, int ldB, int dimB, bool three, int lo, int hi, float w, F4 &acc, F4 &accw) {
+struct CrownSegs { int n, start[kMaxCs + 2], lo[kMaxCs + 1]; float w[kMaxCs + 1]; };   // in shared memory; the last range is the S rows
+__device__ __noinline__ void crown_row_sums(const PArgs &P, const CrownSegs &G, F4 &acc, F4 &accw) {
     const int t = threadIdx.x, g = t >> 6, role = (t >> 5) & 1, c4 = t & 31;
     constexpr int kRows = 8;
-    const bool active = 4 * c4 < (role ? dimB : dimA);
-    if (!active) return;
-    const float *base = (role ? B0 : A) + 4 * c4;
-    const int ld = role ? ldB : ldA;
-    const ptrdiff_t d1 = B1 - B0, d2 = B2 - B0;
-    F4 sum{0.f, 0.f, 0.f, 0.f};
+    const int dim = role ? P.nv : P.nx, ld = role ? P.nvp : P.nxp;
+    if (4 * c4 >= dim) return;
+    const float *crown0 = (role ? P.cm_beta : P.cm_c) + 4 * c4, *s0 = (role ? P.Sr_peer[P.rank] : P.Sq_peer[P.rank]) + 4 * c4;
+    const ptrdiff_t d1 = P.part[0] - P.cm_beta, d2 = P.part[1] - P.cm_beta;
+    const int nseg = G.n, total = G.start[nseg];
+    F4 sum{0.f, 0.f, 0.f, 0.f}, sumw{0.f, 0.f, 0.f, 0.f};
+    int j = 0;
 #pragma unroll 1
-    for (int jn = lo + g; jn < hi; jn += 8 * kRows) {
+    for (int v0 = g; v0 < total; v0 += 8 * kRows) {
         float4 v[kRows];
+        float wv[kRows];
 #pragma unroll
         for (int k = 0; k < kRows; k++) {
-            const int r = jn + 8 * k;
-            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < hi) {
-                const float *q = base + (size_t)r * ld;
+            const int vi = v0 + 8 * k;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f); wv[k] = 0.f;
+            if (vi < total) {
+                while (vi >= G.start[j + 1]) j++;
+                const bool is_s = j == nseg - 1;
+                const float *q = (is_s ? s0 : crown0) + (size_t)(G.lo[j] + vi - G.start[j]) * ld;
                 v[k] = __ldcg(reinterpret_cast<const float4 *>(q));
-                if (role && three) {
+                wv[k] = G.w[j];
+                if (role && !is_s) {
                     const float4 b1 = __ldcg(reinterpret_cast<const float4 *>(q + d1)), b2 = __ldcg(reinterpret_cast<const float4 *>(q + d2));
                     v[k].x = (v[k].x + b1.x) + b2.x; v[k].y = (v[k].y + b1.y) + b2.y; v[k].z = (v[k].z + b1.z) + b2.z; v[k].w = (v[k].w + b1.w) + b2.w;
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < kRows; k++) f4_add(sum, v[k]);
+        for (int k = 0; k < kRows; k++) {
+            sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w;
+            sumw.x = fmaf(wv[k], v[k].x, sumw.x); sumw.y = fmaf(wv[k], v[k].y, sumw.y);
+            sumw.z = fmaf(wv[k], v[k].z, sumw.z); sumw.w = fmaf(wv[k], v[k].w, sumw.w);
+        }
     }
-    acc.x += sum.x; acc.y += sum.y; acc.z += sum.z; acc.w += sum.w;
-    if (!role) { accw.x += w * sum.x; accw.y += w * sum.y; accw.z += w * sum.z; accw.w += w * sum.w; }
+    acc = sum; accw = sumw;
 }
 
 // S_p of bottom-crown node p (stage cs-1): q and r of its chain heads added in ascending child order -- what
@@ -951,41 +970,52 @@ __device__ __noinline__ void parent_sum(const PArgs &P, int p, int it) {
         for (int r = 0; r < P.n_ranks; r++) (isq ? P.Sq_peer[r] : P.Sr_peer[r])[o] = acc;
     }
     cbar();
-    if (t == 0 && P.n_ranks == 1) { __threadfence(); atomicAdd(P.s_ctr, 1u); }   // several GPUs: the barrier across them follows
+    if (t < P.n_ranks) {   // the row is in every rank's table: say so on every rank (lane r -> rank r; a peer's counter over NVLink)
+        __threadfence_system();
+        if (P.n_ranks == 1) atomicAdd(P.s_ctr_peer[0], 1u);
+        else atomicAdd_system(P.s_ctr_peer[t], 1u);
+    }
 }
 
-// `wait_s`: single GPU -- the S rows of the bottom-crown nodes are awaited here (a counter parent_sum bumps), after the
-// first column's sums over its crown descendants, so that the crown overlaps the chains' backward sweep
-__device__ __noinline__ void crown_sums(const PArgs &P, int ncols, unsigned int wait_s, uint32_t mpar) {
+// `do_wait`: the S rows of ALL bottom-crown nodes -- this rank's and the peers' -- are awaited here (a counter every parent_sum
+// bumps on every rank): no barrier across the grid or the GPUs stands between the chains and the crown, which overlaps the rest
+// of the chains' backward sweep
+__device__ __noinline__ void crown_sums(const PArgs &P, int ncols, bool do_wait, unsigned int wait_s, uint32_t mpar) {
     const SweepSmem S = sweep_smem(P);
-    const int t = threadIdx.x, g = t >> 6, role = (t >> 5) & 1, c4 = t & 31, nx = P.nx, nv = P.nv, cs = P.cs, nxp = P.nxp, nvp = P.nvp;
+    const int t = threadIdx.x, g = t >> 6, role = (t >> 5) & 1, c4 = t & 31, nx = P.nx, nv = P.nv, cs = P.cs, nvp = P.nvp;
     static_assert(8 * 3 * 128 <= 128 * kTP, "partial sums of the row groups fit the split-K scratch");
+    static_assert(sizeof(CrownSegs) <= 64 * 4, "the range table fits the metadata words behind the chain cache");
+    CrownSegs &G = *reinterpret_cast<CrownSegs *>(smem_f(kOffSegs));
+    if (do_wait) {
+        // while the chains are still scanning: run the GEMM once on whatever X1 holds (two k-steps, result overwritten
+        // later) -- it pulls tile_gemm's code into the instruction cache, which is cold at this point of every iteration
+        mbar_wait(&S.mfull[0], mpar);
+        if (ncols == 1) tile_gemv2(S.G, nv, 4, S.X1, S.Y, S.scr2, 0, 12);
+        else tile_gemm(S.G, nv, 2, S.X1, S.Y, S.scr2);
+        if (t == 0) {
+            if (P.n_ranks == 1) { while ((int)(ld_acquire_u32(P.s_ctr_peer[0]) - wait_s) < 0) {} }
+            else wait_sys(P.s_ctr_peer[P.rank], wait_s, P.xerr);
+            __threadfence();
+        }
+        cbar();
+    }
 #pragma unroll 1
     for (int col = 0; col < ncols; col++) {
         const int i = S.colid[col], si = __ldg(P.stages + i);
-        const int *rng = P.crown_rng + (size_t)i * (kMaxCs + 1) * 2;
-        F4 acc{0.f, 0.f, 0.f, 0.f}, accw{0.f, 0.f, 0.f, 0.f};   // even warps: q_bar, QS; odd warps: sums of beta + D xi + F psi and of r
-#pragma unroll 1
-        for (int s = si + 1; s < cs; s++)
-            range_sum(P.cm_c, nxp, nx, P.cm_beta, P.part[0], P.part[1], nvp, nv, true, __ldg(rng + 2 * s), __ldg(rng + 2 * s + 1),
-                      (float)(s - si - 1), acc, accw);
-        if (col == 0 && wait_s) {
-            // while the chains are still scanning: run the GEMM once on whatever X1 holds (two k-steps, result overwritten
-            // later) -- it pulls tile_gemm's code into the instruction cache, which is cold at this point of every iteration
-            mbar_wait(&S.mfull[0], mpar);
-            if (ncols == 1) tile_gemv2(S.G, nv, 4, S.X1, S.Y, S.scr2, 0, 12);
-            else tile_gemm(S.G, nv, 2, S.X1, S.Y, S.scr2);
-            if (t == 0) {
-                while ((int)(ld_acquire_u32(P.s_ctr) - wait_s) < 0) {}
-                __threadfence();
+        if (t == 0) {   // the node's row ranges: crown descendants of stages si+1 .. cs-1, then the S rows below it (i itself if bottom)
+            const int *rng = P.crown_rng + (size_t)i * (kMaxCs + 1) * 2;
+            int n = 0, at = 0;
+            for (int s = si + 1; s < cs; s++) {
+                const int lo = __ldg(rng + 2 * s), hi = __ldg(rng + 2 * s + 1);
+                G.start[n] = at; G.lo[n] = lo; G.w[n] = (float)(s - si - 1); at += hi - lo; n++;
             }
-            cbar();
-        }
-        {
-            // the heads below i, through the S rows of the bottom-crown nodes below i (i itself when it is one)
             const int blo = si == cs - 1 ? i : __ldg(rng + 2 * (cs - 1)), bhi = si == cs - 1 ? i + 1 : __ldg(rng + 2 * (cs - 1) + 1);
-            range_sum(P.Sq_peer[P.rank], nxp, nx, P.Sr_peer[P.rank], nullptr, nullptr, nvp, nv, false, blo, bhi, (float)(cs - 1 - si), acc, accw);
+            G.start[n] = at; G.lo[n] = blo; G.w[n] = (float)(cs - 1 - si); at += bhi - blo; n++;
+            G.start[n] = at; G.n = n;
         }
+        cbar();
+        F4 acc{0.f, 0.f, 0.f, 0.f}, accw{0.f, 0.f, 0.f, 0.f};   // even warps: q_bar, QS; odd warps: sums of beta + D xi + F psi and of r
+        crown_row_sums(P, G, acc, accw);
         {
             float *sc = S.scr2 + (g * 3 + (role ? 2 : 0)) * 128 + 4 * c4;
             *reinterpret_cast<float4 *>(sc) = make_float4(acc.x, acc.y, acc.z, acc.w);
@@ -1037,7 +1067,8 @@ __device__ __noinline__ void crown_sigma(const PArgs &P, int ncols) {
 __device__ __forceinline__ int crown_pass2_id(const PArgs &P, int k) { return k < P.own_lo ? k : k + P.n_owned; }
 
 // `mapped`: columns are entries i0 .. i0 + ncols - 1 of the second-pass order; otherwise node ids
-__device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, uint32_t mpar, StagePhase &ph, unsigned int wait_heads, bool mapped) {
+__device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, uint32_t mpar, StagePhase &ph, bool do_wait, unsigned int wait_s,
+                                            bool mapped) {
     const SweepSmem S = sweep_smem(P);
     const int t = threadIdx.x;
     if (t < kTP) {
@@ -1046,7 +1077,7 @@ __device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, u
         S.colp[t] = t < ncols ? 1.f / __ldg(P.prob + __ldg(P.omega_idx + node)) : 1.f;
     }
     cbar();
-    crown_sums(P, ncols, wait_heads, mpar);
+    crown_sums(P, ncols, do_wait, wait_s, mpar);
     dstamp(P, 11);
     mbar_wait(&S.mfull[0], mpar);
     if (ncols == 1) tile_gemv2(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2, 0, 12);
@@ -1833,19 +1864,18 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
             const int p = P.bottom0 + q - C.n_tiles2;
             if (__ldg(P.child_count + p) > 0) {
                 parent_sum(P, p, it);
-                crown_backward(P, p, 1, mpar, K.SP, 0u, false);
+                crown_backward(P, p, 1, mpar, K.SP, false, 0u, false);
             }
         }
-        // Pass 2 -- everything else of the crown needs every S row: with several GPUs they were stored into every rank's table
-        // and this barrier spans the GPUs; on one GPU only the CTAs that own tiles wait, for a counter parent_sum bumps, so
-        // the crown overlaps the rest of the chains' backward sweep
-        if (P.n_ranks > 1) grid_sync_cross(P, bar_count(P, it, 1), P.epoch0 + 2u * (unsigned)it + 1u, -1);
-        unsigned int wait_s = P.n_ranks > 1 ? 0u : (unsigned)P.n_owned * (unsigned)(it + 1);   // counter value once every S row is in
+        // Pass 2 -- everything else of the crown needs every S row, this rank's and the peers': the CTAs that own tiles wait for
+        // the counter parent_sum bumps on every rank; nobody else waits, and the crown overlaps the rest of the chains' sweep
+        const unsigned int wait_s = P.s_base + (unsigned)P.n_bottom_active * (unsigned)(it + 1);   // counter value once every S row is in
         dstamp(P, 20);
+        bool do_wait = true;
 #pragma unroll 1
         for (int tl = slot; tl < C.n_tiles2; tl += grid) {
-            crown_backward(P, tl * C.tile_w, min(C.tile_w, C.n2 - tl * C.tile_w), mpar, K.SP, wait_s, true);
-            wait_s = 0u;   // awaited once
+            crown_backward(P, tl * C.tile_w, min(C.tile_w, C.n2 - tl * C.tile_w), mpar, K.SP, do_wait, wait_s, true);
+            do_wait = false;   // awaited once
         }
         dstamp(P, 21);
     }
@@ -1858,7 +1888,7 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
             atomicAdd(P.bar, 1u);
             if (cta_sweeps_forward(P)) issue_b_load(P);
             if (j0 < nK) issue_chain_forward_loads(P, j0, 1);   // the staging area is free: this CTA's sweeps are done
-            const unsigned int target = bar_count(P, it, P.n_ranks > 1 ? 2 : 1);
+            const unsigned int target = bar_count(P, it, 1);
             while (ld_acquire_u32(P.bar) < target) {}
         }
         cbar();
@@ -1901,16 +1931,19 @@ __device__ __noinline__ void iter_close(const PArgs &P, KState &K, int it) {
             P.dist_part[2 * blockIdx.x] = t1; P.dist_part[2 * blockIdx.x + 1] = t2;
         }
     }
-    const int last_pos = (P.n_crown > 0 ? 2 : 1) + (P.n_ranks > 1 && P.n_crown > 0 ? 1 : 0);
+    const int last_pos = P.n_crown > 0 ? 2 : 1;
     const unsigned int target = bar_count(P, it, last_pos);
     dstamp(P, 28);
     if (P.n_ranks > 1) {
-        // the sweep region is dead (every warp passed the barrier above): start refilling the stream ring for iteration it+1
+        // the one barrier across the GPUs per iteration (it also carries the prox distances).  Arrive first -- the fence would
+        // otherwise also wait for the bulk copies -- then refill the stream ring for iteration it+1 (the sweep region is dead:
+        // every warp passed the CTA barrier inside the arrive), then poll the peers' flags
+        cross_arrive(P, target, P.epoch0 + (unsigned)it + 1u, it);
         if (warp == kLoaderWarp && it + 1 < P.iters) {
             if (!P.sh_mode) loader_role(P, K.R, K.LS, it + 1, 1);
             else if (lane == 0) sh_issue_matrices(P);
         }
-        grid_sync_cross(P, target, P.epoch0 + 2u * (unsigned)it + 2u, it);
+        cross_wait(P, P.epoch0 + (unsigned)it + 1u);
     } else {
         // closing grid barrier, run by the loader warp: arrive first (the fence would otherwise also wait for the bulk
         // copies), then refill the stream ring for iteration it+1 -- the sweep region is dead, the factor matrices are
@@ -2105,15 +2138,15 @@ __global__ void k_to_chain_major(int nodes, int dim, int dimp, const int *__rest
 }
 
 // Exchange buffer of this rank (one cudaMalloc, so that one CUDA IPC handle maps it into the peer processes):
-//   S_q table [n_crown*nxp] | S_r table [n_crown*nvp] (rows padded to 16 bytes) | beta rows of the crown [n_crown*nv] | distance slots [kMaxRanks][2][2] doubles | flags [kMaxRanks] | err
-struct XchgLayout { size_t sq, sr, beta, dslot, flags, err, bytes; };
+//   S_q table [n_crown*nxp] | S_r table [n_crown*nvp] (rows padded to 16 bytes) | beta rows of the crown [n_crown*nv] | distance slots [kMaxRanks][2][2] doubles | flags [kMaxRanks] | S-row counter | err
+struct XchgLayout { size_t sq, sr, beta, dslot, flags, sctr, err, bytes; };
 static XchgLayout xchg_layout(const Handle *h) {
     XchgLayout X{};
     const size_t nc = (size_t)std::max(h->h_cum[h->chain_stage], 1);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~size_t(255); return at; };
     X.sq = take(nc * pad4(h->d.nx) * 4 + 64); X.sr = take(nc * pad4(h->d.nv) * 4 + 64); X.beta = take(nc * h->d.nv * 4); X.dslot = take(kMaxRanks * 4 * 8);
-    X.flags = take(kMaxRanks * 4); X.err = take(4); X.bytes = o;
+    X.flags = take(kMaxRanks * 4); X.sctr = take(4); X.err = take(4); X.bytes = o;
     return X;
 }
 size_t xchg_err_offset(const Handle *h) { return xchg_layout(h).err; }
@@ -2308,6 +2341,7 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
             P.Sq_peer[r] = reinterpret_cast<float *>(base + X.sq); P.Sr_peer[r] = reinterpret_cast<float *>(base + X.sr);
             P.dslot_peer[r] = reinterpret_cast<double *>(base + X.dslot);
             P.xflag_peer[r] = reinterpret_cast<unsigned int *>(base + X.flags);
+            P.s_ctr_peer[r] = reinterpret_cast<unsigned int *>(base + X.sctr);
         }
         char *own = static_cast<char *>(h->xchg);
         P.xerr = reinterpret_cast<int *>(own + X.err);
@@ -2317,11 +2351,16 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
         P.n_owned = 0; P.own_lo = P.bottom0;
         for (int b = 0; b < P.n_bottom; b++)
             if (h->h_child_count[P.bottom0 + b] > 0) { if (P.n_owned == 0) P.own_lo = P.bottom0 + b; P.n_owned++; }
+        // rows every rank's S table receives per iteration: every bottom-crown node that has chains somewhere (all of them in a
+        // scenario tree: a node above the chain stage has children); the counters run on across launches, like the epochs
+        P.n_bottom_active = P.n_ranks > 1 ? P.n_bottom : P.n_owned;
+        P.s_base = h->s_total;
+        h->s_total += (unsigned)P.n_bottom_active * (unsigned)iters;
         for (int b = 0; b < P.n_owned; b++)   // the owned bottom-crown nodes are one contiguous id range (contiguous chain ranges)
             if (h->h_child_count[P.own_lo + b] == 0) return fail(h, RN_ERR_INVALID, "the bottom-crown nodes with local chains are not contiguous");
         RN_CUDA(h, cudaMemsetAsync(own + X.err, 0, sizeof(int), st));   // a timed-out wait of an earlier launch does not poison this one
         P.epoch0 = h->xepoch;
-        h->xepoch += 2u * (unsigned)iters + 2u;   // every rank runs the same launches: the epochs stay aligned
+        h->xepoch += (unsigned)iters + 2u;   // every rank runs the same launches: the epochs stay aligned
     }
     if (h->pinf4_cap < iters) {
         h->pinf4_cap = iters + 8;
@@ -2330,7 +2369,7 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     P.pinf4 = h->pinf4;
     P.cm_c = h->cm_c; P.cm_lv = h->cm_lv; P.cm_beta = h->cm_beta; P.cm_uhat = h->cm_uhat; P.cm_e = h->cm_e;
     P.dist_part = h->dist_part; P.pinf = h->pinf; P.pinf_part = h->pinf_part;
-    P.lambda_tab = h->lambda_tab; P.bar = h->grid_bar; P.s_ctr = h->grid_bar + 32; P.par_ctr = h->grid_bar + 64; P.iter_dev = h->iter_dev; P.phase_ns = h->phase_ns; P.cta_ns = h->cta_ns;
+    P.lambda_tab = h->lambda_tab; P.bar = h->grid_bar; P.par_ctr = h->grid_bar + 64; P.iter_dev = h->iter_dev; P.phase_ns = h->phase_ns; P.cta_ns = h->cta_ns;
     P.step = h->step; P.inv_step = 1 / h->step; P.pen_x = h->pen_x; P.pen_xs = h->pen_xs;
     const SweepLayout Y = sweep_layout(h);
     P.oG = Y.oG; P.oOm = Y.oOm; P.oL = Y.oL; P.oX1 = Y.oX1; P.oY = Y.oY; P.oV = Y.oV; P.oScr2 = Y.oScr2; P.oStg = Y.oStg; P.oXb = Y.oXb;

@@ -44,6 +44,12 @@ if [[ " $PARTS " == *" nccl "* ]]; then
   timeout 300 $TR --master-port 29546 tools/nccl_exchange_baseline.py --parents 80 --row 160 > "$OUT/nccl_baseline_${NG}gpu.log" 2>&1; echo "nccl baseline x$NG rc=$?" | tee -a "$OUT/summary.txt"
   grep NCCL_BASELINE "$OUT/nccl_baseline_${NG}gpu.log"
 fi
+if [[ " $PARTS " == *" c4 "* ]]; then
+  for f in ${C4_FACTORS:-full shared}; do
+    timeout 900 $TR --master-port 29550 tools/c4_study.py --instances ${C4_INSTANCES:-1024} --steps ${C4_STEPS:-24} --factors $f > "$OUT/c4_study_${f}_${NG}gpu.json" 2> "$OUT/c4_study_${f}_${NG}gpu.err"; echo "c4 study $f x$NG rc=$?" | tee -a "$OUT/summary.txt"
+    grep '"study"' "$OUT/c4_study_${f}_${NG}gpu.json" | cut -c1-900
+  done
+fi
 if [[ " $PARTS " == *" ref "* ]]; then
   timeout 900 $TR --master-port 29547 bench.py --impl reference --gpus $NG --steps 3 --warmup 1 > "$OUT/bench_ref_${NG}gpu.json" 2> "$OUT/bench_ref_${NG}gpu.err"; echo "bench ref ${NG}gpu rc=$?" | tee -a "$OUT/summary.txt"
   cut -c1-300 "$OUT/bench_ref_${NG}gpu.json"
