@@ -110,7 +110,7 @@ struct Handle {
     unsigned int s_total = 0;                      // S rows every rank's table has received in all launches so far (the in-kernel counter's base)
     float *pinf4 = nullptr;
     float *bat_y = nullptr, *bat_y3 = nullptr, *bat_x = nullptr;   // RN_SWEEP_BATCHED scratch: GEMM outputs, X = -1/2 (sigma + G q_bar)
-    float *head_q = nullptr, *head_r = nullptr;    // q / r of this rank's chain heads (persistent kernel)
+    float *head_q = nullptr, *head_r = nullptr;    // G q / r of this rank's chain heads, nv floats each (persistent kernel)
     int pinf4_cap = 0;
     float *cm_c = nullptr, *cm_lv = nullptr, *cm_beta = nullptr, *cm_uhat = nullptr, *cm_e = nullptr;   // chain-major arrays
     int *crown_rng = nullptr, *pos_dev = nullptr, *crown_path = nullptr;

@@ -87,12 +87,12 @@ struct PArgs {
     // the crown is replicated.  Every rank's exchange buffer is mapped into every process (CUDA IPC); index = rank.
     int n_ranks, rank, K_glob, chain_off;
     unsigned int epoch0;                        // cross-GPU barrier epochs of this launch start after epoch0
-    float *hq, *hr;                             // q / r of this rank's chain heads [K*nx], [K*nv] (local)
-    // Near-root exchange: S_p = sum over the chain heads below bottom-crown node p (stage cs-1) of (q, r), formed by the rank
+    float *hg, *hr;                             // G q / r of this rank's chain heads [K*nv] each (local)
+    // Near-root exchange: S_p = sum over the chain heads below bottom-crown node p (stage cs-1) of (G q, r), formed by the rank
     // that owns p's chains in ascending child order (the same bits for any number of ranks) and stored into EVERY rank's
-    // table, indexed by crown node id: [n_crown*nx], [n_crown*nv].  solveSumChildren (Utilities.cu:168-201) one level up.
-    float *Sq_peer[kMaxRanks], *Sr_peer[kMaxRanks];
-    unsigned int *par_ctr;                      // [n_crown] local: chains of a bottom-crown node whose head q, r are in hq / hr (cumulative)
+    // table, indexed by crown node id: [n_crown*nvp] each.  solveSumChildren (Utilities.cu:168-201) one level up.
+    float *Sg_peer[kMaxRanks], *Sr_peer[kMaxRanks];
+    unsigned int *par_ctr;                      // [n_crown] local: chains of a bottom-crown node whose head G q, r are in hg / hr (cumulative)
     unsigned int *s_ctr_peer[kMaxRanks];        // on every rank: bottom-crown nodes whose S row has arrived there (cumulative over launches);
                                                 // the owner of a row bumps every rank's counter after storing the row (NVLink atomics)
     unsigned int s_base;                        // value of the counters when this launch starts
@@ -292,11 +292,11 @@ __device__ __forceinline__ SweepSmem sweep_smem(const PArgs &P) {
 }
 struct StagePhase { uint32_t c, r, v, f; };   // parities of the staging mbarriers (every thread tracks them)
 
-// one thread: pull G, OmegaBar, L into the sweep region (it overlays the idle stream ring)
+// one thread: pull OmegaBar, L into the sweep region (it overlays the idle stream ring).  G is not needed: the sweeps take
+// G q from the streamed D xi (chain_rscan)
 __device__ __forceinline__ void issue_matrix_loads(const PArgs &P) {
     const SweepSmem S = sweep_smem(P);
     fence_proxy_async_all();   // the region was last written through the generic proxy (vector ring, w, partial sums)
-    mbar_expect_tx(&S.mfull[0], P.bG); bulk_g2s(S.G, P.pack + P.pG, P.bG, &S.mfull[0]);
     mbar_expect_tx(&S.mfull[1], P.bOm); bulk_g2s(S.Om, P.pack + P.pOm, P.bOm, &S.mfull[1]);
     mbar_expect_tx(&S.mfull[2], P.bL); bulk_g2s(S.L, P.pack + P.pL, P.bL, &S.mfull[2]);
 }
@@ -306,16 +306,14 @@ __device__ __forceinline__ void issue_b_load(const PArgs &P) {
     fence_proxy_async_all();
     mbar_expect_tx(&S.mfull[3], P.bB); bulk_g2s(S.B, P.pack + P.pB, P.bB, &S.mfull[3]);
 }
-// one thread: the backward operand blocks of chain j -> staging.  Staging layout (floats): c | beta | p0 | p1 | p2 | p3
+// one thread: the backward operand blocks of chain j -> staging.  Staging layout (floats): beta | p0 | p1 | p2 | p3
 __device__ __forceinline__ void issue_chain_backward_loads(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
     const int T = P.N - P.cs;
     const size_t row0 = (size_t)P.n_crown + (size_t)j * T;
-    const uint32_t bx = (uint32_t)(T * P.nxp * 4), bv = (uint32_t)(T * P.nvp * 4);
+    const uint32_t bv = (uint32_t)(T * P.nvp * 4);
     float *d = S.stg;
     fence_proxy_async_all();   // the blocks were written with ordinary stores (phase S of other CTAs, before the barrier)
-    mbar_expect_tx(&S.sfull[0], bx);
-    bulk_g2s(d, P.cm_c + row0 * P.nxp, bx, &S.sfull[0]); d += T * P.nxp;
     mbar_expect_tx(&S.sfull[1], 3 * bv);
     bulk_g2s(d, P.cm_beta + row0 * P.nvp, bv, &S.sfull[1]); d += T * P.nvp;
     bulk_g2s(d, P.part[0] + row0 * P.nvp, bv, &S.sfull[1]); d += T * P.nvp;
@@ -585,7 +583,7 @@ __device__ __forceinline__ void sweep_vcombine(const PArgs &P, const SweepSmem &
     if (e >= nv) return;
     const bool df = P.df_mode != 0;
     // Phi xi, Psi psi of the columns: staged [col][nvp] (chains) or chain-major global rows (crown tiles: a few columns)
-    const float *b2p = staged ? S.stg + T * P.nxp + 3 * T * nvp + e : P.part[2] + e, *b3p = staged ? b2p + T * nvp : P.part[3] + e;
+    const float *b2p = staged ? S.stg + 3 * T * nvp + e : P.part[2] + e, *b3p = staged ? b2p + T * nvp : P.part[3] + e;
     float *__restrict__ Vg = P.V + e;
     const float *y = S.Y + e * kTP;
     float *vr = S.V + e * kTP;
@@ -670,60 +668,40 @@ __device__ __noinline__ void chain_columns(const PArgs &P, int j) {
 // once per chain and iteration, and the whole iteration's code does not fit the instruction cache), so a 24-step
 // unrolled body costs more in fetch than the bank conflicts of the [element][kTP] column arrays cost here.
 
-// q-scan: q = c + q_child (:651-658).  X1 rows 0..nx-1 get q_bar (q of the child, 0 at the leaf); head q -> qh[j]
-__device__ __noinline__ void chain_qscan(const PArgs &P, int j) {
-    const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, T = P.N - P.cs, nx = P.nx, nxp = P.nxp;
-    if (e >= nx) return;
-    const float *cs_ = S.stg + e;
-    float *x1 = S.X1 + e * kTP;
-    for (int s = T; s < kTP; s++) x1[s] = 0.f;
-    float qrun = 0.f;
-#pragma unroll 4
-    for (int s = T - 1; s >= 0; s--) {
-        const float c = cs_[s * nxp];
-        x1[s] = qrun;
-        qrun = c + qrun;
-    }
-    P.hq[(size_t)j * nx + e] = qrun;
-}
-
-// r-scan: sigma = beta + r_child (:599); r = ((sigma + D xi) + F psi) + G q_bar (:631-646).  Y = G q_bar on entry.
-// X1 rows nx.. get -1/2 (sigma + G q_bar) (df: -1/2 r); head r -> rh[j]
+// r-scan of a chain.  The reference runs q = c + q_child (:651-658), sigma = beta + r_child (:599) and
+// r = ((sigma + D xi) + F psi) + G q_bar (:631-646), q_bar = q of the child.  q itself is never needed, only G q_bar, and
+// D_i = G sysF_i' (Engine.cu:720-728) makes G c_i the streamed product D_i xi_w that this scan reads anyway: G q = D xi + G q_child
+// runs as a second running sum next to r -- no q-scan and no product with G in the sweeps.
+// X1 rows nx.. get -1/2 (sigma + G q_bar) (df: -1/2 r); the head's G q, r -> hg[j], hr[j]
 __device__ __noinline__ void chain_rscan(const PArgs &P, int j) {
     const SweepSmem S = sweep_smem(P);
     const int e = threadIdx.x, T = P.N - P.cs, nv = P.nv, nvp = P.nvp;
     if (e >= nv) return;
     const bool df = P.df_mode != 0;
-    const float *sb = S.stg + T * P.nxp + e, *s0 = sb + T * nvp, *s1 = s0 + T * nvp;
-    const float *y = S.Y + e * kTP;
+    const float *sb = S.stg + e, *s0 = sb + T * nvp, *s1 = s0 + T * nvp;
     float *x1 = S.X1 + (P.nx + e) * kTP;
     for (int s = T; s < kTP; s++) x1[s] = 0.f;
-    float rrun = 0.f;
+    float rrun = 0.f, grun = 0.f;
 #pragma unroll 4
     for (int s = T - 1; s >= 0; s--) {
-        const float ys = y[s];
+        const float d = s0[s * nvp];
         const float sg = sb[s * nvp] + rrun;
-        rrun = ((sg + s0[s * nvp]) + s1[s * nvp]) + ys;
-        x1[s] = -0.5f * (df ? rrun : sg + ys);
+        rrun = ((sg + d) + s1[s * nvp]) + grun;
+        x1[s] = -0.5f * (df ? rrun : sg + grun);
+        grun = d + grun;
     }
+    P.hg[(size_t)j * nv + e] = grun;
     P.hr[(size_t)j * nv + e] = rrun;
 }
 
 __device__ __noinline__ void chain_backward(const PArgs &P, int j, int next_chain, uint32_t mpar, StagePhase &ph) {
     const SweepSmem S = sweep_smem(P);
     chain_columns(P, j);
-    mbar_wait(&S.sfull[0], ph.c); ph.c ^= 1;
-    chain_qscan(P, j);
-    cbar();
     dstamp(P, 3);
-    mbar_wait(&S.mfull[0], mpar);
-    tile_gemm(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2);                               // G q_bar   (:644-646)
-    dstamp(P, 4);
     mbar_wait(&S.sfull[1], ph.r); ph.r ^= 1;
     chain_rscan(P, j);
     cbar();
-    if (threadIdx.x == 0 && P.n_crown > 0) {   // this chain's head q, r are in the tables: tell whoever sums its parent's heads
+    if (threadIdx.x == 0 && P.n_crown > 0) {   // this chain's head G q, r are in the tables: tell whoever sums its parent's heads
         __threadfence();
         atomicAdd(P.par_ctr + S.anc[P.cs - 1], 1u);
     }
@@ -887,26 +865,26 @@ __device__ __noinline__ void chain_forward(const PArgs &P, int j, int next_chain
 }
 
 // ---- crown (stages above the chains) ------------------------------------------------------------------------------
-// A tile = up to kTP/2 consecutive crown nodes.  solveSumChildren (Utilities.cu:168-201) unrolled over the whole subtree:
-//   q_bar_i = sum_{crown j below i} c_j + sum_{heads h below i} q_h
-//   sigma_i = beta_i + [ sum_{heads} r_h + sum_{crown j below i} (beta_j + D xi_j + F psi_j) ] + G QS_i
-//   QS_i    = sum_{crown j below i} q_bar_j = sum_{crown j below i} (s_j - s_i - 1) c_j + (cs - 1 - s_i) sum_{heads} q_h
+// A tile = up to kTP/2 consecutive crown nodes.  solveSumChildren (Utilities.cu:168-201) unrolled over the whole subtree, with
+// G c_j = D_j xi_w (see chain_rscan) and g_h = G q_h of a chain head:
+//   G q_bar_i = sum_{crown j below i} D xi_j + sum_{heads h below i} g_h
+//   G QS_i    = G sum_{crown j below i} q_bar_j = sum_{crown j below i} (s_j - s_i - 1) D xi_j + (cs - 1 - s_i) sum_{heads} g_h
+//   sigma_i   = beta_i + [ sum_{heads} r_h + sum_{crown j below i} (beta_j + D xi_j + F psi_j) ] + G QS_i
 // (the descendants of a node are one contiguous id range per stage: children are contiguous, Utilities.cu:184-199).
-// X1 q-rows: columns 0..n-1 = QS_i, columns 12..12+n-1 = q_bar_i (one G GEMM gives both products); V rows = base_i
 // Sums over rows of chain-major arrays, as float4 columns, for ONE crown node: all row ranges that enter the node's sums --
 // its crown descendants stage by stage, then the S rows of the bottom-crown nodes below it -- form one virtual row list, so that
 // every load of the node is in flight together (a call per range cost a round trip to L2 each).  The CTA is 8 row groups of two
-// warps: the even warp of a pair adds rows of c / S_q (row length nxp), the odd warp rows of beta + D xi + F psi / S_r (nvp);
+// warps: the even warp of a pair adds rows of D xi / S_g, the odd warp rows of beta + D xi + F psi / S_r (all nvp long);
 // lane = float4 column.  Group g takes virtual rows g, g + 8, ...; kRows of them in flight per trip, added in ascending order.
-// acc += row, accw += w(range) * row (even warps: w = how many times the range counts in QS).
+// acc += row, accw += w(range) * row (even warps: w = how many times the range counts in G QS).
 struct F4 { float x, y, z, w; };
 struct CrownSegs { int n, start[kMaxCs + 2], lo[kMaxCs + 1]; float w[kMaxCs + 1]; };   // in shared memory; the last range is the S rows
 __device__ __noinline__ void crown_row_sums(const PArgs &P, const CrownSegs &G, F4 &acc, F4 &accw) {
     const int t = threadIdx.x, g = t >> 6, role = (t >> 5) & 1, c4 = t & 31;
     constexpr int kRows = 8;
-    const int dim = role ? P.nv : P.nx, ld = role ? P.nvp : P.nxp;
-    if (4 * c4 >= dim) return;
-    const float *crown0 = (role ? P.cm_beta : P.cm_c) + 4 * c4, *s0 = (role ? P.Sr_peer[P.rank] : P.Sq_peer[P.rank]) + 4 * c4;
+    const int ld = P.nvp;
+    if (4 * c4 >= P.nv) return;
+    const float *crown0 = (role ? P.cm_beta : P.part[0]) + 4 * c4, *s0 = (role ? P.Sr_peer[P.rank] : P.Sg_peer[P.rank]) + 4 * c4;
     const ptrdiff_t d1 = P.part[0] - P.cm_beta, d2 = P.part[1] - P.cm_beta;
     const int nseg = G.n, total = G.start[nseg];
     F4 sum{0.f, 0.f, 0.f, 0.f}, sumw{0.f, 0.f, 0.f, 0.f};
@@ -941,11 +919,11 @@ __device__ __noinline__ void crown_row_sums(const PArgs &P, const CrownSegs &G, 
     acc = sum; accw = sumw;
 }
 
-// S_p of bottom-crown node p (stage cs-1): q and r of its chain heads added in ascending child order -- what
-// solveSumChildren (Utilities.cu:168-201) leaves in the parent's slot -- stored into every rank's table.  The CTA waits
-// for p's chains (a counter they bump after their r-scan).  Threads 0..127: q rows, 128..255: r rows.
+// S_p of bottom-crown node p (stage cs-1): G q and r of its chain heads added in ascending child order -- what
+// solveSumChildren (Utilities.cu:168-201) leaves in the parent's slot (times G for q) -- stored into every rank's table.  The
+// CTA waits for p's chains (a counter they bump after their r-scan).  Threads 0..127: G q rows, 128..255: r rows.
 __device__ __noinline__ void parent_sum(const PArgs &P, int p, int it) {
-    const int t = threadIdx.x, nx = P.nx, nv = P.nv;
+    const int t = threadIdx.x, nv = P.nv;
     const int c0 = __ldg(P.child_first + p) - __ldg(P.cum + P.cs), nc = __ldg(P.child_count + p);   // chain indices of p's heads
     if (t == 0) {
         const unsigned int want = (unsigned)nc * (unsigned)(it + 1);
@@ -954,9 +932,9 @@ __device__ __noinline__ void parent_sum(const PArgs &P, int p, int it) {
     }
     cbar();
     const bool isq = t < 128;
-    const int e = isq ? t : t - 128, dim = isq ? nx : nv;
+    const int e = isq ? t : t - 128, dim = nv;
     if (t < 256 && e < dim) {
-        const float *src = (isq ? P.hq : P.hr) + (size_t)c0 * dim + e;
+        const float *src = (isq ? P.hg : P.hr) + (size_t)c0 * dim + e;
         float acc = 0.f;
 #pragma unroll 1
         for (int cb = 0; cb < nc; cb += 8) {
@@ -966,8 +944,8 @@ __device__ __noinline__ void parent_sum(const PArgs &P, int p, int it) {
 #pragma unroll
             for (int k = 0; k < 8; k++) if (cb + k < nc) acc = (cb + k == 0) ? v[k] : acc + v[k];
         }
-        const size_t o = (size_t)p * (isq ? P.nxp : P.nvp) + e;
-        for (int r = 0; r < P.n_ranks; r++) (isq ? P.Sq_peer[r] : P.Sr_peer[r])[o] = acc;
+        const size_t o = (size_t)p * P.nvp + e;
+        for (int r = 0; r < P.n_ranks; r++) (isq ? P.Sg_peer[r] : P.Sr_peer[r])[o] = acc;
     }
     cbar();
     if (t < P.n_ranks) {   // the row is in every rank's table: say so on every rank (lane r -> rank r; a peer's counter over NVLink)
@@ -983,15 +961,16 @@ __device__ __noinline__ void parent_sum(const PArgs &P, int p, int it) {
 __device__ __noinline__ void crown_sums(const PArgs &P, int ncols, bool do_wait, unsigned int wait_s, uint32_t mpar) {
     const SweepSmem S = sweep_smem(P);
     const int t = threadIdx.x, g = t >> 6, role = (t >> 5) & 1, c4 = t & 31, nx = P.nx, nv = P.nv, cs = P.cs, nvp = P.nvp;
+    const bool df = P.df_mode != 0;
     static_assert(8 * 3 * 128 <= 128 * kTP, "partial sums of the row groups fit the split-K scratch");
     static_assert(sizeof(CrownSegs) <= 64 * 4, "the range table fits the metadata words behind the chain cache");
     CrownSegs &G = *reinterpret_cast<CrownSegs *>(smem_f(kOffSegs));
     if (do_wait) {
         // while the chains are still scanning: run the GEMM once on whatever X1 holds (two k-steps, result overwritten
         // later) -- it pulls tile_gemm's code into the instruction cache, which is cold at this point of every iteration
-        mbar_wait(&S.mfull[0], mpar);
-        if (ncols == 1) tile_gemv2(S.G, nv, 4, S.X1, S.Y, S.scr2, 0, 12);
-        else tile_gemm(S.G, nv, 2, S.X1, S.Y, S.scr2);
+        mbar_wait(&S.mfull[1], mpar);
+        if (ncols == 1) tile_gemv2(S.Om, nv, 4, S.X1 + nx * kTP, S.Y, S.scr2, 0, 0);
+        else tile_gemm(S.Om, nv, 2, S.X1 + nx * kTP, S.Y, S.scr2);
         if (t == 0) {
             if (P.n_ranks == 1) { while ((int)(ld_acquire_u32(P.s_ctr_peer[0]) - wait_s) < 0) {} }
             else wait_sys(P.s_ctr_peer[P.rank], wait_s, P.xerr);
@@ -1014,7 +993,7 @@ __device__ __noinline__ void crown_sums(const PArgs &P, int ncols, bool do_wait,
             G.start[n] = at; G.n = n;
         }
         cbar();
-        F4 acc{0.f, 0.f, 0.f, 0.f}, accw{0.f, 0.f, 0.f, 0.f};   // even warps: q_bar, QS; odd warps: sums of beta + D xi + F psi and of r
+        F4 acc{0.f, 0.f, 0.f, 0.f}, accw{0.f, 0.f, 0.f, 0.f};   // even warps: G q_bar, G QS; odd warps: sums of beta + D xi + F psi and of r
         crown_row_sums(P, G, acc, accw);
         {
             float *sc = S.scr2 + (g * 3 + (role ? 2 : 0)) * 128 + 4 * c4;
@@ -1022,44 +1001,23 @@ __device__ __noinline__ void crown_sums(const PArgs &P, int ncols, bool do_wait,
             if (!role) *reinterpret_cast<float4 *>(sc + 128) = make_float4(accw.x, accw.y, accw.z, accw.w);
         }
         cbar();
-        if (t < 128) {
+        if (t < nv) {
             const float *s0 = S.scr2 + t;
             float qb = s0[0], qs = s0[128], bs = s0[256];
 #pragma unroll
             for (int k = 1; k < 8; k++) { qb += s0[k * 384]; qs += s0[k * 384 + 128]; bs += s0[k * 384 + 256]; }
-            if (t < nx) { S.X1[t * kTP + 12 + col] = qb; S.X1[t * kTP + col] = qs; }                    // q_bar, QS
-            if (t < nv) S.V[t * kTP + col] = __ldg(P.cm_beta + (size_t)i * nvp + t) + bs;               // sigma - G QS
+            // sigma = (beta + sums) + G QS;  X1 sigma-row = -1/2 (sigma + G q_bar)  (df: -1/2 r, r = ((sigma + D xi) + F psi) + G q_bar)
+            const float sg = (__ldg(P.cm_beta + (size_t)i * nvp + t) + bs) + qs;
+            S.X1[(nx + t) * kTP + col] = -0.5f * (df ? ((sg + __ldcg(P.part[0] + (size_t)i * nvp + t)) + __ldcg(P.part[1] + (size_t)i * nvp + t)) + qb
+                                                     : sg + qb);
         }
         cbar();
     }
-    if (t < nx) {   // unused columns: zeros
-        float *x1 = S.X1 + t * kTP;
-        for (int col = ncols; col < 12; col++) { x1[col] = 0.f; x1[12 + col] = 0.f; }
+    if (t < nv) {   // unused columns: zeros
+        float *x1 = S.X1 + (nx + t) * kTP;
+        for (int col = ncols; col < kTP; col++) x1[col] = 0.f;
     }
     cbar();
-}
-
-// sigma = (beta + sums) + G QS;  X1 sigma-rows = -1/2 (sigma + G q_bar)  (df: -1/2 r, r = ((sigma + D xi) + F psi) + G q_bar)
-__device__ __noinline__ void crown_sigma(const PArgs &P, int ncols) {
-    const SweepSmem S = sweep_smem(P);
-    const int e = threadIdx.x, nv = P.nv, nvp = P.nvp;
-    if (e >= nv) return;
-    const bool df = P.df_mode != 0;
-    const float *__restrict__ p0 = P.part[0] + e, *__restrict__ p1 = P.part[1] + e;
-    const float *y = S.Y + e * kTP, *b = S.V + e * kTP;
-    float *x1 = S.X1 + (P.nx + e) * kTP;
-#pragma unroll 1
-    for (int s = 0; s < 12; s++) {
-        float out = 0.f;
-        if (s < ncols) {
-            const float sg = b[s] + y[s];
-            if (df) {
-                const size_t idx = (size_t)S.colnode[s] * nvp;
-                out = -0.5f * (((sg + __ldcg(p0 + idx)) + __ldcg(p1 + idx)) + y[12 + s]);
-            } else out = -0.5f * (sg + y[12 + s]);
-        }
-        x1[s] = out; x1[12 + s] = 0.f;
-    }
 }
 
 // crown nodes in the order of the second crown pass: the upper crown, then the bottom-crown nodes whose chains live on
@@ -1079,12 +1037,6 @@ __device__ __noinline__ void crown_backward(const PArgs &P, int i0, int ncols, u
     cbar();
     crown_sums(P, ncols, do_wait, wait_s, mpar);
     dstamp(P, 11);
-    mbar_wait(&S.mfull[0], mpar);
-    if (ncols == 1) tile_gemv2(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2, 0, 12);
-    else tile_gemm(S.G, P.nv, P.nx, S.X1, S.Y, S.scr2);                          // G [QS | q_bar]
-    crown_sigma(P, ncols);
-    cbar();
-    dstamp(P, 12);
     sweep_backward_finish(P, ncols, false, mpar, ph, -1);
 }
 
@@ -1170,7 +1122,7 @@ struct LoaderState { int st; uint32_t ph; int vs; uint32_t vph; int skip; };
 // fills while the barrier and the next iteration's prologue are pending
 __device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderState &L, int it, int prefetch) {
     const Pipe M = pipe_smem();
-    const int nx = P.nx, nu = P.nu, nv = P.nv, ny = 2 * nx + nu, lane = threadIdx.x & 31;
+    const int nx = P.nx, nu = P.nu, nv = P.nv, lane = threadIdx.x & 31;
     int st = L.st, vs = L.vs; uint32_t ph = L.ph, vph = L.vph;
     const int skip = prefetch ? 0 : L.skip;
     fence_proxy_async();   // the ring region was last written through the generic proxy by the sweeps
@@ -1179,7 +1131,7 @@ __device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderS
     // read everything out of P / R once: the asm statements below clobber memory, so P.x inside the loops would be
     // re-read (through a generic pointer) after every copy
     const int prev_ = (it + 1) & 1;   // W[(it-1)&1] and Y[(it&1)^1]
-    const float *g0 = P.pri_xi, *g1 = P.Wxi[prev_], *g2 = P.dual_xi, *g3 = P.Yxi[prev_], *g8 = P.diag;
+    const float *g0 = P.pri_xi, *g1 = P.Wxi[prev_], *g2 = P.dual_xi, *g3 = P.Yxi[prev_];
     const float *g4 = P.pri_psi, *g5 = P.Wpsi[prev_], *g6 = P.dual_psi, *g7 = P.Ypsi[prev_];
     const float *m0 = P.mat[0], *m1 = P.mat[1], *m2 = P.mat[2], *m3 = P.mat[3];
     const int n_mats = P.n_mats, cols_per_chunk = P.cols_per_chunk, n_stages = P.n_stages, stage_stride = P.stage_stride;
@@ -1194,12 +1146,11 @@ __device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderS
         mbar_wait(&M.vempty[vs], vph ^ 1);
         float *dst = M.vec + vs * kVecCount * kVStride;
         const float *s0 = g0 + ox, *s1 = g1 + ox, *s2 = g2 + ox, *s3 = g3 + ox;
-        const float *s8 = g8 + (size_t)node * ny;
         const float *s4 = g4 + op, *s5 = g5 + op, *s6 = g6 + op, *s7 = g7 + op;
         if (pair_ok) {
             for (int k = 2 * lane; k < 2 * nx; k += 64) {
                 cp_async8(dst + k, s0 + k); cp_async8(dst + kVStride + k, s1 + k); cp_async8(dst + 2 * kVStride + k, s2 + k);
-                cp_async8(dst + 3 * kVStride + k, s3 + k); cp_async8(dst + 8 * kVStride + k, s8 + k);
+                cp_async8(dst + 3 * kVStride + k, s3 + k);
             }
             for (int k = 2 * lane; k < nu; k += 64) {
                 cp_async8(dst + 4 * kVStride + k, s4 + k); cp_async8(dst + 5 * kVStride + k, s5 + k);
@@ -1208,7 +1159,7 @@ __device__ __noinline__ void loader_role(const PArgs &P, const Slice &R, LoaderS
         } else {
             for (int k = lane; k < 2 * nx; k += 32) {
                 cp_async4(dst + k, s0 + k); cp_async4(dst + kVStride + k, s1 + k); cp_async4(dst + 2 * kVStride + k, s2 + k);
-                cp_async4(dst + 3 * kVStride + k, s3 + k); cp_async4(dst + 8 * kVStride + k, s8 + k);
+                cp_async4(dst + 3 * kVStride + k, s3 + k);
             }
             for (int k = lane; k < nu; k += 32) {
                 cp_async4(dst + 4 * kVStride + k, s4 + k); cp_async4(dst + 5 * kVStride + k, s5 + k);
@@ -1447,9 +1398,9 @@ __device__ __noinline__ void ew_role(const PArgs &P, const Slice &R, EwState &E,
     const float inv_step = P.inv_step, step = P.step, a1 = I.a1, a2 = I.a2, sc1 = I.sc1, sc2 = I.sc2;
     const bool br1 = I.br1 != 0, br2 = I.br2 != 0;
     float *__restrict__ Yxi = P.Yxi[I.cur], *__restrict__ Wxi = P.Wxi[I.cur], *__restrict__ Ypsi = P.Ypsi[I.cur],
-          *__restrict__ Wpsi = P.Wpsi[I.cur], *__restrict__ cg = P.cm_c;
+          *__restrict__ Wpsi = P.Wpsi[I.cur];
     const int *__restrict__ pos = P.pos;
-    const int nxp = P.nxp, nvp = P.nvp;
+    const int nvp = P.nvp;
     float *__restrict__ part0 = P.part[0], *__restrict__ part1 = P.part[1], *__restrict__ part2 = P.part[2],
           *__restrict__ part3 = P.part[3];
     Cand lbx = bx, lbp = bp;
@@ -1486,12 +1437,7 @@ __device__ __noinline__ void ew_role(const PArgs &P, const Slice &R, EwState &E,
                 if (xi_type) cand_merge(lbx, cd); else cand_merge(lbp, cd);
             }
         }
-        ewbar();
-        if (wr_xi) {   // c = sysF' xi_w  (:651-658)
-            const float *dg = vsl + 8 * kVStride;
-            const size_t row = (size_t)__ldg(pos + node) * nxp;
-            for (int t = et; t < nx; t += kEwWarps * 32) cg[row + t] = dg[t] * wdst[t] + dg[nx + t] * wdst[nx + t];
-        }
+        // (c = sysF' xi_w of :651-658 is not formed: the sweeps take G q from D xi_w, chain_rscan)
         __syncwarp();
         if (lane == 0) { mbar_arrive(&M.vempty[vs]); mbar_arrive(&M.wfull[wb]); }
         if (++vs == kVecSlots) { vs = 0; vph ^= 1; }
@@ -1587,11 +1533,11 @@ __device__ __noinline__ void sh_issue_vectors(const PArgs &P, int it, int t0, in
 }
 
 __device__ __noinline__ void sh_elementwise(const PArgs &P, const EwIter &I, int it, int t0, int nt, Cand &bx, Cand &bp) {
-    const int nx = P.nx, nu = P.nu, ny = 2 * nx + nu, nxp = P.nxp, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nx = P.nx, nu = P.nu, ny = 2 * nx + nu, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float inv_step = P.inv_step, step = P.step, a1 = I.a1, a2 = I.a2, sc1 = I.sc1, sc2 = I.sc2;
     const bool br1 = I.br1 != 0, br2 = I.br2 != 0;
     float *__restrict__ Yxi = P.Yxi[I.cur], *__restrict__ Wxi = P.Wxi[I.cur], *__restrict__ Ypsi = P.Ypsi[I.cur],
-          *__restrict__ Wpsi = P.Wpsi[I.cur], *__restrict__ cg = P.cm_c;
+          *__restrict__ Wpsi = P.Wpsi[I.cur];
     float *ccol = smem_f(P.sh_oC), *gcol = smem_f(P.sh_oGc);
     const int *colnode = reinterpret_cast<const int *>(smem_f(kOffMisc));
     // every array's slice starts `skip` floats into its 16-byte window
@@ -1611,7 +1557,6 @@ __device__ __noinline__ void sh_elementwise(const PArgs &P, const EwIter &I, int
             continue;
         }
         const int node = t0 + nl;
-        const size_t crow = (size_t)colnode[nl] * nxp;
         const float *hx = b[0] + nl * 2 * nx, *wp = b[1] + nl * 2 * nx, *zz = b[2] + nl * 2 * nx, *yp = b[3] + nl * 2 * nx;
         const float *dg = b[8] + nl * ny;
         // state-box element t and safety element nx + t of the node: together they give c[t] = (sysF' xi_w)[t]  (:651-658)
@@ -1638,7 +1583,6 @@ __device__ __noinline__ void sh_elementwise(const PArgs &P, const EwIter &I, int
                 wv[h] = w;
             }
             const float cv = dg[t] * wv[0] + dg[nx + t] * wv[1];
-            cg[crow + t] = cv;
             ccol[t * kTP + nl] = cv;
         }
         const float *hp = b[4] + nl * nu, *wpp = b[5] + nl * nu, *zp = b[6] + nl * nu, *ypp = b[7] + nl * nu;
@@ -1851,7 +1795,7 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
     // ---- phase C: backward sweep of the crown (tiles are dealt from the last CTA down: those have the fewest chains)
     if (P.n_crown > 0) {
         // the crown needs the heads of every chain: with several GPUs their q, r were stored into every rank's
-        // table (chain_qscan / chain_rscan), and this barrier spans the GPUs.  On one GPU only the CTAs that own crown
+        // table (chain_rscan), and this barrier spans the GPUs.  On one GPU only the CTAs that own crown
         // tiles wait, and only for the heads (a counter the chains bump after their r-scan): the crown overlaps the
         // rest of the chains' backward sweep
         const CrownDeal C = crown_deal(P);
@@ -2066,7 +2010,7 @@ static SweepLayout sweep_layout(const Handle *h) {
     Y.oScr2 = Y.oV + std::max(nv, nu) * kTP;
     Y.oStg = Y.oScr2 + 128 * kTP;
     const int cs = h->chain_stage;
-    Y.oXb = Y.oStg + std::max(T * Y.nxp + 5 * T * Y.nvp, 2 * T * Y.nup + T * Y.nxp + cs * (2 * Y.nup + Y.nxp));
+    Y.oXb = Y.oStg + std::max(5 * T * Y.nvp, 2 * T * Y.nup + T * Y.nxp + cs * (2 * Y.nup + Y.nxp));
     Y.end = Y.oXb + nx * kTP;
     return Y;
 }
@@ -2138,14 +2082,14 @@ __global__ void k_to_chain_major(int nodes, int dim, int dimp, const int *__rest
 }
 
 // Exchange buffer of this rank (one cudaMalloc, so that one CUDA IPC handle maps it into the peer processes):
-//   S_q table [n_crown*nxp] | S_r table [n_crown*nvp] (rows padded to 16 bytes) | beta rows of the crown [n_crown*nv] | distance slots [kMaxRanks][2][2] doubles | flags [kMaxRanks] | S-row counter | err
+//   S_g table [n_crown*nvp] | S_r table [n_crown*nvp] (rows padded to 16 bytes) | beta rows of the crown [n_crown*nv] | distance slots [kMaxRanks][2][2] doubles | flags [kMaxRanks] | S-row counter | err
 struct XchgLayout { size_t sq, sr, beta, dslot, flags, sctr, err, bytes; };
 static XchgLayout xchg_layout(const Handle *h) {
     XchgLayout X{};
     const size_t nc = (size_t)std::max(h->h_cum[h->chain_stage], 1);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~size_t(255); return at; };
-    X.sq = take(nc * pad4(h->d.nx) * 4 + 64); X.sr = take(nc * pad4(h->d.nv) * 4 + 64); X.beta = take(nc * h->d.nv * 4); X.dslot = take(kMaxRanks * 4 * 8);
+    X.sq = take(nc * pad4(h->d.nv) * 4 + 64); X.sr = take(nc * pad4(h->d.nv) * 4 + 64); X.beta = take(nc * h->d.nv * 4); X.dslot = take(kMaxRanks * 4 * 8);
     X.flags = take(kMaxRanks * 4); X.sctr = take(4); X.err = take(4); X.bytes = o;
     return X;
 }
@@ -2232,7 +2176,7 @@ rn_status persistent_prepare(Handle *h) {
     RN_CHECK(ensure_xchg(h));
     // [0] grid barrier, [32] published-S counter (its own 128-byte line), [64 ...] per bottom-crown node: heads in
     RN_CHECK(dev_alloc(h, &h->grid_bar, 64 + (size_t)std::max(n_crown, 1)));
-    RN_CHECK(dev_alloc(h, &h->head_q, (size_t)d.K * d.nx)); RN_CHECK(dev_alloc(h, &h->head_r, (size_t)d.K * d.nv));
+    RN_CHECK(dev_alloc(h, &h->head_q, (size_t)d.K * d.nv)); RN_CHECK(dev_alloc(h, &h->head_r, (size_t)d.K * d.nv));
     RN_CHECK(dev_alloc(h, &h->phase_ns, 32));
     RN_CHECK(dev_alloc(h, &h->cta_ns, 2 * 1024));
     // G | OmegaBar | L | B | L', each padded to 16 bytes: the bulk copies of the sweeps (and of phase S in shared-factor mode)
@@ -2338,14 +2282,14 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
         for (int r = 0; r < P.n_ranks; r++) {
             char *base = static_cast<char *>(h->xchg_peer[r]);
             if (!base) return fail(h, RN_ERR_STATE, "rank %d's exchange buffer is not connected (rn_dist_connect)", r);
-            P.Sq_peer[r] = reinterpret_cast<float *>(base + X.sq); P.Sr_peer[r] = reinterpret_cast<float *>(base + X.sr);
+            P.Sg_peer[r] = reinterpret_cast<float *>(base + X.sq); P.Sr_peer[r] = reinterpret_cast<float *>(base + X.sr);
             P.dslot_peer[r] = reinterpret_cast<double *>(base + X.dslot);
             P.xflag_peer[r] = reinterpret_cast<unsigned int *>(base + X.flags);
             P.s_ctr_peer[r] = reinterpret_cast<unsigned int *>(base + X.sctr);
         }
         char *own = static_cast<char *>(h->xchg);
         P.xerr = reinterpret_cast<int *>(own + X.err);
-        P.hq = h->head_q; P.hr = h->head_r;
+        P.hg = h->head_q; P.hr = h->head_r;
         const int cs_ = h->chain_stage;
         P.bottom0 = cs_ > 0 ? h->h_cum[cs_ - 1] : 0; P.n_bottom = cs_ > 0 ? h->h_cum[cs_] - h->h_cum[cs_ - 1] : 0;
         P.n_owned = 0; P.own_lo = P.bottom0;

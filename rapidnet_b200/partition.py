@@ -10,9 +10,9 @@ first stage of its non-branching tail ("chain stage" cs: below it every scenario
 The cut is aligned to the nodes of the last crown stage (stage cs-1, the "bottom-crown" nodes): all chains below one of
 them go to the same rank.  Each rank builds an ordinary, smaller problem (crown + its chains, nodes renumbered
 breadth-first) and creates its handle on it; per APG iteration the ranks exchange -- inside the persistent kernel, over
-NVLink peer memory mapped with CUDA IPC -- for every bottom-crown node they own the sum of q and of r over its chain
-heads (nx + nv floats: what the reference's solveSumChildren leaves in the parent's slot, so that every rank can finish
-the crown) and the two squared prox distances.  Per solve, the beta rows of the bottom-crown nodes travel the same way.
+NVLink peer memory mapped with CUDA IPC -- for every bottom-crown node they own the sum of G q and of r over its chain
+heads (2 nv floats: what the reference's solveSumChildren leaves in the parent's slot, q already multiplied by G, so that
+every rank can finish the crown) and the two squared prox distances.  Per solve, the beta rows of the bottom-crown nodes travel the same way.
 Nothing else crosses GPUs.  torch.distributed hands the 64-byte IPC handles around and provides the host barrier.
 """
 from __future__ import annotations
@@ -225,7 +225,7 @@ class DistributedSolver:
         t, m, n = self.local.tree, self.meta, self.local.network
         cum = t.nodes_per_stage_cumul
         owned = int(np.count_nonzero(t.n_children[int(cum[m.cs - 1]): int(cum[m.cs])])) if m.cs > 0 else 0
-        return (owned * (n.nx + self.local.config.nv) * 4 + 2 * 16 + 2 * 4) * (self.world - 1)
+        return (owned * 2 * self.local.config.nv * 4 + 2 * 16 + 2 * 4) * (self.world - 1)
 
     def gather(self, name: str, dim: int) -> np.ndarray:
         """A per-node buffer ([nodes][dim]) assembled in GLOBAL node order on every rank."""

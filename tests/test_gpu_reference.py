@@ -23,7 +23,7 @@ from rapidnet_b200 import cabi
 from rapidnet_b200.datagen import named_problem
 from rapidnet_b200.problem import write_problem
 from oracle.oracle import Oracle
-from refcompare import RTOL, accuracy_gate, floor_tol, pinf_close, rel_err
+from refcompare import ACC_MEDIAN, RTOL, accuracy_gate, floor_tol, median_ratio, pinf_close, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -72,18 +72,22 @@ def test_iterates_match_reference_build(case, iters, toy, tmp_path):
     o64.factor_step(); o64.update_state(); o64.eliminate(fc.demand[slot], fc.prices[slot]); o64.apg(iters)
     worst = ("", 0.0, 0.0)
     limited = False
+    acc = []
     for gname, rname, oname in PAIRS:
         ours = s.read(gname)
         err = rel_err(ours, ref[rname])
         tol, floor = floor_tol(ref[rname], o64.get(oname))
         ok, e_ours, e_ref = accuracy_gate(ours, ref[rname], o64.get(oname))
         limited |= tol > RTOL
+        acc.append((e_ours, e_ref))
         if err > worst[1]:
             worst = (gname, err, floor)
         assert ok, (f"{case} it={iters}: {gname} is {e_ours:.3e} from the double-precision trajectory, the reference build "
                     f"{e_ref:.3e}: more than ACC_FACTOR times as far")
         assert err < tol, (f"{case} it={iters}: {gname} rel err {err:.3e} vs the reference build "
                            f"(tolerance {tol:.1e}; the reference is {floor:.1e} from the double-precision trajectory)")
+    med = median_ratio(acc)
+    assert med <= ACC_MEDIAN, f"{case} it={iters}: median over the variables of err(ours, f64) / err(reference, f64) = {med:.2f}"
     u0_tol, u0_floor = floor_tol(ref["u0"], o64.get("U")[: u0.size])
     ok, e_ours, e_ref = accuracy_gate(u0, ref["u0"], o64.get("U")[: u0.size])
     assert ok, f"{case} it={iters}: u0 is {e_ours:.3e} from the double-precision trajectory, the reference build {e_ref:.3e}"
@@ -97,7 +101,7 @@ def test_iterates_match_reference_build(case, iters, toy, tmp_path):
     # same cuSOLVER routine on the same matrix -> the same null-space basis; then V and beta must agree too
     lerr = rel_err(s.read("SYS_MAT_L"), ref["L"])
     print(f"{case} it={iters}: worst {worst[0]} {worst[1]:.2e} (reference vs double {worst[2]:.2e}); u0 {rel_err(u0, ref['u0']):.2e} "
-          f"(floor {u0_floor:.2e}{', floor-limited' if limited else ''}); U ours vs double {ours_vs_64:.2e}; L vs ref {lerr:.2e}; "
+          f"(floor {u0_floor:.2e}{', floor-limited' if limited else ''}); median accuracy ratio {med:.2f}; U ours vs double {ours_vs_64:.2e}; L vs ref {lerr:.2e}; "
           f"{log.strip()}")
     s.close()
     s2 = cabi.Solver(prob)
