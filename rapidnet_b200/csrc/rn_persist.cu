@@ -33,6 +33,7 @@
 //
 // The last iteration's finalisation is done by k_finalize (rn_apg.cu) after the kernel.
 #include <algorithm>
+#include <mutex>
 
 #include "rn_internal.h"
 #include "rn_device.cuh"
@@ -1748,15 +1749,24 @@ __device__ __noinline__ void iter_stream(const PArgs &P, KState &K, int it) {
     if (it > 0 && (int)blockIdx.x == pcta && warp == 0) pinf_merge(P, it);
 }
 
-// Crown work is dealt from the last CTA down (those have the fewest chains): first the tiles of the second crown pass (the upper
-// crown is the critical path), then the bottom-crown nodes of the first pass.  Item q goes to the CTA with slot = q mod grid.
+// Crown work is dealt from the last CTA down (those have the fewest chains, none when K < grid).  Item q goes to the CTA with
+// slot = q mod grid.  First the bottom-crown nodes this rank owns (first pass: their S rows are what every rank's crown waits
+// for, so they must not queue behind a chain's whole backward sweep), then the tiles of the second pass in id order (the upper
+// crown first).  What overflows onto CTAs that sweep a chain are the last second-pass tiles, which wait for the S rows anyway.
 struct CrownDeal { int n2, tile_w, n_tiles2, n_items; };
 __device__ __forceinline__ CrownDeal crown_deal(const PArgs &P) {
     CrownDeal C;
     C.n2 = P.n_crown - P.n_owned;
-    C.tile_w = min(kTP / 2, max(1, (C.n2 + (int)gridDim.x - 1) / (int)gridDim.x));
+    const int grid = (int)gridDim.x;
+    C.tile_w = min(kTP / 2, max(1, (C.n2 + grid - 1) / grid));
+    // CTAs without a chain that the first pass leaves free: if tiles of up to four nodes fit them, no second-pass tile queues
+    // behind a chain's whole backward sweep (a tile of w nodes costs about 5 + 2 w us, the chain 13 us)
+    const int free2 = grid - min(P.K, grid) - P.n_owned;
+    if (free2 > 0)
+        for (int w = 1; w <= 4; w++)
+            if ((C.n2 + w - 1) / w <= free2) { C.tile_w = w; break; }
     C.n_tiles2 = (C.n2 + C.tile_w - 1) / C.tile_w;
-    C.n_items = C.n_tiles2 + P.n_bottom;
+    C.n_items = P.n_owned + C.n_tiles2;
     return C;
 }
 // does this CTA sweep anything backward / forward?  CTAs that do not leave the shared matrices where they are: no bulk copy
@@ -1764,15 +1774,17 @@ __device__ __forceinline__ CrownDeal crown_deal(const PArgs &P) {
 __device__ __noinline__ bool cta_sweeps_backward(const PArgs &P) {
     if ((int)blockIdx.x < P.K) return true;
     if (P.n_crown == 0) return false;
-    const CrownDeal C = crown_deal(P);
-    for (int q = (int)gridDim.x - 1 - (int)blockIdx.x; q < C.n_items; q += (int)gridDim.x)
-        if (q < C.n_tiles2 || __ldg(P.child_count + P.bottom0 + q - C.n_tiles2) > 0) return true;
-    return false;
+    return (int)gridDim.x - 1 - (int)blockIdx.x < crown_deal(P).n_items;
 }
 struct CrownTiles { int tile_w, n_tiles; };
-__device__ __forceinline__ CrownTiles crown_tiles(const PArgs &P) {   // forward: as narrow as the grid allows
+__device__ __forceinline__ CrownTiles crown_tiles(const PArgs &P) {
+    // forward: as narrow as the CTAs WITHOUT a chain allow (a crown tile costs about as much as a chain's forward sweep, and up
+    // to four columns of a tile cost the same as one: a tile on a chain's CTA would double that CTA's phase F); as narrow as the
+    // grid allows when every CTA has chains
     CrownTiles C;
-    C.tile_w = min(kTP / 2, max(1, (P.n_crown + (int)gridDim.x - 1) / (int)gridDim.x));
+    const int grid = (int)gridDim.x, free_ctas = grid - min(P.K, grid);
+    const int ctas = free_ctas > 0 ? free_ctas : grid;
+    C.tile_w = min(kTP / 2, max(1, (P.n_crown + ctas - 1) / ctas));
     C.n_tiles = (P.n_crown + C.tile_w - 1) / C.tile_w;
     return C;
 }
@@ -1803,13 +1815,10 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
         // Pass 1 -- the bottom-crown nodes whose chains live on this rank: S_p (the sum over p's chain heads; awaits only p's
         // chains) goes to every rank's table, then p's own backward step follows at once.
 #pragma unroll 1
-        for (int q = slot; q < C.n_items; q += grid) {
-            if (q < C.n_tiles2) continue;
-            const int p = P.bottom0 + q - C.n_tiles2;
-            if (__ldg(P.child_count + p) > 0) {
-                parent_sum(P, p, it);
-                crown_backward(P, p, 1, mpar, K.SP, false, 0u, false);
-            }
+        for (int q = slot; q < P.n_owned; q += grid) {
+            const int p = P.own_lo + q;
+            parent_sum(P, p, it);
+            crown_backward(P, p, 1, mpar, K.SP, false, 0u, false);
         }
         // Pass 2 -- everything else of the crown needs every S row, this rank's and the peers': the CTAs that own tiles wait for
         // the counter parent_sum bumps on every rank; nobody else waits, and the crown overlaps the rest of the chains' sweep
@@ -1817,7 +1826,9 @@ __device__ __noinline__ void iter_backward(const PArgs &P, KState &K, int it) {
         dstamp(P, 20);
         bool do_wait = true;
 #pragma unroll 1
-        for (int tl = slot; tl < C.n_tiles2; tl += grid) {
+        for (int q = slot; q < C.n_items; q += grid) {
+            if (q < P.n_owned) continue;
+            const int tl = q - P.n_owned;
             crown_backward(P, tl * C.tile_w, min(C.tile_w, C.n2 - tl * C.tile_w), mpar, K.SP, do_wait, wait_s, true);
             do_wait = false;   // awaited once
         }
@@ -1990,6 +2001,8 @@ __global__ void __launch_bounds__(kPT, 1) k_apg_persistent(const __grid_constant
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize of k_apg_persistent: one value per device for the whole process
+static rn_status raise_persist_smem_limit(Handle *h, int bytes);
 struct SweepLayout {
     int oG, oOm, oL, oX1, oY, oV, oScr2, oStg, oXb, end;   // shared-memory float offsets
     int pG, pOm, pL, pB, pLt, pack_floats, sB, sLt;   // float offsets inside the pack (G | OmegaBar | L | B | L'), sizes of B and L'
@@ -2216,7 +2229,7 @@ rn_status persistent_prepare(Handle *h) {
     RN_CUDA(h, cudaStreamSynchronize(h->stream));
     size_t smem = persist_smem_bytes(h);
     if ((size_t)shared_layout(h).end * 4 + 128 <= 227 * 1024) smem = std::max(smem, (size_t)shared_layout(h).end * 4 + 128);
-    RN_CUDA(h, cudaFuncSetAttribute(k_apg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // for the occupancy query; set again at every launch
+    RN_CHECK(raise_persist_smem_limit(h, (int)smem));   // for the occupancy query and every launch of this handle
     int per_sm = 0;
     RN_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_apg_persistent, kPT, smem));
     if (per_sm < 1) return fail(h, RN_ERR_INVALID, "persistent kernel does not fit on an SM (%zu B shared memory)", smem);
@@ -2235,9 +2248,14 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     PArgs P{};
     P.parent = h->t.parent; P.child_first = h->t.child_first; P.child_count = h->t.child_count; P.omega_idx = h->t.omega_idx;
     P.cum = h->cum_dev; P.stages = h->t.stages; P.crown_rng = h->crown_rng; P.pos = h->pos_dev; P.crown_path = h->crown_path;
+    // the reference's branching stages (:699-719) are those of the WHOLE tree: a rank of a partition holds K of K_glob chains
+    // below the replicated crown, and a count of its own stages would call the chain heads' stage non-branching as soon as
+    // K < nodes of the last crown stage (eight GPUs on C3: 60 < 80) -- same mathematics, different order of the additions
     P.branch_mask = 0;
-    for (int st_ = 1; st_ < d.N && st_ < 32; st_++)
-        if (h->h_cum[st_ + 1] - h->h_cum[st_] > h->h_cum[st_] - h->h_cum[st_ - 1]) P.branch_mask |= 1u << st_;
+    for (int st_ = 1; st_ < d.N && st_ < 32; st_++) {
+        auto n_at = [&](int s) { return (h->dist_world > 1 && s >= h->chain_stage) ? h->dist_K_glob : h->h_cum[s + 1] - h->h_cum[s]; };
+        if (n_at(st_) > n_at(st_ - 1)) P.branch_mask |= 1u << st_;
+    }
     P.N = d.N; P.cs = h->chain_stage; P.K = d.K; P.nodes = d.nodes; P.n_crown = h->h_cum[h->chain_stage];
     P.n_mats = h->factor_mode == RN_FACTORS_FULL ? 4 : 2;
     P.df_mode = h->factor_mode != RN_FACTORS_FULL ? 1 : 0;           // v = -1/2 Omega r
@@ -2330,11 +2348,25 @@ rn_status persistent_launch(Handle *h, cudaStream_t st, int iters) {
     RN_CUDA(h, cudaMemsetAsync(h->dist_part, 0, 2 * sizeof(double) * h->persist_grid, st));
     if (h->pack_dirty) RN_CHECK(refresh_pack(h, st));
     // the attribute belongs to the function and the device, not to the handle: a handle of a smaller problem prepared later
-    // would otherwise lower the limit under this one (launch_stream / launch_sweeps do the same for their kernels)
-    RN_CUDA(h, cudaFuncSetAttribute(k_apg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem_bytes(h)));
+    // must not lower the limit under this one.  A running maximum per device, raised only when a launch needs more: setting the
+    // attribute at every launch serialised the lanes of a closed-loop study (four handles solving side by side on one GPU ran at
+    // the pace of one)
+    RN_CHECK(raise_persist_smem_limit(h, (int)persist_smem_bytes(h)));
     void *args[] = {&P};
     RN_CUDA(h, cudaLaunchCooperativeKernel((const void *)k_apg_persistent, dim3(h->persist_grid), dim3(kPT), args,
                                            persist_smem_bytes(h), st));
+    return RN_OK;
+}
+
+static rn_status raise_persist_smem_limit(Handle *h, int bytes) {
+    static std::mutex mu;
+    static int limit[64] = {0};
+    std::lock_guard<std::mutex> lock(mu);
+    const int dev = h->device >= 0 && h->device < 64 ? h->device : 0;
+    if (bytes > limit[dev]) {
+        RN_CUDA(h, cudaFuncSetAttribute(k_apg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        limit[dev] = bytes;
+    }
     return RN_OK;
 }
 

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--iters", default="1,10,100")
     ap.add_argument("--factors", default="full")
     ap.add_argument("--bench", type=int, default=0, help="also time this many solves of 100 iterations")
+    ap.add_argument("--diag", action="store_true", help="where do the iterates differ: per variable, stage and owning rank; crown copies rank by rank")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -50,8 +51,30 @@ def main():
         dist.all_gather_object(parts, ds.solver.pinf_parts(iters))
         got = {name: ds.gather(name, dim) for name, dim in (("VEC_U", n.nu), ("VEC_X", n.nx), ("VEC_UPDATE_XI", 2 * n.nx),
                                                             ("VEC_UPDATE_PSI", n.nu), ("VEC_DUAL_XI", 2 * n.nx))}
+        if args.diag:
+            m = ds.meta
+            for name, dim in (("VEC_X", n.nx), ("VEC_U", n.nu), ("VEC_V", prob.config.nv), ("VEC_UPDATE_XI", 2 * n.nx), ("VEC_DUAL_XI", 2 * n.nx)):
+                loc = ds.solver.read(name).reshape(-1, dim)[: m.n_crown]
+                allc = [None] * world
+                dist.all_gather_object(allc, loc)
+                if rank == 0:
+                    for r in range(1, world):
+                        bad = np.flatnonzero((allc[r] != allc[0]).any(axis=1))
+                        if bad.size:
+                            print(f"  DIAG it={iters} {name}: crown copy of rank {r} differs from rank 0 at {bad.size} crown nodes, first {bad[:8]}, "
+                                  f"max abs {float(np.abs(allc[r] - allc[0]).max()):.3e}", flush=True)
         if rank == 0:
             ru0, rinf = ref.apg_solve(iters, want_infs=True)
+            if args.diag:
+                stages = np.asarray(prob.tree.stages).reshape(-1)
+                for name, a in got.items():
+                    b = ref.read(name).reshape(a.shape)
+                    bad = np.flatnonzero((a != b).any(axis=1))
+                    if bad.size:
+                        st, cnt = np.unique(stages[bad], return_counts=True)
+                        rel = np.abs(a[bad].astype(np.float64) - b[bad]).max(axis=1) / np.maximum(np.abs(b[bad]).max(axis=1), 1e-30)
+                        print(f"  DIAG it={iters} {name}: {bad.size} of {a.shape[0]} nodes differ from the 1-GPU solve; by stage {dict(zip(st.tolist(), cnt.tolist()))}; "
+                              f"first nodes {bad[:10].tolist()}; worst row-relative diff {float(rel.max()):.3e} at node {int(bad[np.argmax(rel)])}", flush=True)
             worst = 0.0
             for name, a in got.items():
                 b = ref.read(name).reshape(a.shape)
