@@ -1759,12 +1759,9 @@ __device__ __forceinline__ CrownDeal crown_deal(const PArgs &P) {
     C.n2 = P.n_crown - P.n_owned;
     const int grid = (int)gridDim.x;
     C.tile_w = min(kTP / 2, max(1, (C.n2 + grid - 1) / grid));
-    // CTAs without a chain that the first pass leaves free: if tiles of up to four nodes fit them, no second-pass tile queues
-    // behind a chain's whole backward sweep (a tile of w nodes costs about 5 + 2 w us, the chain 13 us)
-    const int free2 = grid - min(P.K, grid) - P.n_owned;
-    if (free2 > 0)
-        for (int w = 1; w <= 4; w++)
-            if ((C.n2 + w - 1) / w <= free2) { C.tile_w = w; break; }
+    // (wider tiles that would keep the second pass off the CTAs with chains were measured slower at 8 GPUs on C3 -- the nodes of
+    // a tile are summed one after the other: 8 967 against 9 462 iter/s with two nodes per tile -- so the overflow queues
+    // behind a chain's backward sweep, which ends about when the S rows arrive anyway)
     C.n_tiles2 = (C.n2 + C.tile_w - 1) / C.tile_w;
     C.n_items = P.n_owned + C.n_tiles2;
     return C;

@@ -48,3 +48,9 @@ if [[ " $PARTS " == *" ncu "* ]]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_bench_C2.csv" python bench.py --steps 2 --warmup 3 --iters 20 --no-cpu-baseline --no-alt --by-config "" --closed-loop-instances 0 > "$OUT/ncu_launch.log" 2>&1; echo "ncu launches rc=$?" | tee -a "$OUT/summary.txt"
   ncu --set full --clock-control none --import-source on -k regex:k_apg_persistent -c 1 -o "$OUT/ncu_full_k_apg_persistent_C2" -f python bench.py --steps 1 --warmup 3 --iters 10 --no-cpu-baseline --no-alt --by-config "" --closed-loop-instances 0 > "$OUT/ncu_full.log" 2>&1; echo "ncu full rc=$?" | tee -a "$OUT/summary.txt"
 fi
+if [[ " $PARTS " == *" c4 "* ]]; then
+  for f in shared full; do
+    timeout 300 python tools/c4_study.py --instances ${C4_INSTANCES:-32} --steps ${C4_STEPS:-4} --factors $f > "$OUT/c4_study_${f}_1gpu.json" 2> "$OUT/c4_study_${f}_1gpu.err"; echo "c4 study $f rc=$?" | tee -a "$OUT/summary.txt"
+    grep '"study"' "$OUT/c4_study_${f}_1gpu.json" | cut -c1-600
+  done
+fi
